@@ -1,0 +1,137 @@
+"""ctypes binding of librank_b200.so (include/rank_b200.h).
+
+There is exactly one compute path: the CUDA library.  If it cannot be loaded, every op raises —
+there is no eager/CPU fallback.  Torch is used for device memory and streams only; tensors
+cross the boundary as raw device pointers.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from pathlib import Path
+
+import torch
+
+PKG_DIR = Path(__file__).resolve().parent
+LIB_PATH = PKG_DIR / "librank_b200.so"
+
+RK_MAX_FIELDS = 24
+RK_MAX_TABLES = 32
+RK_MAX_LAYERS = 8
+ABI_VERSION = 1
+
+
+class RkField(C.Structure):
+    _fields_ = [("weight", C.c_void_p), ("idx", C.c_void_p), ("rows", C.c_int64),
+                ("dim", C.c_int32), ("out_off", C.c_int32)]
+
+
+class RkGradTable(C.Structure):
+    _fields_ = [("g", C.c_void_p), ("ld", C.c_int64), ("dw", C.c_void_p),
+                ("dim", C.c_int32), ("field", C.c_int32)]
+
+
+_P = C.c_void_p
+_I = C.c_int
+_L = C.c_int64
+_Z = C.c_size_t
+
+# name -> (restype, argtypes); mirrors include/rank_b200.h one to one
+PROTOTYPES = {
+    "rk_version": (_I, []),
+    "rk_last_error": (C.c_char_p, []),
+    "rk_device_sm_count": (_I, []),
+    "rk_plan_workspace_bytes": (_Z, [_L]),
+    "rk_plan_build": (_I, [_P, _P, _P, _I, _P, _P, _P, _Z, _P, _P]),
+    "rk_reduce_workspace_bytes": (_Z, [_P, _I, _P, _I]),
+    "rk_embgrad_segment_reduce": (_I, [_P, _P, _P, _P, _I, _P, _I, _P, _Z, _P]),
+    "rk_gather_concat_fwd": (_I, [_P, _I, _P, _I, _L, _P, _I, _P, _P]),
+    "rk_deepfm_fwd": (_I, [_P, _P, _I, _L, _P, _P, _P, _P, _P]),
+    "rk_deepfm_bwd": (_I, [_P, _P, _P, _I, _I, _L, _P, _P]),
+    "rk_crossnet_fwd": (_I, [_P, _I, _P, _I, _P, _P, _I, _L, _P, _P, _P, _P]),
+    "rk_crossnet_bwd": (_I, [_P, _P, _P, _I, _I, _L, _P, _P, _P, _P]),
+    "rk_cross_layer_fwd": (_I, [_P, _P, _P, _P, _I, _L, _P, _P]),
+    "rk_cross_layer_bwd": (_I, [_P, _P, _P, _I, _L, _P, _P, _P, _P]),
+}
+
+_lib = None
+
+
+class RankB200Error(RuntimeError):
+    """A librank_b200 entry point returned non-zero."""
+
+
+def library_path() -> Path:
+    return LIB_PATH
+
+
+def load() -> C.CDLL:
+    """Load librank_b200.so (once).  Raises if it is absent or has the wrong ABI."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not LIB_PATH.exists():
+        raise RankB200Error(
+            f"{LIB_PATH} is missing: build it with `python -c 'import __graft_entry__ as g; "
+            "g.build()'` (needs nvcc, sm_100a).  There is no CPU fallback.")
+    lib = C.CDLL(str(LIB_PATH))
+    for name, (res, args) in PROTOTYPES.items():
+        fn = getattr(lib, name)  # AttributeError if the symbol is not exported
+        fn.restype = res
+        fn.argtypes = args
+    if lib.rk_version() != ABI_VERSION:
+        raise RankB200Error(f"librank_b200 ABI {lib.rk_version()} != expected {ABI_VERSION}")
+    _lib = lib
+    return lib
+
+
+def check(rc: int, what: str) -> None:
+    if rc != 0:
+        msg = load().rk_last_error().decode("utf-8", "replace")
+        raise RankB200Error(f"{what} failed (rc={rc}): {msg}")
+
+
+def stream_ptr() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def ptr(t: torch.Tensor | None) -> int | None:
+    return None if t is None else t.data_ptr()
+
+
+def require_cuda(t: torch.Tensor, name: str, dtype: torch.dtype) -> torch.Tensor:
+    """The boundary takes contiguous CUDA tensors of one dtype; anything else is an error."""
+    if not isinstance(t, torch.Tensor):
+        raise TypeError(f"{name}: expected a torch.Tensor, got {type(t).__name__}")
+    if not t.is_cuda:
+        raise RankB200Error(f"{name}: tensor is on {t.device}; the hot path runs on CUDA only "
+                            "(no CPU fallback)")
+    if t.dtype != dtype:
+        raise TypeError(f"{name}: expected {dtype}, got {t.dtype}")
+    return t if t.is_contiguous() else t.contiguous()
+
+
+_err_flags: dict[int, torch.Tensor] = {}
+
+
+def err_flag(device: torch.device) -> torch.Tensor:
+    """Per-device sticky int32 flag the kernels raise when an index is out of range."""
+    key = device.index if device.index is not None else torch.cuda.current_device()
+    flag = _err_flags.get(key)
+    if flag is None:
+        flag = torch.zeros(1, dtype=torch.int32, device=device)
+        _err_flags[key] = flag
+    return flag
+
+
+def check_index_errors(device=None) -> None:
+    """Synchronising check: raise IndexError if any kernel saw an out-of-range index since the
+    last check (the reference raises IndexError from nn.Embedding on CPU)."""
+    dev = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+    flag = err_flag(dev)
+    if int(flag.item()) != 0:
+        flag.zero_()
+        raise IndexError("index out of range in self")
+
+
+CHECK_EVERY_CALL = os.environ.get("RANK_B200_CHECK_INDICES", "0") == "1"

@@ -1,0 +1,70 @@
+// abi.cu — ABI bookkeeping: version, thread-local error text, field packing.
+#include <stdarg.h>
+#include <string.h>
+#include "common.cuh"
+
+namespace rk {
+
+static thread_local char g_err[512] = "";
+
+void set_error(const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+
+int sm_count() {
+    static int cached = 0;
+    if (cached) return cached;
+    int dev = 0, n = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) return 148;
+    if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0)
+        return 148;
+    cached = n;
+    return n;
+}
+
+int pick_vec(const rk_field_t* f, int F, int n_dense, int extra) {
+    int g = 4;
+    auto fold = [&](int x) {
+        while (g > 1 && (x % g) != 0) g >>= 1;
+    };
+    fold(n_dense);
+    fold(extra);
+    for (int i = 0; i < F; ++i) {
+        fold(f[i].dim);
+        fold(f[i].out_off);
+    }
+    return g;
+}
+
+int pack_fields(const rk_field_t* f, int F, FieldSet* out) {
+    RK_CHECK_ARG(F >= 0 && F <= RK_MAX_FIELDS, "F=%d outside [0,%d]", F, RK_MAX_FIELDS);
+    RK_CHECK_ARG(F == 0 || f != nullptr, "fields is NULL");
+    memset(out, 0, sizeof(*out));
+    out->F = F;
+    for (int i = 0; i < F; ++i) {
+        RK_CHECK_ARG(f[i].weight && f[i].idx, "field %d: NULL weight or idx", i);
+        RK_CHECK_ARG(f[i].rows > 0 && f[i].dim > 0, "field %d: rows=%lld dim=%d", i,
+                     (long long)f[i].rows, f[i].dim);
+        out->weight[i] = f[i].weight;
+        out->idx[i]    = f[i].idx;
+        out->rows[i]   = f[i].rows;
+        out->dim[i]    = f[i].dim;
+        out->off[i]    = f[i].out_off;
+    }
+    return 0;
+}
+
+}  // namespace rk
+
+extern "C" {
+
+int rk_version(void) { return RK_ABI_VERSION; }
+
+const char* rk_last_error(void) { return rk::g_err; }
+
+int rk_device_sm_count(void) { return rk::sm_count(); }
+
+}  // extern "C"

@@ -1,0 +1,235 @@
+// segment_reduce.cu — rk_embgrad_segment_reduce: dense [rows, dim] embedding gradients from
+// per-occurrence gradient rows, using the (field,row)-sorted order made by rk_plan_build.
+// Replaces ATen embedding_dense_backward (autograd of nn.Embedding, e.g. DCN/dcn.py:166 via
+// loss.backward()).  No atomics: every row's occurrences are summed in sorted (= occurrence)
+// order; rows hotter than one 16-occurrence chunk are finished by a second, equally
+// deterministic pass that adds the chunk partials left to right.
+//
+// HBM/L2-bound: each gradient row is read once (gathered through perm), each touched table row
+// written once.  One table with `dim` columns uses ceil(dim/vec) lanes per chunk, every lane
+// owning `vec` columns, so no cross-lane traffic is needed.
+#include <string.h>
+#include "common.cuh"
+
+namespace rk {
+
+constexpr int kChunk = 16;
+
+struct ReduceJob {
+    const float* g;
+    float*       dw;
+    float*       lead;        // [n_chunks, dim] partial of a segment begun in an earlier chunk
+    int64_t      ld;
+    int64_t      seg_start;   // first sorted position of the field
+    int64_t      n;           // occurrences of the field
+    int64_t      thread_start;
+    uint32_t     key_base;
+    int32_t      dim;
+    int32_t      lanes;
+    int32_t      vec;
+};
+struct ReduceParams {
+    ReduceJob job[RK_MAX_TABLES];
+    int64_t   total_threads;
+    int32_t   n_tables;
+};
+
+template <int V>
+__device__ __forceinline__ void reduce_chunk(const ReduceJob& jb, const uint32_t* __restrict__ keys,
+                                             const uint32_t* __restrict__ perm, int64_t c,
+                                             int lane) {
+    const int     col  = lane * V;
+    const int64_t pos0 = jb.seg_start + c * kChunk;
+    const int     cnt  = (int)((jb.n - c * kChunk) < kChunk ? (jb.n - c * kChunk) : kChunk);
+    const uint32_t* K  = keys + pos0;
+    const uint32_t* P  = perm + pos0;
+    uint32_t cur  = K[0];
+    bool     lead = (c > 0) && (keys[pos0 - 1] == cur);
+    Vec<V>   acc;
+    vec_zero(acc);
+    float* lead_out = jb.lead + c * (int64_t)jb.dim + col;
+
+#pragma unroll 1
+    for (int j0 = 0; j0 < cnt; j0 += 8) {
+        uint32_t kk[8];
+        Vec<V>   vv[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            const int j = j0 + u < cnt ? j0 + u : cnt - 1;
+            kk[u] = K[j];
+            vv[u].load_plain(jb.g + (int64_t)P[j] * jb.ld + col);
+        }
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            if (j0 + u < cnt) {
+                if (kk[u] != cur) {
+                    if (lead) acc.store(lead_out);
+                    else      acc.store(jb.dw + (int64_t)(cur - jb.key_base) * jb.dim + col);
+                    lead = false;
+                    vec_zero(acc);
+                    cur = kk[u];
+                }
+#pragma unroll
+                for (int e = 0; e < V; ++e) acc.v[e] += vv[u].v[e];
+            }
+        }
+    }
+    if (lead) acc.store(lead_out);
+    else      acc.store(jb.dw + (int64_t)(cur - jb.key_base) * jb.dim + col);
+}
+
+__device__ __forceinline__ int find_job(const ReduceParams& p, int64_t t) {
+    int j = 0;
+#pragma unroll 1
+    while (j + 1 < p.n_tables && t >= p.job[j + 1].thread_start) ++j;
+    return j;
+}
+
+__global__ void __launch_bounds__(256)
+segment_chunk_kernel(const __grid_constant__ ReduceParams p, const uint32_t* __restrict__ keys,
+                     const uint32_t* __restrict__ perm) {
+    const int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (t >= p.total_threads) return;
+    const ReduceJob& jb = p.job[find_job(p, t)];
+    const int64_t local = t - jb.thread_start;
+    const int64_t c     = local / jb.lanes;
+    const int     lane  = (int)(local - c * jb.lanes);
+    if (c * kChunk >= jb.n) return;
+    if (jb.vec == 4)      reduce_chunk<4>(jb, keys, perm, c, lane);
+    else if (jb.vec == 2) reduce_chunk<2>(jb, keys, perm, c, lane);
+    else                  reduce_chunk<1>(jb, keys, perm, c, lane);
+}
+
+// Second pass: the chunk that holds the head of a row spilling into later chunks adds their
+// lead partials, left to right.
+template <int V>
+__device__ __forceinline__ void combine_chunk(const ReduceJob& jb, const uint32_t* __restrict__ keys,
+                                              int64_t c, int lane) {
+    const int64_t n_chunks = (jb.n + kChunk - 1) / kChunk;
+    const int64_t pos0     = jb.seg_start + c * kChunk;
+    const int     cnt      = (int)((jb.n - c * kChunk) < kChunk ? (jb.n - c * kChunk) : kChunk);
+    const int64_t last     = pos0 + cnt - 1;
+    if (c + 1 >= n_chunks) return;
+    const uint32_t k = keys[last];
+    if (keys[last + 1] != k) return;  // last row of the chunk ends here
+    const bool head_here = (keys[pos0] != k) || c == 0 || keys[pos0 - 1] != k;
+    if (!head_here) return;
+    const int col = lane * V;
+    float*    out = jb.dw + (int64_t)(k - jb.key_base) * jb.dim + col;
+    Vec<V>    acc;
+    acc.load_plain(out);
+#pragma unroll 1
+    for (int64_t cc = c + 1; cc < n_chunks; ++cc) {
+        const int64_t p0 = jb.seg_start + cc * kChunk;
+        if (keys[p0] != k) break;
+        Vec<V> part;
+        part.load_plain(jb.lead + cc * (int64_t)jb.dim + col);
+#pragma unroll
+        for (int e = 0; e < V; ++e) acc.v[e] += part.v[e];
+        const int64_t rem = jb.n - cc * kChunk;
+        const int64_t l2  = p0 + (rem < kChunk ? rem : kChunk) - 1;
+        if (keys[l2] != k) break;
+    }
+    acc.store(out);
+}
+
+__global__ void __launch_bounds__(256)
+segment_combine_kernel(const __grid_constant__ ReduceParams p, const uint32_t* __restrict__ keys) {
+    const int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (t >= p.total_threads) return;
+    const ReduceJob& jb = p.job[find_job(p, t)];
+    const int64_t local = t - jb.thread_start;
+    const int64_t c     = local / jb.lanes;
+    const int     lane  = (int)(local - c * jb.lanes);
+    if (c * kChunk >= jb.n) return;
+    if (jb.vec == 4)      combine_chunk<4>(jb, keys, c, lane);
+    else if (jb.vec == 2) combine_chunk<2>(jb, keys, c, lane);
+    else                  combine_chunk<1>(jb, keys, c, lane);
+}
+
+static int vec_of(int dim) { return dim % 4 == 0 ? 4 : (dim % 2 == 0 ? 2 : 1); }
+
+}  // namespace rk
+
+extern "C" {
+
+size_t rk_reduce_workspace_bytes(const int64_t* n, int F, const rk_grad_table_t* tables,
+                                 int n_tables) {
+    size_t bytes = 0;
+    for (int t = 0; t < n_tables; ++t) {
+        const int f = tables[t].field;
+        if (f < 0 || f >= F) continue;
+        const size_t chunks = (size_t)rk::ceil_div(n[f], rk::kChunk);
+        bytes += ((chunks * (size_t)tables[t].dim * 4) + 255) & ~(size_t)255;
+    }
+    return bytes ? bytes : 256;
+}
+
+int rk_embgrad_segment_reduce(const uint32_t* sorted_keys, const uint32_t* perm,
+                              const int64_t* n, const int64_t* rows, int F,
+                              const rk_grad_table_t* tables, int n_tables, void* ws,
+                              size_t ws_bytes, rk_stream_t stream_) {
+    using namespace rk;
+    cudaStream_t s = (cudaStream_t)stream_;
+    RK_CHECK_ARG(F >= 1 && F <= RK_MAX_FIELDS, "segment_reduce: F=%d", F);
+    RK_CHECK_ARG(n_tables >= 1 && n_tables <= RK_MAX_TABLES, "segment_reduce: n_tables=%d",
+                 n_tables);
+    RK_CHECK_ARG(n && rows && tables, "segment_reduce: NULL host array");
+    RK_CHECK_ARG(ws_bytes >= rk_reduce_workspace_bytes(n, F, tables, n_tables),
+                 "segment_reduce: workspace too small");
+    int64_t  start[RK_MAX_FIELDS + 1];
+    uint32_t base[RK_MAX_FIELDS];
+    int64_t  tot = 0, space = 0;
+    for (int f = 0; f < F; ++f) {
+        start[f] = tot;
+        base[f]  = (uint32_t)space;
+        tot += n[f];
+        space += rows[f];
+    }
+    if (tot == 0) return 0;
+    RK_CHECK_ARG(sorted_keys && perm && ws, "segment_reduce: NULL device pointer");
+
+    ReduceParams p;
+    memset(&p, 0, sizeof(p));
+    p.n_tables = 0;
+    int64_t threads = 0;
+    size_t  ws_off  = 0;
+    for (int t = 0; t < n_tables; ++t) {
+        const rk_grad_table_t& tb = tables[t];
+        RK_CHECK_ARG(tb.field >= 0 && tb.field < F, "segment_reduce: table %d field %d", t,
+                     tb.field);
+        RK_CHECK_ARG(tb.dim > 0 && tb.g && tb.dw, "segment_reduce: table %d dim/pointers", t);
+        const int f = tb.field;
+        if (n[f] == 0) continue;
+        int v = vec_of(tb.dim);
+        // vector access needs matching alignment of the gradient rows and of the table
+        while (v > 1 && ((tb.ld % v) != 0 || ((uintptr_t)tb.g % (4 * v)) != 0 ||
+                         ((uintptr_t)tb.dw % (4 * v)) != 0))
+            v >>= 1;
+        ReduceJob& jb   = p.job[p.n_tables++];
+        jb.g            = tb.g;
+        jb.dw           = tb.dw;
+        jb.ld           = tb.ld;
+        jb.dim          = tb.dim;
+        jb.vec          = v;
+        jb.lanes        = tb.dim / v;
+        jb.seg_start    = start[f];
+        jb.n            = n[f];
+        jb.key_base     = base[f];
+        jb.lead         = (float*)((char*)ws + ws_off);
+        jb.thread_start = threads;
+        const int64_t chunks = ceil_div(n[f], kChunk);
+        ws_off += ((size_t)chunks * tb.dim * 4 + 255) & ~(size_t)255;
+        threads += ceil_div(chunks * jb.lanes, 32) * 32;  // keep warps inside one table
+    }
+    p.total_threads = threads;
+    if (threads == 0) return 0;
+    const int grid = (int)ceil_div(threads, 256);
+    segment_chunk_kernel<<<grid, 256, 0, s>>>(p, sorted_keys, perm);
+    RK_LAUNCH_CHECK();
+    segment_combine_kernel<<<grid, 256, 0, s>>>(p, sorted_keys);
+    RK_LAUNCH_CHECK();
+    return 0;
+}
+
+}  // extern "C"

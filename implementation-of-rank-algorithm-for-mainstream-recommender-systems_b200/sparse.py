@@ -1,0 +1,133 @@
+"""Host side of the sparse-field machinery shared by all six models.
+
+* `field_array`     packs (table, index column, offset) triples into the C `rk_field_t[]`.
+* `OccurrencePlan`  = rk_plan_build: the stable (field,row) order of every index occurrence of
+                      the batch, computed once in forward (it depends on the indices only).
+* `reduce_to_dense` = rk_embgrad_segment_reduce: per-occurrence gradient rows -> the dense
+                      `[V, D]` gradients `optim.Adam` expects (the reference's nn.Embedding is
+                      sparse=False, e.g. DeepFM/deepfm.py:90-98), deterministic, no atomics.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass
+
+import torch
+
+from . import _lib
+
+
+def field_array(weights, indices, offsets):
+    """rk_field_t[F] for tables `weights[f]` read through `indices[f]`, landing at column
+    `offsets[f]` of the concatenated row.  Returns (ctypes array, keep-alive list)."""
+    F = len(weights)
+    if F > _lib.RK_MAX_FIELDS:
+        raise ValueError(f"{F} sparse fields exceed RK_MAX_FIELDS={_lib.RK_MAX_FIELDS}")
+    arr = (_lib.RkField * max(F, 1))()
+    keep = []
+    for f in range(F):
+        w = _lib.require_cuda(weights[f], f"table[{f}]", torch.float32)
+        i = _lib.require_cuda(indices[f], f"index[{f}]", torch.int64)
+        if w.dim() != 2:
+            raise ValueError(f"table[{f}] must be [rows, dim], got {tuple(w.shape)}")
+        keep += [w, i]
+        arr[f].weight = w.data_ptr()
+        arr[f].idx = i.data_ptr()
+        arr[f].rows = w.shape[0]
+        arr[f].dim = w.shape[1]
+        arr[f].out_off = int(offsets[f])
+    return arr, keep
+
+
+def _i64_array(values):
+    return (C.c_int64 * max(len(values), 1))(*values)
+
+
+@dataclass
+class GradSource:
+    """Per-occurrence gradient rows of one table: row o lives at base[o*ld : o*ld+dim]."""
+    base: torch.Tensor   # any fp32 CUDA tensor; `offset` is in floats from its data_ptr
+    offset: int
+    ld: int
+    dim: int
+    rows: int
+    field: int           # which plan field's occurrences feed this table
+
+
+class OccurrencePlan:
+    """Sorted order of all index occurrences of a batch (one entry per field)."""
+
+    def __init__(self, indices: list[torch.Tensor], rows: list[int]):
+        lib = _lib.load()
+        self.F = len(indices)
+        if not 1 <= self.F <= _lib.RK_MAX_FIELDS:
+            raise ValueError(f"plan over {self.F} fields (max {_lib.RK_MAX_FIELDS})")
+        self.indices = [_lib.require_cuda(i, f"index[{k}]", torch.int64)
+                        for k, i in enumerate(indices)]
+        self.n = [int(i.numel()) for i in self.indices]
+        self.rows = [int(r) for r in rows]
+        dev = self.indices[0].device
+        total = sum(self.n)
+        self.total = total
+        self.sorted_keys = torch.empty(max(total, 1), dtype=torch.int32, device=dev)
+        self.perm = torch.empty(max(total, 1), dtype=torch.int32, device=dev)
+        ws_bytes = lib.rk_plan_workspace_bytes(total)
+        ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+        idx_ptrs = (C.c_void_p * self.F)(*[i.data_ptr() for i in self.indices])
+        rc = lib.rk_plan_build(idx_ptrs, _i64_array(self.n), _i64_array(self.rows), self.F,
+                               self.sorted_keys.data_ptr(), self.perm.data_ptr(),
+                               ws.data_ptr(), ws_bytes, _lib.err_flag(dev).data_ptr(),
+                               _lib.stream_ptr())
+        _lib.check(rc, "rk_plan_build")
+
+    def reduce_to_dense(self, sources: list[GradSource]) -> list[torch.Tensor]:
+        """One dense `[rows, dim]` gradient per source, summed over duplicate indices."""
+        lib = _lib.load()
+        T = len(sources)
+        if not 1 <= T <= _lib.RK_MAX_TABLES:
+            raise ValueError(f"{T} gradient tables (max {_lib.RK_MAX_TABLES})")
+        dev = self.sorted_keys.device
+        # one zero-filled slab for all dense gradients (a single memset), carved per table
+        sizes = [s.rows * s.dim for s in sources]
+        starts, acc = [], 0
+        for sz in sizes:
+            starts.append(acc)
+            acc += (sz + 3) // 4 * 4          # keep every table 16-byte aligned
+        slab = torch.zeros(acc, dtype=torch.float32, device=dev)
+        grads = [slab[st:st + sz].view(s.rows, s.dim) for st, sz, s in zip(starts, sizes, sources)]
+        tabs = (_lib.RkGradTable * T)()
+        for t, (s, g) in enumerate(zip(sources, grads)):
+            if s.rows != self.rows[s.field]:
+                raise ValueError("gradient table height does not match its plan field")
+            tabs[t].g = s.base.data_ptr() + 4 * s.offset
+            tabs[t].ld = s.ld
+            tabs[t].dw = g.data_ptr()
+            tabs[t].dim = s.dim
+            tabs[t].field = s.field
+        n_arr = _i64_array(self.n)
+        ws_bytes = lib.rk_reduce_workspace_bytes(n_arr, self.F, tabs, T)
+        ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+        rc = lib.rk_embgrad_segment_reduce(self.sorted_keys.data_ptr(), self.perm.data_ptr(),
+                                           n_arr, _i64_array(self.rows), self.F, tabs, T,
+                                           ws.data_ptr(), ws_bytes, _lib.stream_ptr())
+        _lib.check(rc, "rk_embgrad_segment_reduce")
+        return grads
+
+
+def gather_concat(weights, indices, offsets, dense=None, width=None) -> torch.Tensor:
+    """[dense | W_0[idx_0] | W_1[idx_1] | ...] in one launch (no autograd)."""
+    lib = _lib.load()
+    arr, keep = field_array(weights, indices, offsets)
+    B = int(indices[0].shape[0]) if indices else int(dense.shape[0])
+    n_dense = 0
+    if dense is not None:
+        dense = _lib.require_cuda(dense, "dense", torch.float32)
+        n_dense = int(dense.shape[1])
+    d = max([n_dense] + [int(o) + int(w.shape[1]) for w, o in zip(weights, offsets)])
+    width = d if width is None else width
+    dev = keep[0].device if keep else dense.device
+    out = torch.empty(B, width, dtype=torch.float32, device=dev)
+    rc = lib.rk_gather_concat_fwd(arr, len(weights), _lib.ptr(dense), n_dense, B, out.data_ptr(),
+                                  width, _lib.err_flag(dev).data_ptr(), _lib.stream_ptr())
+    _lib.check(rc, "rk_gather_concat_fwd")
+    return out

@@ -1,0 +1,119 @@
+/*
+ * rank_b200.h — C ABI of librank_b200.so: the B200 (sm_100a) CTR hot path.
+ *
+ * The reference (reallinshengxiang/Implementation-of-Rank-Algorithm-for-Mainstream-
+ * Recommender-Systems) has no FFI of its own: its hot path is the body of each
+ * nn.Module.forward plus the autograd backward of it.  Every entry point below replaces one
+ * such body (cited as file:line relative to the reference root, algorithm/...).
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer owned by the caller unless the comment says "host";
+ *   - tables are fp32 row-major [rows, dim]; indices are int64 (torch.long), lengths int64;
+ *   - all work is enqueued on `stream`; the library never synchronises, allocates or frees
+ *     device memory, so a whole training step is CUDA-graph capturable;
+ *   - return value: 0 = ok, >0 = cudaError_t of the failing runtime call, <0 = argument
+ *     error; rk_last_error() gives a thread-local message;
+ *   - out-of-range indices are clamped to row 0 and raise bit 0 of *err_flag (the reference
+ *     raises IndexError on CPU / device-asserts on CUDA); err_flag may be NULL.
+ */
+#ifndef RANK_B200_H
+#define RANK_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define RK_ABI_VERSION 1
+#define RK_MAX_FIELDS 24
+#define RK_MAX_TABLES 32
+#define RK_MAX_LAYERS 8
+
+typedef void* rk_stream_t; /* cudaStream_t */
+
+/* One sparse field: a table and the index column that reads it (nn.Embedding + lookup,
+ * e.g. DeepFM/deepfm.py:90-98,123-132; DCN/dcn.py:130-137,163-167). */
+typedef struct rk_field {
+    const float*   weight;  /* [rows, dim] */
+    const int64_t* idx;     /* [n] */
+    int64_t        rows;    /* V */
+    int32_t        dim;     /* D */
+    int32_t        out_off; /* first column of this field in the concatenated row */
+} rk_field_t;
+
+/* One table's share of the embedding-gradient reduction: per-occurrence gradient rows live at
+ * g + occurrence*ld (+0..dim-1); the dense gradient [rows, dim] is written to dw. */
+typedef struct rk_grad_table {
+    const float* g;
+    int64_t      ld;
+    float*       dw;     /* [rows, dim], must be zero-filled by the caller */
+    int32_t      dim;
+    int32_t      field;  /* which field's (sorted) occurrences feed this table */
+} rk_grad_table_t;
+
+int         rk_version(void);
+const char* rk_last_error(void);
+int         rk_device_sm_count(void);
+
+/* ---- sparse embedding-gradient reduction (autograd of nn.Embedding: embedding_dense_backward,
+ *      reached from loss.backward() e.g. DIN/din.py:346) -------------------------------------
+ * rk_plan_build sorts all occurrences of F index columns by (field, row), stably, so that the
+ * later reduction sums each row's gradients in occurrence order: deterministic, no atomics.
+ *   idx[f]  device pointer to n[f] int64 indices, rows[f] = table height      (host arrays)
+ *   sorted_keys[n_total], perm[n_total] : outputs (uint32); perm holds the occurrence number
+ *   inside its field.  ws: scratch of rk_plan_workspace_bytes(n_total). */
+size_t rk_plan_workspace_bytes(int64_t n_total);
+int rk_plan_build(const int64_t* const* idx, const int64_t* n, const int64_t* rows, int F,
+                  uint32_t* sorted_keys, uint32_t* perm, void* ws, size_t ws_bytes,
+                  int32_t* err_flag, rk_stream_t stream);
+/* ws for the reduction: rk_reduce_workspace_bytes(sum over tables of ceil(n/16)*dim floats). */
+size_t rk_reduce_workspace_bytes(const int64_t* n, int F, const rk_grad_table_t* tables,
+                                 int n_tables);
+int rk_embgrad_segment_reduce(const uint32_t* sorted_keys, const uint32_t* perm,
+                              const int64_t* n, const int64_t* rows, int F,
+                              const rk_grad_table_t* tables, int n_tables, void* ws,
+                              size_t ws_bytes, rk_stream_t stream);
+
+/* ---- gather + concat (the per-field lookup loops + torch.cat, DCN/dcn.py:163-169,
+ *      DeepCrossing/deepcrossing.py:148-155) ------------------------------------------------
+ * out[b, 0:n_dense] = dense[b, :]; out[b, off_f:off_f+dim_f] = W_f[idx_f[b], :]. */
+int rk_gather_concat_fwd(const rk_field_t* fields, int F, const float* dense, int n_dense,
+                         int64_t B, float* out, int ld_out, int32_t* err_flag,
+                         rk_stream_t stream);
+
+/* ---- DeepFM FM part (DeepFM/deepfm.py:121-142) ------------------------------------------
+ * second[f] are the F second-order tables (dim D each, idx shared with first[f], dim 1).
+ * deep_input[B, F*D] = cat_f e_f; fm_first[B] = sum_f w_f; fm_second[B] = 0.5*sum_d((sum_f e)^2
+ * - sum_f e^2). */
+int rk_deepfm_fwd(const rk_field_t* second, const float* const* first_weight, int F, int64_t B,
+                  float* deep_input, float* fm_first, float* fm_second, int32_t* err_flag,
+                  rk_stream_t stream);
+/* Per-occurrence second-order gradients g_rows[B, F*D] = g_deep + g_second*(S - e_f);
+ * g_deep or g_second may be NULL (treated as zero). */
+int rk_deepfm_bwd(const float* deep_input, const float* g_deep, const float* g_second, int F,
+                  int D, int64_t B, float* g_rows, rk_stream_t stream);
+
+/* ---- DCN CrossNet (cross_layer + loop, DCN/dcn.py:25-50,169-173) -------------------------
+ * fwd: x0 = [dense | gathered rows] -> concat_all[B,d]; x_{l+1} = x0*(x_l.w_l) + b_l + x_l
+ * -> cross_vec[B,d].  w, b: [L, d]. */
+int rk_crossnet_fwd(const rk_field_t* fields, int F, const float* dense, int n_dense,
+                    const float* w, const float* b, int L, int64_t B, float* concat_all,
+                    float* cross_vec, int32_t* err_flag, rk_stream_t stream);
+/* bwd: g_x0[B,d] = g_concat_all + d(cross_vec)/d(x0) . g_cross_vec (either may be NULL). */
+int rk_crossnet_bwd(const float* concat_all, const float* w, const float* b, int L, int d,
+                    int64_t B, const float* g_concat_all, const float* g_cross_vec,
+                    float* g_x0, rk_stream_t stream);
+
+/* Stand-alone cross_layer(x0, xl, index) (DCN/dcn.py:25-50): out = x0*(xl.w) + b + xl with
+ * w, b of d floats; bwd gives g_x0 = g*(xl.w), g_xl = g + w*(g.x0). */
+int rk_cross_layer_fwd(const float* x0, const float* xl, const float* w, const float* b, int d,
+                       int64_t B, float* out, rk_stream_t stream);
+int rk_cross_layer_bwd(const float* x0, const float* xl, const float* w, int d, int64_t B,
+                       const float* g_out, float* g_x0, float* g_xl, rk_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* RANK_B200_H */
