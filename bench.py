@@ -1,0 +1,378 @@
+#!/usr/bin/env python
+"""bench.py — train samples/s (fwd+bwd) of the CTR hot path + unchanged torch tower on B200.
+
+    python bench.py --gpus N --steps K --warmup W [--workload dcn] [--impl reference]
+
+One "step" = zero_grad, forward, loss, backward of the whole model on one synthetic
+WeChat-shaped batch (per-GPU batch fixed: weak scaling; for N > 1 the dense-gradient allreduce
+is part of the step).  Rank 0 prints ONE JSON line (see DESIGN.md "Measurement").
+  value     : device-timed (CUDA events), inputs already resident in HBM, max over ranks
+  e2e       : same metric through the public module API with pinned HOST inputs, H2D copies and
+              the D2H read of the loss inside the timed region
+  roofline  : algorithmic bytes of the hot path / summed device time of the
+              hot-path ABI calls of a step, against MEASURED_PEAKS.json
+  cpu_baseline / --impl reference : the oracle port of the reference model on the host cores
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.dont_write_bytecode = True
+
+import torch  # noqa: E402
+import torch.nn.functional as F  # noqa: E402
+
+METRIC = "train samples/sec (fwd+bwd)"
+L2_FLUSH_BYTES = 256 << 20
+
+
+# ------------------------------------------------------------------------------- workloads
+class Workload:
+    """One BASELINE.json config: how to build the model (ours or the oracle port), its batch,
+    its loss, and the algorithmic bytes/flops per sample of its hot path."""
+    name = ""
+    batch = 8192
+    bytes_per_sample = 0          # fwd + bwd, algorithmic
+    flops_per_sample = 0
+    bound = "hbm"
+    hot_calls = ()                # ABI entry points that make up the hot path of a step
+
+    def model(self, ns, oracle, vocab_dir):
+        raise NotImplementedError
+
+    def make_batch(self, B, seed):
+        raise NotImplementedError
+
+    def loss(self, model, batch):
+        raise NotImplementedError
+
+
+class DeepFMWorkload(Workload):
+    name, batch, bytes_per_sample, flops_per_sample = "deepfm_d16", 1024, 2896, 600
+    hot_calls = ("rk_deepfm_fwd", "rk_plan_build", "rk_deepfm_bwd", "rk_embgrad_segment_reduce")
+
+    def model(self, ns, oracle, vocab_dir):
+        cls = ns.OracleDeepFM if oracle else ns.DeepFM
+        return cls(vocab_dir, embedding_dim=16, dropout_rate=0.0)
+
+    def make_batch(self, B, seed):
+        from rank_b200 import synthetic
+        return synthetic.deepfm_batch(B, seed)
+
+    def loss(self, model, batch):
+        prob = model(batch["category"])[0]
+        return F.binary_cross_entropy(prob.squeeze(), batch["label"])
+
+
+class DCNWorkload(Workload):
+    name, batch, bytes_per_sample, flops_per_sample = "dcn_l3_dnn512-256-128", 8192, 1704, 2300
+    hot_calls = ("rk_crossnet_fwd", "rk_plan_build", "rk_crossnet_bwd", "rk_embgrad_segment_reduce")
+
+    def model(self, ns, oracle, vocab_dir):
+        cls = ns.OracleDCN if oracle else ns.DCNModel
+        return cls(vocab_dir, hidden_units=[512, 256, 128], num_cross_layer=3)
+
+    def make_batch(self, B, seed):
+        from rank_b200 import synthetic
+        return synthetic.side_batch(B, seed)
+
+    def loss(self, model, batch):
+        logit = model(batch["dense"], batch["category"])[1]
+        return F.binary_cross_entropy_with_logits(logit.squeeze(), batch["label"])
+
+
+WORKLOADS = {"deepfm": DeepFMWorkload, "dcn": DCNWorkload}
+
+
+# ------------------------------------------------------------------------------- helpers
+def peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            p = json.load(f)
+        return dict(hbm_gbs=p["hbm_gbs"], bf16_tflops=p["bf16_tflops_sustained"], source="measured")
+    return dict(hbm_gbs=6650.0, bf16_tflops=1400.0, source="fallback")
+
+
+class ClockSampler:
+    """nvidia-smi clocks/throttle reasons sampled every 200 ms while the timed region runs."""
+    QUERY = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,"
+             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+             "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.proc, self.lines = index, None, []
+
+    def __enter__(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.QUERY}",
+                 "--format=csv,noheader,nounits", "-lms", "200"],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._pump, daemon=True)
+            self.thread.start()
+        except OSError:
+            self.proc = None
+        return self
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def __exit__(self, *exc):
+        if self.proc is not None:
+            time.sleep(0.25)
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=2)
+            except subprocess.TimeoutExpired:
+                self.proc.kill()
+        return False
+
+    def summary(self):
+        sm, smax, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for line in self.lines:
+            parts = [p.strip() for p in line.split(",")]
+            if len(parts) < 6:
+                continue
+            try:
+                sm.append(float(parts[0]))
+                smax.append(float(parts[1]))
+            except ValueError:
+                continue
+            for n, v in zip(names, parts[2:6]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        return {"sm_mhz": statistics.median(sm), "sm_max_mhz": max(smax), "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+def dist_setup(n_gpus):
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    return world, rank, local
+
+
+def cpu_reference_run(wl, steps, warmup, batch_size, budget_s=None):
+    """The oracle port of the reference model on the host cores: fwd + loss + bwd per step."""
+    from oracle import models as oracle_models
+    import rank_b200
+    threads = os.cpu_count() or 1
+    torch.set_num_threads(threads)
+    vocab = rank_b200.write_vocab_dir(tempfile.mkdtemp(prefix="rk_vocab_")) + "/"
+    torch.manual_seed(0)
+    model = wl.model(oracle_models, True, vocab)
+    model.train()
+    batches = [wl.make_batch(batch_size, 100 + i) for i in range(2)]
+    times = []
+    t_begin = time.perf_counter()
+    for i in range(warmup + steps):
+        b = batches[i % len(batches)]
+        t0 = time.perf_counter()
+        model.zero_grad(set_to_none=True)
+        torch.manual_seed(i)
+        loss = wl.loss(model, b)
+        loss.backward()
+        dt = time.perf_counter() - t0
+        if i >= warmup:
+            times.append(dt)
+        if budget_s is not None and i >= warmup + 2 and time.perf_counter() - t_begin > budget_s:
+            break
+    ms = 1e3 * sum(times) / len(times)
+    return dict(value=batch_size / (ms / 1e3), ms_per_step=ms, steps=len(times), cores=threads,
+                loss=float(loss))
+
+
+# ------------------------------------------------------------------------------- reference arm
+def run_reference(args, wl):
+    world, rank, _ = dist_setup(args.gpus)
+    if rank != 0:
+        return
+    B = args.batch or wl.batch
+    r = cpu_reference_run(wl, args.steps, args.warmup, B)
+    line = {
+        "impl": "reference", "metric": METRIC, "value": r["value"], "unit": "samples/s",
+        "n_gpus": args.gpus, "steps": r["steps"], "warmup": args.warmup, "ms_per_step": r["ms_per_step"],
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+        "data": "synthetic",
+        "config": {"workload": wl.name, "batch_per_step": B, "dropout": 0.0,
+                   "what": "oracle port of the reference nn.Module (the reference is Python and cannot "
+                           "travel to the GPU box), torch CPU fp32, all host threads"},
+        "cpu_baseline": {"value": r["value"], "unit": "samples/s", "cores": r["cores"], "kind": "port",
+                         "sample": f"{r['steps']} full steps of batch {B} (fwd+loss+bwd), host CPU"},
+        "e2e": {"value": r["value"], "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------- our arm
+def batch_bytes(batch):
+    n = 0
+    for v in batch.values():
+        if torch.is_tensor(v):
+            n += v.numel() * v.element_size()
+        elif isinstance(v, dict):
+            n += batch_bytes(v)
+    return n
+
+
+def pin(batch):
+    if torch.is_tensor(batch):
+        return batch.pin_memory()
+    return {k: pin(v) for k, v in batch.items()}
+
+
+def run_ours(args, wl):
+    import rank_b200
+    from rank_b200 import _lib, synthetic
+    from rank_b200.parallel import GradientAllReducer
+
+    world, rank, local = dist_setup(args.gpus)
+    assert torch.cuda.is_available(), "bench.py needs a CUDA device (no CPU fallback)"
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=dev)
+    lib = _lib.load()
+    B = args.batch or wl.batch
+
+    vocab = rank_b200.write_vocab_dir(tempfile.mkdtemp(prefix="rk_vocab_")) + "/"
+    torch.manual_seed(0)                    # identical replicas on every rank
+    model = wl.model(rank_b200, False, vocab).to(dev)
+    model.train()
+    reducer = GradientAllReducer(model) if world > 1 else None
+
+    n_pool = 4
+    host = [pin(wl.make_batch(B, 1000 + 17 * rank + i)) for i in range(n_pool)]
+    resident = [synthetic.to_device(b, dev) for b in host]
+    flush = torch.empty(L2_FLUSH_BYTES, dtype=torch.uint8, device=dev)
+
+    def step(batch, seed):
+        model.zero_grad(set_to_none=True)
+        torch.manual_seed(seed)             # per-call random weights: same draw on every rank
+        loss = wl.loss(model, batch)
+        loss.backward()
+        if reducer is not None:
+            reducer.allreduce()
+        return loss
+
+    def barrier():
+        if world > 1:
+            torch.distributed.barrier()
+        torch.cuda.synchronize()
+
+    def timed(n_steps, first_seed, from_host):
+        evs = []
+        for i in range(n_steps):
+            flush.fill_(i & 0xff)           # evict L2 between steps; outside the timed events
+            s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            s.record()
+            if from_host:
+                b = synthetic.to_device(host[i % n_pool], dev, non_blocking=True)
+                loss = step(b, first_seed + i)
+                loss_host = loss.detach().to("cpu", non_blocking=True)   # D2H read of the step's result
+            else:
+                loss = step(resident[i % n_pool], first_seed + i)
+            e.record()
+            evs.append((s, e))
+        torch.cuda.synchronize()
+        return sum(s.elapsed_time(e) for s, e in evs), float(loss)
+
+    for i in range(args.warmup):
+        step(resident[i % n_pool], i)
+    barrier()
+    launches0 = lib.rk_launch_count()
+    with ClockSampler(local) as clocks:
+        barrier()
+        total_ms, last_loss = timed(args.steps, 10_000, from_host=False)
+        barrier()
+    launches = lib.rk_launch_count() - launches0
+    # end to end: pinned host inputs -> H2D -> step -> D2H loss
+    for i in range(min(args.warmup, 3)):
+        timed(1, 50 + i, from_host=True)
+    barrier()
+    e2e_ms, _ = timed(args.steps, 20_000, from_host=True)
+    barrier()
+
+    # per-call device times of the hot path (separate pass; events bracket each ABI call)
+    with _lib.CallTimer() as ct:
+        for i in range(args.steps):
+            flush.fill_(i & 0xff)
+            step(resident[i % n_pool], 30_000 + i)
+    calls = ct.summary()
+
+    t = torch.tensor([total_ms, e2e_ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
+    total_ms, e2e_ms = float(t[0]), float(t[1])
+
+    if rank == 0:
+        pk = peaks()
+        hot_ms = sum(ms for name, (n, ms) in calls.items() if name in wl.hot_calls) / args.steps
+        achieved = (B * wl.bytes_per_sample) / (hot_ms * 1e-3) / 1e9 if hot_ms > 0 else 0.0
+        line = {
+            "metric": METRIC, "value": world * B * args.steps / (total_ms / 1e3), "unit": "samples/s",
+            "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": total_ms / args.steps,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+            "data": "synthetic",
+            "config": {"workload": wl.name, "batch_per_gpu": B, "global_batch": world * B, "dropout": 0.0,
+                       "parallelism": f"dp{world}", "l2": "256 MiB written between steps, outside the timed events",
+                       "step": "zero_grad+fwd+loss+bwd" + ("+grad allreduce" if world > 1 else ""),
+                       "indices": "zipf(1.05), fresh batch each step from a pool of 4"},
+            "clocks": clocks.summary(),
+            "e2e": {"value": world * B * args.steps / (e2e_ms / 1e3), "unit": "samples/s",
+                    "h2d_bytes_per_step": batch_bytes(host[0]), "d2h_bytes_per_step": 4},
+            "gpu_launches": int(launches),
+            "roofline": {"bound": wl.bound, "achieved": achieved, "peak": pk["hbm_gbs"], "unit": "GB/s",
+                         "frac": achieved / pk["hbm_gbs"], "traffic": None, "peak_source": pk["source"],
+                         "what": "hot path (all ABI calls of a step: " + ", ".join(wl.hot_calls) + ")",
+                         "algorithmic_bytes_per_sample": wl.bytes_per_sample, "hot_ms_per_step": hot_ms},
+            "hotpath_calls": {k: {"calls_per_step": n / args.steps, "ms_per_step": ms / args.steps}
+                              for k, (n, ms) in sorted(calls.items())},
+            "loss": last_loss,
+        }
+        if world == 1 and not args.no_cpu_baseline:
+            r = cpu_reference_run(wl, 50, 2, B, budget_s=15.0)
+            line["cpu_baseline"] = {"value": r["value"], "unit": "samples/s", "cores": r["cores"], "kind": "port",
+                                    "sample": f"{r['steps']} full steps of batch {B} (fwd+loss+bwd) of the oracle "
+                                              "port, torch CPU fp32"}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        torch.distributed.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="dcn", choices=sorted(WORKLOADS))
+    ap.add_argument("--batch", type=int, default=0, help="per-GPU batch (default: the workload's)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3)
+    wl = WORKLOADS[args.workload]()
+    if args.impl == "reference":
+        run_reference(args, wl)
+    else:
+        run_ours(args, wl)
+
+
+if __name__ == "__main__":
+    main()

@@ -41,6 +41,7 @@ PROTOTYPES = {
     "rk_version": (_I, []),
     "rk_last_error": (C.c_char_p, []),
     "rk_device_sm_count": (_I, []),
+    "rk_launch_count": (C.c_longlong, []),
     "rk_plan_workspace_bytes": (_Z, [_L]),
     "rk_plan_build": (_I, [_P, _P, _P, _I, _P, _P, _P, _Z, _P, _P]),
     "rk_reduce_workspace_bytes": (_Z, [_P, _I, _P, _I]),
@@ -83,6 +84,54 @@ def load() -> C.CDLL:
         raise RankB200Error(f"librank_b200 ABI {lib.rk_version()} != expected {ABI_VERSION}")
     _lib = lib
     return lib
+
+
+class CallTimer:
+    """Brackets every kernel-launching ABI call with CUDA events on the launching stream
+    (bench.py's live per-call device times).  Use as a context manager; `summary()` after a
+    synchronize gives {entry point: (calls, total ms)}."""
+
+    NO_KERNEL = ("rk_version", "rk_last_error", "rk_device_sm_count", "rk_launch_count",
+                 "rk_plan_workspace_bytes", "rk_reduce_workspace_bytes")
+
+    def __init__(self):
+        self.records = []
+
+    def __enter__(self):
+        lib = load()
+        self._saved = {}
+        for name in PROTOTYPES:
+            if name in self.NO_KERNEL:
+                continue
+            fn = getattr(lib, name)
+            self._saved[name] = fn
+            setattr(lib, name, self._wrap(name, fn))
+        return self
+
+    def _wrap(self, name, fn):
+        def timed(*args):
+            s = torch.cuda.Event(enable_timing=True)
+            e = torch.cuda.Event(enable_timing=True)
+            s.record()
+            rc = fn(*args)
+            e.record()
+            self.records.append((name, s, e))
+            return rc
+        return timed
+
+    def __exit__(self, *exc):
+        lib = load()
+        for name, fn in self._saved.items():
+            setattr(lib, name, fn)
+        return False
+
+    def summary(self):
+        torch.cuda.synchronize()
+        out = {}
+        for name, s, e in self.records:
+            calls, ms = out.get(name, (0, 0.0))
+            out[name] = (calls + 1, ms + s.elapsed_time(e))
+        return out
 
 
 def check(rc: int, what: str) -> None:

@@ -1,6 +1,7 @@
 // abi.cu — ABI bookkeeping: version, thread-local error text, field packing.
 #include <stdarg.h>
 #include <string.h>
+#include <atomic>
 #include "common.cuh"
 
 namespace rk {
@@ -13,6 +14,10 @@ void set_error(const char* fmt, ...) {
     vsnprintf(g_err, sizeof(g_err), fmt, ap);
     va_end(ap);
 }
+
+static std::atomic<long long> g_launches{0};
+void note_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
+long long launches() { return g_launches.load(std::memory_order_relaxed); }
 
 int sm_count() {
     static int cached = 0;
@@ -66,5 +71,7 @@ int rk_version(void) { return RK_ABI_VERSION; }
 const char* rk_last_error(void) { return rk::g_err; }
 
 int rk_device_sm_count(void) { return rk::sm_count(); }
+
+long long rk_launch_count(void) { return rk::launches(); }
 
 }  // extern "C"

@@ -19,6 +19,7 @@ constexpr unsigned kFull = 0xffffffffu;
 // ---- host-side error plumbing (thread-local message, see rk_last_error) -------------------
 void set_error(const char* fmt, ...);
 int  sm_count();
+void note_launch();  // counts kernels launched through the ABI (rk_launch_count)
 
 #define RK_CHECK_ARG(cond, ...)              \
     do {                                     \
@@ -40,6 +41,7 @@ int  sm_count();
 
 #define RK_LAUNCH_CHECK()                                                              \
     do {                                                                               \
+        rk::note_launch();                                                             \
         cudaError_t e_ = cudaPeekAtLastError();                                        \
         if (e_ != cudaSuccess) {                                                       \
             rk::set_error("kernel launch failed: %s (%s:%d)", cudaGetErrorString(e_),  \

@@ -56,6 +56,7 @@ typedef struct rk_grad_table {
 int         rk_version(void);
 const char* rk_last_error(void);
 int         rk_device_sm_count(void);
+long long   rk_launch_count(void);   /* kernels launched through this library so far (process-wide) */
 
 /* ---- sparse embedding-gradient reduction (autograd of nn.Embedding: embedding_dense_backward,
  *      reached from loss.backward() e.g. DIN/din.py:346) -------------------------------------

@@ -1,0 +1,124 @@
+"""GPU parity of the drop-in modules: against the reference's recorded outputs (golden
+fixtures), and against the oracle on WeChat-sized synthetic batches.
+Tolerances (north star): gathered rows bit-exact; logits and gradients within 1e-5 relative
+(fp32 paths), 2e-2 on the bf16 tensor-core paths (named where used)."""
+import os
+
+import pytest
+import torch
+
+import rank_b200
+from rank_b200 import synthetic
+from conftest import golden_files, grad_floor, load_golden, rel_err, to_device
+import golden_cases
+from oracle import models as oracle_models
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+FP32_TOL = 1e-5
+IMPLEMENTED = {n for n in ("DeepFM", "DCNModel", "DeepCrossingModel", "AFM", "DIN", "BSTModel")
+               if hasattr(rank_b200, n)}
+FIXTURES = [p for p in golden_files() if "smoke" not in p]
+
+
+def compare(outs, grads, ref_outs, ref_grads, tol):
+    assert len(outs) == len(ref_outs)
+    for i, (o, r) in enumerate(zip(outs, ref_outs)):
+        if torch.is_tensor(r):
+            assert rel_err(o, r) <= tol, f"output {i}: {rel_err(o, r):.3e}"
+        else:
+            assert o == r
+    assert set(grads) == set(ref_grads)
+    floor = grad_floor(ref_grads)
+    for k, g in ref_grads.items():
+        e = rel_err(grads[k], g, floor)
+        assert e <= tol, f"grad {k}: {e:.3e}"
+
+
+@pytest.mark.parametrize("path", FIXTURES, ids=[os.path.basename(p) for p in FIXTURES])
+def test_module_matches_reference_fixture(path, small_vocab_dir):
+    fx = load_golden(path)
+    if fx["model"] not in IMPLEMENTED:
+        pytest.skip(f"{fx['model']} not built yet")
+    model = golden_cases.build(fx, rank_b200, small_vocab_dir, oracle=False)
+    model.load_state_dict(fx["state_dict"], strict=True)      # state_dict compatibility
+    model.to(DEV)
+    outs, grads = golden_cases.replay(model, fx, to_device(fx["inputs"], DEV), to_device(fx["cotangents"], DEV))
+    rank_b200.check_index_errors()
+    compare(outs, grads, fx["outputs"], fx["grads"], FP32_TOL)
+
+
+def _pair(name, oracle_name, vocab_dir, *args, **kw):
+    torch.manual_seed(0)
+    ours = getattr(rank_b200, name)(vocab_dir, *args, **kw)
+    ref = getattr(oracle_models, oracle_name)(vocab_dir, *args, **kw)
+    ref.load_state_dict(ours.state_dict(), strict=True)
+    return ours.to(DEV), ref
+
+
+def _run_both(ours, ref, fx_model, batch, seed=3):
+    fx = {"model": fx_model, "seed": seed}
+    inputs = {k: v for k, v in batch.items() if k != "label"}
+    with torch.no_grad():
+        n_out = sum(torch.is_tensor(o) for o in golden_cases.call(ref, fx, inputs))
+    B = batch["label"].shape[0]
+    gen = torch.Generator().manual_seed(seed)
+    cots = [torch.randn(B, 1, generator=gen) / B for _ in range(n_out)]
+    if fx_model == "DIN":
+        cots[-1] = torch.tensor(1.0)      # l2_reg is a scalar added to the loss (DIN/din.py:344)
+    r_outs, r_grads = golden_cases.replay(ref, fx, inputs, cots)
+    o_outs, o_grads = golden_cases.replay(ours, fx, to_device(inputs, DEV), to_device(cots, DEV))
+    rank_b200.check_index_errors()
+    return o_outs, o_grads, r_outs, r_grads
+
+
+@pytest.mark.parametrize("B,D", [(1024, 16), (8192, 8), (333, 10)])
+def test_deepfm_vs_oracle_wechat_sizes(wechat_vocab_dir, B, D):
+    ours, ref = _pair("DeepFM", "OracleDeepFM", wechat_vocab_dir, embedding_dim=D, dropout_rate=0.0)
+    compare(*_run_both(ours, ref, "DeepFM", synthetic.deepfm_batch(B)), FP32_TOL)
+
+
+def test_deepfm_gathered_rows_are_bit_exact(wechat_vocab_dir):
+    ours, ref = _pair("DeepFM", "OracleDeepFM", wechat_vocab_dir, embedding_dim=16, dropout_rate=0.0)
+    batch = synthetic.deepfm_batch(4096)
+    from rank_b200.deepfm import _FMInteraction, DEEPFM_COLUMNS
+    cat = to_device(batch["category"], DEV)
+    args = ([cat[c] for c in DEEPFM_COLUMNS] + [ours.first_order_embeddings[c].weight for c in DEEPFM_COLUMNS]
+            + [ours.second_order_embeddings[c].weight for c in DEEPFM_COLUMNS])
+    with torch.no_grad():
+        deep_input, _, _ = _FMInteraction.apply(6, *args)
+        want = torch.cat([ref.second_order_embeddings[c].weight[batch["category"][c]] for c in DEEPFM_COLUMNS], 1)
+    assert torch.equal(deep_input.cpu(), want)
+
+
+@pytest.mark.parametrize("B,L", [(8192, 3), (1000, 1), (64, 0), (2048, 6)])
+def test_dcn_vs_oracle_wechat_sizes(wechat_vocab_dir, B, L):
+    ours, ref = _pair("DCNModel", "OracleDCN", wechat_vocab_dir, num_cross_layer=L)
+    compare(*_run_both(ours, ref, "DCNModel", synthetic.side_batch(B)), FP32_TOL)
+
+
+def test_dcn_loads_reference_state_dict_keys(wechat_vocab_dir):
+    ours = rank_b200.DCNModel(wechat_vocab_dir, num_cross_layer=3)
+    keys = list(ours.state_dict())
+    assert keys[:6] == [f"embeddings.{c}.weight" for c in
+                        ("userid", "device", "authorid", "bgm_song_id", "bgm_singer_id", "manual_tag_list")]
+    assert keys[6:] == ["dnn.0.weight", "dnn.0.bias", "dnn.2.weight", "dnn.2.bias", "dnn.4.weight",
+                        "dnn.4.bias", "output_layer.weight", "output_layer.bias"]
+    assert ours.state_dict()["output_layer.weight"].shape == (1, 178)
+
+
+def test_cross_layer_function(wechat_vocab_dir):
+    gen = torch.Generator().manual_seed(2)
+    x0 = torch.randn(257, 50, generator=gen, requires_grad=True)
+    xl = torch.randn(257, 50, generator=gen, requires_grad=True)
+    torch.manual_seed(8)
+    w = torch.zeros(50, 1)
+    torch.nn.init.xavier_normal_(w)
+    want = x0 * torch.matmul(xl, w) + xl
+    want.sum().backward()
+    a0, al = x0.detach().to(DEV).requires_grad_(), xl.detach().to(DEV).requires_grad_()
+    torch.manual_seed(8)
+    got = rank_b200.cross_layer(a0, al, 0)
+    got.sum().backward()
+    assert rel_err(got, want) <= FP32_TOL
+    assert rel_err(a0.grad, x0.grad) <= FP32_TOL and rel_err(al.grad, xl.grad) <= FP32_TOL
