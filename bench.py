@@ -236,6 +236,72 @@ def pin(batch):
     return {k: pin(v) for k, v in batch.items()}
 
 
+class Stepper:
+    """One training step (zero_grad, forward, loss, backward) on static device buffers, replayed
+    from a CUDA graph (default) or run eagerly (--no-graph).  The per-call random weights of
+    DCN / DeepCrossing / DIN are re-drawn on the CPU generator before every step, as the
+    reference does inside forward, and shipped to a fixed device buffer outside the graph."""
+
+    def __init__(self, model, wl, example, use_graph, reducer):
+        self.model, self.wl, self.reducer = model, wl, reducer
+        self.static = clone_batch(example)
+        self.has_ephemeral = hasattr(model, "draw_ephemeral")
+        self.graph = None
+        self.grads = None
+        if use_graph:
+            side = torch.cuda.Stream()
+            side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(side):
+                for i in range(3):
+                    self._eager(i)
+            torch.cuda.current_stream().wait_stream(side)
+            torch.cuda.synchronize()
+            model.zero_grad(set_to_none=True)
+            if self.has_ephemeral:
+                model.draw_ephemeral()
+                model.ephemeral_frozen = True
+            self.graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(self.graph):
+                self.loss = wl.loss(model, self.static)
+                self.loss.backward()
+            self.grads = [p.grad for p in model.parameters()]
+
+    def _eager(self, seed):
+        self.model.zero_grad(set_to_none=True)
+        torch.default_generator.manual_seed(seed)
+        self.loss = self.wl.loss(self.model, self.static)
+        self.loss.backward()
+
+    def load(self, batch):
+        copy_batch(self.static, batch)
+
+    def run(self, seed):
+        if self.graph is None:
+            self._eager(seed)
+            grads = None
+        else:
+            if self.has_ephemeral:
+                torch.default_generator.manual_seed(seed)   # same draw on every rank
+                self.model.draw_ephemeral()
+            self.graph.replay()
+            grads = self.grads
+        if self.reducer is not None:
+            self.reducer.allreduce(grads)
+        return self.loss
+
+
+def clone_batch(b):
+    return b.clone() if torch.is_tensor(b) else {k: clone_batch(v) for k, v in b.items()}
+
+
+def copy_batch(dst, src):
+    if torch.is_tensor(dst):
+        dst.copy_(src, non_blocking=True)
+    else:
+        for k in dst:
+            copy_batch(dst[k], src[k])
+
+
 def run_ours(args, wl):
     import rank_b200
     from rank_b200 import _lib, synthetic
@@ -261,15 +327,7 @@ def run_ours(args, wl):
     host = [pin(wl.make_batch(B, 1000 + 17 * rank + i)) for i in range(n_pool)]
     resident = [synthetic.to_device(b, dev) for b in host]
     flush = torch.empty(L2_FLUSH_BYTES, dtype=torch.uint8, device=dev)
-
-    def step(batch, seed):
-        model.zero_grad(set_to_none=True)
-        torch.manual_seed(seed)             # per-call random weights: same draw on every rank
-        loss = wl.loss(model, batch)
-        loss.backward()
-        if reducer is not None:
-            reducer.allreduce()
-        return loss
+    stepper = Stepper(model, wl, resident[0], not args.no_graph, reducer)
 
     def barrier():
         if world > 1:
@@ -278,23 +336,28 @@ def run_ours(args, wl):
 
     def timed(n_steps, first_seed, from_host):
         evs = []
+        loss_host = None
         for i in range(n_steps):
             flush.fill_(i & 0xff)           # evict L2 between steps; outside the timed events
             s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            s.record()
             if from_host:
-                b = synthetic.to_device(host[i % n_pool], dev, non_blocking=True)
-                loss = step(b, first_seed + i)
+                s.record()
+                stepper.load(host[i % n_pool])                       # H2D of this step's inputs (pinned)
+                loss = stepper.run(first_seed + i)
                 loss_host = loss.detach().to("cpu", non_blocking=True)   # D2H read of the step's result
+                e.record()
             else:
-                loss = step(resident[i % n_pool], first_seed + i)
-            e.record()
+                stepper.load(resident[i % n_pool])                   # device-to-device, untimed
+                s.record()
+                loss = stepper.run(first_seed + i)
+                e.record()
             evs.append((s, e))
         torch.cuda.synchronize()
-        return sum(s.elapsed_time(e) for s, e in evs), float(loss)
+        return sum(s.elapsed_time(e) for s, e in evs), float(loss.detach())
 
     for i in range(args.warmup):
-        step(resident[i % n_pool], i)
+        stepper.load(resident[i % n_pool])
+        stepper.run(i)
     barrier()
     launches0 = lib.rk_launch_count()
     with ClockSampler(local) as clocks:
@@ -302,18 +365,27 @@ def run_ours(args, wl):
         total_ms, last_loss = timed(args.steps, 10_000, from_host=False)
         barrier()
     launches = lib.rk_launch_count() - launches0
+    if stepper.graph is not None:
+        launches = stepper_launches_per_replay(stepper, lib) * args.steps
     # end to end: pinned host inputs -> H2D -> step -> D2H loss
-    for i in range(min(args.warmup, 3)):
+    for i in range(3):
         timed(1, 50 + i, from_host=True)
     barrier()
     e2e_ms, _ = timed(args.steps, 20_000, from_host=True)
     barrier()
 
-    # per-call device times of the hot path (separate pass; events bracket each ABI call)
+    # Per-call device times of the hot path: eager steps queued behind a spin kernel, so the
+    # kernels run back to back and the events bracketing each ABI call see device time only.
+    eager = Stepper(model, wl, resident[0], False, None)
+    if hasattr(model, "ephemeral_frozen"):
+        model.ephemeral_frozen = False
     with _lib.CallTimer() as ct:
         for i in range(args.steps):
+            eager.load(resident[i % n_pool])
             flush.fill_(i & 0xff)
-            step(resident[i % n_pool], 30_000 + i)
+            _lib.check(lib.rk_debug_spin(4000, _lib.stream_ptr()), "rk_debug_spin")
+            eager.run(30_000 + i)
+            torch.cuda.synchronize()
     calls = ct.summary()
 
     t = torch.tensor([total_ms, e2e_ms], dtype=torch.float64, device=dev)
@@ -333,6 +405,7 @@ def run_ours(args, wl):
             "config": {"workload": wl.name, "batch_per_gpu": B, "global_batch": world * B, "dropout": 0.0,
                        "parallelism": f"dp{world}", "l2": "256 MiB written between steps, outside the timed events",
                        "step": "zero_grad+fwd+loss+bwd" + ("+grad allreduce" if world > 1 else ""),
+                       "launch": "eager" if stepper.graph is None else "cuda graph replay per step",
                        "indices": "zipf(1.05), fresh batch each step from a pool of 4"},
             "clocks": clocks.summary(),
             "e2e": {"value": world * B * args.steps / (e2e_ms / 1e3), "unit": "samples/s",
@@ -356,6 +429,22 @@ def run_ours(args, wl):
         torch.distributed.destroy_process_group()
 
 
+def stepper_launches_per_replay(stepper, lib):
+    """Kernels of librank_b200 inside one captured step = what one eager step launches."""
+    probe = Stepper(stepper.model, stepper.wl, stepper.static, False, None)
+    frozen = getattr(stepper.model, "ephemeral_frozen", None)
+    n0 = lib.rk_launch_count()
+    probe.run(1)
+    torch.cuda.synchronize()
+    n = lib.rk_launch_count() - n0
+    if frozen is not None:
+        stepper.model.ephemeral_frozen = frozen
+    stepper.model.zero_grad(set_to_none=True)
+    for p, g in zip(stepper.model.parameters(), stepper.grads):
+        p.grad = g
+    return n
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -365,6 +454,7 @@ def main():
     ap.add_argument("--workload", default="dcn", choices=sorted(WORKLOADS))
     ap.add_argument("--batch", type=int, default=0, help="per-GPU batch (default: the workload's)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-graph", action="store_true", help="launch every step eagerly instead of a CUDA graph")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
     wl = WORKLOADS[args.workload]()

@@ -16,10 +16,11 @@ from .vocab import VOCAB_FILE, WECHAT_VOCAB_LINES, table_heights, write_vocab_di
 from .sparse import GradSource, OccurrencePlan, gather_concat
 from .deepfm import DeepFM
 from .dcn import DCNModel, cross_layer
+from .din import DIN, Dice, din_attention, din_collate_fn
 
 __all__ = [
     "RankB200Error", "check_index_errors", "library_path",
     "VOCAB_FILE", "WECHAT_VOCAB_LINES", "table_heights", "write_vocab_dir",
     "GradSource", "OccurrencePlan", "gather_concat",
-    "DeepFM", "DCNModel", "cross_layer",
+    "DeepFM", "DCNModel", "cross_layer", "DIN", "Dice", "din_attention", "din_collate_fn",
 ]

@@ -31,6 +31,17 @@ class RkGradTable(C.Structure):
                 ("dim", C.c_int32), ("field", C.c_int32)]
 
 
+class RkDinArgs(C.Structure):
+    _fields_ = [("cat", C.c_void_p), ("n_cat", C.c_int32), ("n_dense", C.c_int32),
+                ("dense_cols", C.c_void_p), ("dense_stride", C.c_int64),
+                ("target", RkField), ("history", RkField), ("hist_len", C.c_void_p),
+                ("T", C.c_int32), ("att_off", C.c_int32), ("width", C.c_int32),
+                ("l2_from", C.c_int32), ("use_softmax", C.c_int32), ("mlp", C.c_void_p),
+                ("B", C.c_int64)]
+
+
+LIVE_ALL, LIVE_PREFIX, LIVE_PREFIX_OR_EMPTY = 0, 1, 2
+
 _P = C.c_void_p
 _I = C.c_int
 _L = C.c_int64
@@ -42,8 +53,9 @@ PROTOTYPES = {
     "rk_last_error": (C.c_char_p, []),
     "rk_device_sm_count": (_I, []),
     "rk_launch_count": (C.c_longlong, []),
+    "rk_debug_spin": (_I, [_I, _P]),
     "rk_plan_workspace_bytes": (_Z, [_L]),
-    "rk_plan_build": (_I, [_P, _P, _P, _I, _P, _P, _P, _Z, _P, _P]),
+    "rk_plan_build": (_I, [_P, _P, _P, _I, _P, _P, _P, _P, _P, _P, _Z, _P, _P]),
     "rk_reduce_workspace_bytes": (_Z, [_P, _I, _P, _I]),
     "rk_embgrad_segment_reduce": (_I, [_P, _P, _P, _P, _I, _P, _I, _P, _Z, _P]),
     "rk_gather_concat_fwd": (_I, [_P, _I, _P, _I, _L, _P, _I, _P, _P]),
@@ -53,6 +65,9 @@ PROTOTYPES = {
     "rk_crossnet_bwd": (_I, [_P, _P, _P, _I, _I, _L, _P, _P, _P, _P]),
     "rk_cross_layer_fwd": (_I, [_P, _P, _P, _P, _I, _L, _P, _P]),
     "rk_cross_layer_bwd": (_I, [_P, _P, _P, _I, _L, _P, _P, _P, _P]),
+    "rk_din_mlp_floats": (_I, [_I]),
+    "rk_din_fwd": (_I, [_P, _P, _P, _P, _P, _P, _P]),
+    "rk_din_bwd": (_I, [_P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P]),
 }
 
 _lib = None
@@ -91,7 +106,7 @@ class CallTimer:
     (bench.py's live per-call device times).  Use as a context manager; `summary()` after a
     synchronize gives {entry point: (calls, total ms)}."""
 
-    NO_KERNEL = ("rk_version", "rk_last_error", "rk_device_sm_count", "rk_launch_count",
+    NO_KERNEL = ("rk_din_mlp_floats", "rk_version", "rk_last_error", "rk_device_sm_count", "rk_launch_count", "rk_debug_spin",
                  "rk_plan_workspace_bytes", "rk_reduce_workspace_bytes")
 
     def __init__(self):

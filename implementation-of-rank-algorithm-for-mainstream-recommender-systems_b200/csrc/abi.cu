@@ -62,6 +62,17 @@ int pack_fields(const rk_field_t* f, int F, FieldSet* out) {
     return 0;
 }
 
+// Measurement aid: keeps the stream busy for `us` microseconds so that the host can enqueue a
+// whole step behind it; the kernels then run back to back and CUDA events see device time only.
+__global__ void spin_kernel(unsigned long long ns) {
+    unsigned long long t0, t1;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+    do {
+        __nanosleep(1000);
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+    } while (t1 - t0 < ns);
+}
+
 }  // namespace rk
 
 extern "C" {
@@ -73,5 +84,13 @@ const char* rk_last_error(void) { return rk::g_err; }
 int rk_device_sm_count(void) { return rk::sm_count(); }
 
 long long rk_launch_count(void) { return rk::launches(); }
+
+int rk_debug_spin(int us, rk_stream_t stream) {
+    RK_CHECK_ARG(us >= 0 && us <= 100000, "rk_debug_spin: %d us outside [0, 100000]", us);
+    rk::spin_kernel<<<1, 1, 0, (cudaStream_t)stream>>>((unsigned long long)us * 1000ull);
+    cudaError_t e = cudaPeekAtLastError();
+    if (e != cudaSuccess) { rk::set_error("spin launch failed: %s", cudaGetErrorString(e)); return (int)e; }
+    return 0;
+}
 
 }  // extern "C"

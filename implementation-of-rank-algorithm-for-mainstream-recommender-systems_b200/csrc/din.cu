@@ -1,0 +1,599 @@
+// din.cu — DIN hot path: every gather of DIN.forward (DIN/din.py:294-305), the local activation
+// unit din_attention (DIN/din.py:42-84), the concat (:310) and the per-sample L2 norm of the
+// mini-batch-aware regulariser (:318-322), forward and backward, fp32 SIMT.
+//
+// One CTA owns kSamples consecutive samples.  Only history positions t < len feed the
+// activation-unit MLP (padded positions get weight 0 in raw mode and exp(-2^32/sqrt(D)) = 0 in
+// softmax mode, so their scores are never observable); whole samples are packed into tiles of at
+// most kRows (b,t) rows.  Per tile:
+//   gather   K rows (64 B each at D=16) -> shared memory, feature-major, with q, q-k, q*k
+//   MLP      [rows,4D]x[4D,64] -> ReLU -> [rows,64]x[64,32] -> ReLU -> .w3   (tile_gemm.cuh)
+//   pooling  masked raw / scaled-softmax weights, sum_t w_t k_t  (warp per sample, shuffles)
+// The backward never needs dW of the unit (its weights are drawn per call and unregistered,
+// DIN/din.py:61-67), so the forward keeps only the two ReLU masks as bits (12 B per row) and the
+// weights w_t; the backward is g_score -> 32 -> 64 -> 4D through the transposed weights.
+#include <string.h>
+#include "common.cuh"
+#include "tile_gemm.cuh"
+
+namespace rk {
+
+constexpr int kDinThreads = 256;
+constexpr int kRows       = 128;   // (b,t) rows per MLP tile
+constexpr int kSamples    = 8;     // samples per CTA
+constexpr int kH1 = 64, kH2 = 32;
+constexpr int kMaxDense   = 32;
+
+struct DinParams {
+    FieldSet       cat;                      // off = column in the concat row
+    const float*   dense_col[kMaxDense];
+    int64_t        dense_stride;
+    int32_t        n_dense;
+    const float*   tgt_w;  const int64_t* tgt_idx;  int64_t tgt_rows;  int32_t tgt_off;
+    const float*   his_w;  const int64_t* his_idx;  int64_t his_rows;
+    const int64_t* his_len;
+    int32_t        T, D, att_off, width, l2_from, use_softmax;
+    const float*   mlp;
+    int64_t        B;
+};
+
+// Offsets (floats) inside the packed per-call weights; K1 = 4*D.
+struct MlpLayout {
+    int w1t, b1, w2t, b2, w3, b3, w1, w2, total;
+    __host__ __device__ explicit MlpLayout(int D) {
+        const int K1 = 4 * D;
+        w1t = 0;                 // [K1][64]   W1t[k][n] = W1[n][k]
+        b1  = w1t + K1 * kH1;    // [64]
+        w2t = b1 + kH1;          // [64][32]   W2t[k][n] = W2[n][k]
+        b2  = w2t + kH1 * kH2;   // [32]
+        w3  = b2 + kH2;          // [32]
+        b3  = w3 + kH2;          // [1] (+3 pad)
+        w1  = b3 + 4;            // [64][K1]   as registered: W1[n][k]
+        w2  = w1 + kH1 * K1;     // [32][64]   W2[n][k]
+        total = w2 + kH2 * kH1;
+    }
+};
+
+// Shared-memory carve-up shared by forward and backward.
+struct DinSmem {
+    float *wA, *wB, *vec;          // weights: fwd (W1t, W2t) / bwd (W1, W2); vec = b1,b2,w3,b3
+    float *x, *h1, *h2;            // [4D][kRows], [64][kRows], [32][kRows]
+    float *score, *gw;             // [kRows]
+    float *q, *gatt, *gq;          // [kSamples][D]
+    int   *row_s, *row_t;          // row -> (local sample, t)
+    int   *len, *start;            // per sample: clipped length, first row in the tile list
+    uint32_t* mask;                // [3][kRows] (backward)
+    __device__ DinSmem(float* base, int D) {
+        const int K1 = 4 * D;
+        float* p = base;
+        wA = p;     p += K1 * kH1;
+        wB = p;     p += kH1 * kH2;
+        vec = p;    p += 2 * kH1 + 2 * kH2 + 4;
+        x = p;      p += K1 * kRows;
+        h1 = p;     p += kH1 * kRows;
+        h2 = p;     p += kH2 * kRows;
+        score = p;  p += kRows;
+        gw = p;     p += kRows;
+        q = p;      p += kSamples * D;
+        gatt = p;   p += kSamples * D;
+        gq = p;     p += kSamples * D;
+        row_s = (int*)p;  p += kRows;
+        row_t = (int*)p;  p += kRows;
+        len = (int*)p;    p += kSamples;
+        start = (int*)p;  p += kSamples + 4;
+        mask = (uint32_t*)p;  p += 3 * kRows;
+    }
+    static size_t bytes(int D) {
+        const int K1 = 4 * D;
+        return sizeof(float) * (size_t)(K1 * kH1 + kH1 * kH2 + 2 * kH1 + 2 * kH2 + 4 + K1 * kRows +
+                                        kH1 * kRows + kH2 * kRows + 2 * kRows + 3 * kSamples * D +
+                                        2 * kRows + 2 * kSamples + 4 + 3 * kRows);
+    }
+};
+
+template <int TN, class Epi>
+__device__ __forceinline__ void tile_gemm_rows(const float* As, const float* Bs, int K, int N,
+                                               int m_used, Epi epi) {
+    tile_gemm<TN, kDinThreads>(As, kRows, Bs, N, K, N, m_used, epi);
+}
+
+// History positions that carry gradient / attention weight: t < len, or every t when len == 0 in
+// softmax mode (all scores equal the padding value -> uniform weights 1/T, DIN/din.py:74-77).
+__device__ __forceinline__ int clip_len(int64_t len, int T) {
+    return len < 0 ? 0 : (len > T ? T : (int)len);
+}
+
+// Stage the K rows of a tile feature-major into x[D..2D), optionally with q, q-k, q*k.
+template <bool FULL_CROSS>
+__device__ __forceinline__ void stage_rows(const DinParams& p, const DinSmem& sm, int64_t b0,
+                                           int n_rows, int32_t* err_flag) {
+    const int D = p.D, D4 = D / 4;
+    for (int item = threadIdx.x; item < D4 * kRows; item += kDinThreads) {
+        const int c4 = item / kRows, m = item - c4 * kRows;
+        float4 k = make_float4(0.f, 0.f, 0.f, 0.f), q = k;
+        if (m < n_rows) {
+            const int s = sm.row_s[m], t = sm.row_t[m];
+            const int64_t row = checked_row(__ldg(p.his_idx + (b0 + s) * p.T + t), p.his_rows, err_flag);
+            k = __ldg(reinterpret_cast<const float4*>(p.his_w + row * D) + c4);
+            q = *reinterpret_cast<const float4*>(sm.q + s * D + c4 * 4);
+        }
+        const float kv[4] = {k.x, k.y, k.z, k.w}, qv[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            const int c = c4 * 4 + e;
+            sm.x[(D + c) * kRows + m] = kv[e];
+            if (FULL_CROSS) {
+                sm.x[c * kRows + m]           = qv[e];
+                sm.x[(2 * D + c) * kRows + m] = qv[e] - kv[e];
+                sm.x[(3 * D + c) * kRows + m] = qv[e] * kv[e];
+            }
+        }
+    }
+}
+
+// Pack whole samples [s_begin, s_end) of the CTA into one tile of <= kRows rows (thread 0 plans).
+__device__ __forceinline__ int plan_tile(const DinSmem& sm, int n_samples, int s_begin, int* s_end_out) {
+    // every thread computes the same small scan: no divergence, no extra barrier
+    int rows = 0, s = s_begin;
+    while (s < n_samples && rows + sm.len[s] <= kRows) {
+        rows += sm.len[s];
+        ++s;
+    }
+    *s_end_out = s;
+    return rows;
+}
+
+__global__ void __launch_bounds__(kDinThreads)
+din_fwd_kernel(const __grid_constant__ DinParams p, float* __restrict__ concat_all,
+               float* __restrict__ norm_out, float* __restrict__ att_w, uint32_t* __restrict__ masks,
+               int32_t* err_flag) {
+    extern __shared__ __align__(16) float smem_raw[];
+    const int D = p.D, K1 = 4 * D, T = p.T;
+    DinSmem sm(smem_raw, D);
+    const MlpLayout L(D);
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int64_t b0 = (int64_t)blockIdx.x * kSamples;
+    const int n_samples = (int)((p.B - b0) < kSamples ? (p.B - b0) : kSamples);
+
+    // ---- stage the per-call weights and the CTA's q rows / lengths
+    for (int i = tid; i < K1 * kH1; i += kDinThreads) sm.wA[i] = __ldg(p.mlp + L.w1t + i);
+    for (int i = tid; i < kH1 * kH2; i += kDinThreads) sm.wB[i] = __ldg(p.mlp + L.w2t + i);
+    for (int i = tid; i < kH1; i += kDinThreads) sm.vec[i] = __ldg(p.mlp + L.b1 + i);
+    for (int i = tid; i < kH2; i += kDinThreads) {
+        sm.vec[kH1 + i]       = __ldg(p.mlp + L.b2 + i);
+        sm.vec[kH1 + kH2 + i] = __ldg(p.mlp + L.w3 + i);
+    }
+    if (tid == 0) sm.vec[kH1 + 2 * kH2] = __ldg(p.mlp + L.b3);
+    for (int i = tid; i < n_samples * D; i += kDinThreads) {
+        const int s = i / D, e = i - s * D;
+        const int64_t row = checked_row(__ldg(p.tgt_idx + b0 + s), p.tgt_rows, err_flag);
+        sm.q[i] = __ldg(p.tgt_w + row * D + e);
+    }
+    if (tid < kSamples) sm.len[tid] = tid < n_samples ? clip_len(__ldg(p.his_len + b0 + tid), T) : 0;
+    __syncthreads();
+    const float* b1 = sm.vec;
+    const float* b2 = sm.vec + kH1;
+    const float* w3 = sm.vec + kH1 + kH2;
+    const float  b3 = sm.vec[kH1 + 2 * kH2];
+    const float  inv_sqrt_d = 1.0f / sqrtf((float)D);
+
+    int s_begin = 0;
+    while (s_begin < n_samples) {
+        int s_end;
+        const int n_rows = plan_tile(sm, n_samples, s_begin, &s_end);
+        // row map: tile row -> (sample, t)
+        if (tid < kSamples + 1) {
+            int acc = 0;
+            for (int s = s_begin; s < s_begin + tid && s < s_end; ++s) acc += sm.len[s];
+            sm.start[tid] = acc;     // start[j] = first row of sample s_begin + j
+        }
+        __syncthreads();
+        for (int m = tid; m < kRows; m += kDinThreads) {
+            int s = s_begin;
+            while (s + 1 < s_end && m >= sm.start[s + 1 - s_begin]) ++s;
+            sm.row_s[m] = s;
+            sm.row_t[m] = m - sm.start[s - s_begin];
+        }
+        __syncthreads();
+        if (n_rows > 0) {
+            stage_rows<true>(p, sm, b0, n_rows, err_flag);
+            __syncthreads();
+            const int m_used = (n_rows + 3) / 4 * 4;
+            // layer 1: [rows,4D] x [4D,64] + b1, ReLU
+            tile_gemm_rows<8>(sm.x, sm.wA, K1, kH1, m_used, [&](int m0, int n0, float (&acc)[4][8]) {
+#pragma unroll
+                for (int j = 0; j < 8; ++j)
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) acc[i][j] = fmaxf(acc[i][j] + b1[n0 + j], 0.f);
+                store_tile_kmajor<8>(sm.h1, kRows, m0, n0, acc);
+            });
+            __syncthreads();
+            // layer 2: [rows,64] x [64,32] + b2, ReLU
+            tile_gemm_rows<4>(sm.h1, sm.wB, kH1, kH2, m_used, [&](int m0, int n0, float (&acc)[4][4]) {
+#pragma unroll
+                for (int j = 0; j < 4; ++j)
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) acc[i][j] = fmaxf(acc[i][j] + b2[n0 + j], 0.f);
+                store_tile_kmajor<4>(sm.h2, kRows, m0, n0, acc);
+            });
+            __syncthreads();
+            // layer 3 (32 -> 1) and the two ReLU masks as bits
+            if (tid < n_rows) {
+                const int m = tid;
+                float sc = b3;
+                uint32_t m2 = 0, m1a = 0, m1b = 0;
+#pragma unroll 8
+                for (int n = 0; n < kH2; ++n) {
+                    const float h = sm.h2[n * kRows + m];
+                    sc = fmaf(h, w3[n], sc);
+                    m2 |= (h > 0.f ? 1u : 0u) << n;
+                }
+#pragma unroll 8
+                for (int n = 0; n < 32; ++n) {
+                    m1a |= (sm.h1[n * kRows + m] > 0.f ? 1u : 0u) << n;
+                    m1b |= (sm.h1[(32 + n) * kRows + m] > 0.f ? 1u : 0u) << n;
+                }
+                sm.score[m] = sc;
+                if (masks) {
+                    uint32_t* mk = masks + ((b0 + sm.row_s[m]) * T + sm.row_t[m]) * 3;
+                    mk[0] = m1a; mk[1] = m1b; mk[2] = m2;
+                }
+            }
+            __syncthreads();
+        }
+        // ---- pooling: one warp per sample of the tile
+        for (int s = s_begin + warp; s < s_end; s += kDinThreads / 32) {
+            const int len = sm.len[s], r0 = sm.start[s - s_begin];
+            float* wrow = att_w + (b0 + s) * T;
+            float* out  = concat_all + (b0 + s) * p.width + p.att_off;
+            if (len == 0) {
+                if (!p.use_softmax) {
+                    for (int t = lane; t < T; t += 32) wrow[t] = 0.f;
+                    for (int e = lane; e < D; e += 32) { out[e] = 0.f; sm.gatt[s * D + e] = 0.f; }
+                } else {  // uniform 1/T over ALL positions (they all hold the padding score)
+                    const float u = 1.0f / (float)T;
+                    for (int t = lane; t < T; t += 32) wrow[t] = u;
+                    for (int e = 0; e < D; ++e) {
+                        float a = 0.f;
+                        for (int t = lane; t < T; t += 32) {
+                            const int64_t row = checked_row(__ldg(p.his_idx + (b0 + s) * T + t), p.his_rows, err_flag);
+                            a = fmaf(u, __ldg(p.his_w + row * D + e), a);
+                        }
+                        a = warp_sum(a);
+                        if (lane == 0) { out[e] = a; sm.gatt[s * D + e] = a; }
+                    }
+                }
+                continue;
+            }
+            float inv_sum = 1.f, mx = 0.f;
+            if (p.use_softmax) {
+                mx = -INFINITY;
+                for (int t = lane; t < len; t += 32) mx = fmaxf(mx, sm.score[r0 + t] * inv_sqrt_d);
+                mx = warp_max(mx);
+                float sum = 0.f;
+                for (int t = lane; t < len; t += 32) sum += expf(sm.score[r0 + t] * inv_sqrt_d - mx);
+                inv_sum = 1.0f / warp_sum(sum);
+            }
+            for (int t = lane; t < T; t += 32) {
+                float w = 0.f;
+                if (t < len) {
+                    w = p.use_softmax ? expf(sm.score[r0 + t] * inv_sqrt_d - mx) * inv_sum : sm.score[r0 + t];
+                    sm.gw[r0 + t] = w;
+                }
+                wrow[t] = w;
+            }
+            __syncwarp();
+            for (int e = 0; e < D; ++e) {
+                float a = 0.f;
+                for (int t = lane; t < len; t += 32) a = fmaf(sm.gw[r0 + t], sm.x[(D + e) * kRows + r0 + t], a);
+                a = warp_sum(a);
+                if (lane == 0) { out[e] = a; sm.gatt[s * D + e] = a; }
+            }
+        }
+        __syncthreads();
+        s_begin = s_end;
+    }
+
+    // ---- assemble the rest of the concat row and the L2 norm: one warp per sample
+    for (int s = warp; s < n_samples; s += kDinThreads / 32) {
+        const int64_t b = b0 + s;
+        float* out = concat_all + b * p.width;
+        float ss = 0.f;
+        for (int c = lane; c < p.width; c += 32) {
+            float v;
+            if (c < p.n_dense) {
+                v = __ldg(p.dense_col[c] + b * p.dense_stride);
+                out[c] = v;
+            } else if (c >= p.att_off && c < p.att_off + D) {
+                v = sm.gatt[s * D + c - p.att_off];        // pooled above (kept in shared memory)
+            } else if (c >= p.tgt_off && c < p.tgt_off + D) {
+                v = sm.q[s * D + c - p.tgt_off];
+                out[c] = v;
+            } else {
+                v = 0.f;
+                for (int f = 0; f < p.cat.F; ++f)
+                    if (c >= p.cat.off[f] && c < p.cat.off[f] + p.cat.dim[f]) {
+                        const int64_t row = checked_row(__ldg(p.cat.idx[f] + b), p.cat.rows[f], err_flag);
+                        v = __ldg(p.cat.weight[f] + row * p.cat.dim[f] + c - p.cat.off[f]);
+                    }
+                out[c] = v;
+            }
+            if (c >= p.l2_from) ss = fmaf(v, v, ss);
+        }
+        ss = warp_sum(ss);
+        if (lane == 0 && norm_out) norm_out[b] = sqrtf(ss);
+    }
+}
+
+// Backward.  g_row[B,width]: gradient w.r.t. every column of the concat row INCLUDING what flows
+// back through the attention into q (target columns) — these are the per-occurrence gradients of
+// the category / target tables.  g_hist[B,T,D]: per-occurrence gradients of the history table
+// (written for live positions only).
+__global__ void __launch_bounds__(kDinThreads)
+din_bwd_kernel(const __grid_constant__ DinParams p, const float* __restrict__ concat_all,
+               const float* __restrict__ norm, const float* __restrict__ att_w,
+               const uint32_t* __restrict__ masks, const float* __restrict__ g_concat,
+               const float* __restrict__ g_norm, float* __restrict__ g_row,
+               float* __restrict__ g_hist, int32_t* err_flag) {
+    extern __shared__ __align__(16) float smem_raw[];
+    const int D = p.D, K1 = 4 * D, T = p.T;
+    DinSmem sm(smem_raw, D);
+    const MlpLayout L(D);
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int64_t b0 = (int64_t)blockIdx.x * kSamples;
+    const int n_samples = (int)((p.B - b0) < kSamples ? (p.B - b0) : kSamples);
+
+    // weights in their registered orientation: B operands of the transposed products
+    for (int i = tid; i < kH1 * K1; i += kDinThreads) sm.wA[i] = __ldg(p.mlp + L.w1 + i);   // [64][K1]
+    for (int i = tid; i < kH2 * kH1; i += kDinThreads) sm.wB[i] = __ldg(p.mlp + L.w2 + i);  // [32][64]
+    for (int i = tid; i < kH2; i += kDinThreads) sm.vec[i] = __ldg(p.mlp + L.w3 + i);
+    if (tid < kSamples) sm.len[tid] = tid < n_samples ? clip_len(__ldg(p.his_len + b0 + tid), T) : 0;
+    // per sample: q, and g_att = upstream gradient of the attention output (tower + L2 term)
+    for (int i = tid; i < n_samples * D; i += kDinThreads) {
+        const int s = i / D, e = i - s * D;
+        const int64_t b = b0 + s;
+        sm.q[i] = concat_all[b * p.width + p.tgt_off + e];
+        float g = g_concat ? g_concat[b * p.width + p.att_off + e] : 0.f;
+        if (g_norm) {
+            const float nv = norm[b];
+            if (nv > 0.f) g = fmaf(g_norm[b] / nv, concat_all[b * p.width + p.att_off + e], g);
+        }
+        sm.gatt[i] = g;
+        sm.gq[i]   = 0.f;
+    }
+    __syncthreads();
+    const float* w3 = sm.vec;
+    const float  inv_sqrt_d = 1.0f / sqrtf((float)D);
+
+    int s_begin = 0;
+    while (s_begin < n_samples) {
+        int s_end;
+        const int n_rows = plan_tile(sm, n_samples, s_begin, &s_end);
+        if (tid < kSamples + 1) {
+            int acc = 0;
+            for (int s = s_begin; s < s_begin + tid && s < s_end; ++s) acc += sm.len[s];
+            sm.start[tid] = acc;
+        }
+        __syncthreads();
+        for (int m = tid; m < kRows; m += kDinThreads) {
+            int s = s_begin;
+            while (s + 1 < s_end && m >= sm.start[s + 1 - s_begin]) ++s;
+            sm.row_s[m] = s;
+            sm.row_t[m] = m - sm.start[s - s_begin];
+        }
+        __syncthreads();
+        if (n_rows > 0) {
+            stage_rows<false>(p, sm, b0, n_rows, err_flag);      // K rows -> x[D..2D)
+            __syncthreads();
+            // g_w[row] = g_att . k_row ; load w_t and the ReLU masks
+            if (tid < kRows) {
+                const int m = tid;
+                float gw = 0.f, w = 0.f;
+                uint32_t k0 = 0, k1 = 0, k2 = 0;
+                if (m < n_rows) {
+                    const int s = sm.row_s[m], t = sm.row_t[m];
+                    for (int e = 0; e < D; ++e) gw = fmaf(sm.gatt[s * D + e], sm.x[(D + e) * kRows + m], gw);
+                    w = att_w[(b0 + s) * T + t];
+                    const uint32_t* mk = masks + ((b0 + s) * T + t) * 3;
+                    k0 = mk[0]; k1 = mk[1]; k2 = mk[2];
+                }
+                sm.gw[m] = gw;
+                sm.score[m] = w;
+                sm.mask[m] = k0; sm.mask[kRows + m] = k1; sm.mask[2 * kRows + m] = k2;
+            }
+            __syncthreads();
+            // softmax backward needs sum_u w_u g_w_u per sample (warp per sample)
+            if (p.use_softmax) {
+                for (int s = s_begin + warp; s < s_end; s += kDinThreads / 32) {
+                    const int len = sm.len[s], r0 = sm.start[s - s_begin];
+                    float dot = 0.f;
+                    for (int t = lane; t < len; t += 32) dot = fmaf(sm.score[r0 + t], sm.gw[r0 + t], dot);
+                    dot = warp_sum(dot);
+                    for (int t = lane; t < len; t += 32)
+                        sm.gw[r0 + t] = sm.score[r0 + t] * (sm.gw[r0 + t] - dot) * inv_sqrt_d;
+                }
+                __syncthreads();
+            }
+            // g_z2[n][m] = g_s[m] * w3[n] * relu2'  -> h2 region
+            if (tid < kRows) {
+                const int m = tid;
+                const float gs = m < n_rows ? sm.gw[m] : 0.f;
+                const uint32_t k2 = sm.mask[2 * kRows + m];
+#pragma unroll 8
+                for (int n = 0; n < kH2; ++n) sm.h2[n * kRows + m] = ((k2 >> n) & 1u) ? gs * w3[n] : 0.f;
+            }
+            __syncthreads();
+            const int m_used = (n_rows + 3) / 4 * 4;
+            // g_z1 = (g_z2 x W2) * relu1'   [rows,32]x[32,64]
+            tile_gemm_rows<8>(sm.h2, sm.wB, kH2, kH1, m_used, [&](int m0, int n0, float (&acc)[4][8]) {
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    const uint32_t bits = sm.mask[(n0 >> 5) * kRows + m0 + i] >> (n0 & 31);
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) acc[i][j] = ((bits >> j) & 1u) ? acc[i][j] : 0.f;
+                }
+                store_tile_kmajor<8>(sm.h1, kRows, m0, n0, acc);
+            });
+            __syncthreads();
+            // g_cross = g_z1 x W1   [rows,64]x[64,4D]  -> reuse x[0..D) and x[2D..4D) ... keep K rows:
+            // write g_cross into a scratch that does not overlap x[D..2D): use h-major temp in h1? no:
+            // h1 is this product's A operand.  g_cross goes to x rows {0..D) U [2D,4D) directly and its
+            // k-block [D,2D) into h2 (free now, D <= 32 rows).
+            tile_gemm_rows<4>(sm.h1, sm.wA, kH1, K1, m_used, [&](int m0, int n0, float (&acc)[4][4]) {
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const int c = n0 + j;
+                    float* dst = (c >= D && c < 2 * D) ? sm.h2 + (c - D) * kRows : sm.x + c * kRows;
+                    *reinterpret_cast<float4*>(dst + m0) = make_float4(acc[0][j], acc[1][j], acc[2][j], acc[3][j]);
+                }
+            });
+            __syncthreads();
+            // per row: g_k = w_t g_att + gc_k - gc_d + gc_p * q ; g_q_row = gc_q + gc_d + gc_p * k
+            for (int item = tid; item < D * kRows; item += kDinThreads) {
+                const int e = item / kRows, m = item - e * kRows;
+                if (m < n_rows) {
+                    const int s = sm.row_s[m], t = sm.row_t[m];
+                    const float k  = sm.x[(D + e) * kRows + m];
+                    const float q  = sm.q[s * D + e];
+                    const float gq = sm.x[e * kRows + m];
+                    const float gk = sm.h2[e * kRows + m];
+                    const float gd = sm.x[(2 * D + e) * kRows + m];
+                    const float gp = sm.x[(3 * D + e) * kRows + m];
+                    const float w  = sm.score[m];
+                    // overwrite x[e] with this row's contribution to g_q; the K row with g_k
+                    sm.x[e * kRows + m]       = gq + gd + gp * k;
+                    sm.x[(D + e) * kRows + m] = fmaf(w, sm.gatt[s * D + e], gk - gd + gp * q);
+                    (void)t;
+                }
+            }
+            __syncthreads();
+            // write g_k rows (coalesced over e inside a row) and reduce g_q over each sample's rows
+            for (int item = tid; item < (D / 4) * kRows; item += kDinThreads) {
+                const int c4 = item / kRows, m = item - c4 * kRows;
+                if (m < n_rows) {
+                    const float* src = sm.x + (D + 4 * c4) * kRows + m;
+                    *reinterpret_cast<float4*>(g_hist + ((b0 + sm.row_s[m]) * T + sm.row_t[m]) * D + 4 * c4) =
+                        make_float4(src[0], src[kRows], src[2 * kRows], src[3 * kRows]);
+                }
+            }
+            for (int s = s_begin + warp; s < s_end; s += kDinThreads / 32) {
+                const int len = sm.len[s], r0 = sm.start[s - s_begin];
+                for (int e = 0; e < D; ++e) {
+                    float a = 0.f;
+                    for (int t = lane; t < len; t += 32) a += sm.x[e * kRows + r0 + t];
+                    a = warp_sum(a);
+                    if (lane == 0) sm.gq[s * D + e] = a;
+                }
+            }
+            __syncthreads();
+        }
+        // samples with no history in softmax mode: uniform weights, gradient g_att / T everywhere
+        if (p.use_softmax) {
+            for (int s = s_begin; s < s_end; ++s) {
+                if (sm.len[s] != 0) continue;
+                const float u = 1.0f / (float)T;
+                for (int i = tid; i < T * D; i += kDinThreads)
+                    g_hist[(b0 + s) * T * D + i] = u * sm.gatt[s * D + (i % D)];
+            }
+        }
+        __syncthreads();
+        s_begin = s_end;
+    }
+
+    // ---- gradient of the concat row: tower gradient + L2 term (+ attention's d/dq on the target)
+    for (int s = warp; s < n_samples; s += kDinThreads / 32) {
+        const int64_t b = b0 + s;
+        float scale = 0.f;
+        if (g_norm) {
+            const float nv = norm[b];
+            scale = nv > 0.f ? g_norm[b] / nv : 0.f;
+        }
+        for (int c = lane; c < p.width; c += 32) {
+            float g = g_concat ? g_concat[b * p.width + c] : 0.f;
+            if (c >= p.l2_from) g = fmaf(scale, concat_all[b * p.width + c], g);
+            if (c >= p.tgt_off && c < p.tgt_off + D) g += sm.gq[s * D + c - p.tgt_off];
+            g_row[b * p.width + c] = g;
+        }
+    }
+}
+
+}  // namespace rk
+
+extern "C" {
+
+int rk_din_mlp_floats(int D) { return rk::MlpLayout(D).total; }
+
+static int din_pack(const rk_din_args_t* a, rk::DinParams* p) {
+    using namespace rk;
+    RK_CHECK_ARG(a, "din: args is NULL");
+    memset(p, 0, sizeof(*p));
+    if (int rc = pack_fields(a->cat, a->n_cat, &p->cat)) return rc;
+    RK_CHECK_ARG(a->n_dense >= 0 && a->n_dense <= kMaxDense, "din: n_dense=%d", a->n_dense);
+    for (int c = 0; c < a->n_dense; ++c) {
+        RK_CHECK_ARG(a->dense_cols && a->dense_cols[c], "din: dense column %d is NULL", c);
+        p->dense_col[c] = a->dense_cols[c];
+    }
+    p->dense_stride = a->dense_stride;
+    p->n_dense = a->n_dense;
+    const int D = a->history.dim;
+    RK_CHECK_ARG(D >= 4 && D <= 32 && D % 4 == 0, "din: embedding dim %d not in {4,8,..,32}", D);
+    RK_CHECK_ARG(a->target.dim == D, "din: target dim %d != history dim %d", a->target.dim, D);
+    RK_CHECK_ARG(a->T >= 1 && a->T <= kRows, "din: history length %d outside [1,%d]", a->T, kRows);
+    RK_CHECK_ARG(a->target.weight && a->target.idx && a->history.weight && a->history.idx && a->hist_len && a->mlp,
+                 "din: NULL pointer");
+    RK_CHECK_ARG(((uintptr_t)a->history.weight % 16) == 0, "din: history table must be 16-byte aligned");
+    p->tgt_w = a->target.weight;   p->tgt_idx = a->target.idx;   p->tgt_rows = a->target.rows;
+    p->tgt_off = a->target.out_off;
+    p->his_w = a->history.weight;  p->his_idx = a->history.idx;  p->his_rows = a->history.rows;
+    p->his_len = a->hist_len;
+    p->T = a->T;  p->D = D;  p->att_off = a->att_off;  p->width = a->width;
+    p->l2_from = a->l2_from;  p->use_softmax = a->use_softmax;
+    p->mlp = a->mlp;  p->B = a->B;
+    RK_CHECK_ARG(p->width > 0 && p->att_off + D <= p->width && p->tgt_off + D <= p->width, "din: bad layout");
+    return 0;
+}
+
+static int din_smem(int D, size_t* bytes, const void* kernel) {
+    using namespace rk;
+    *bytes = DinSmem::bytes(D);
+    RK_CHECK_ARG(*bytes <= 227 * 1024, "din: %zu bytes of shared memory", *bytes);
+    RK_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)*bytes));
+    return 0;
+}
+
+int rk_din_fwd(const rk_din_args_t* args, float* concat_all, float* norm, float* att_w,
+               uint32_t* relu_masks, int32_t* err_flag, rk_stream_t stream_) {
+    using namespace rk;
+    DinParams p;
+    if (int rc = din_pack(args, &p)) return rc;
+    RK_CHECK_ARG(concat_all && att_w, "din_fwd: NULL output");
+    if (p.B == 0) return 0;
+    size_t smem;
+    if (int rc = din_smem(p.D, &smem, (const void*)din_fwd_kernel)) return rc;
+    const int grid = (int)ceil_div(p.B, kSamples);
+    din_fwd_kernel<<<grid, kDinThreads, smem, (cudaStream_t)stream_>>>(p, concat_all, norm, att_w,
+                                                                       relu_masks, err_flag);
+    RK_LAUNCH_CHECK();
+    return 0;
+}
+
+int rk_din_bwd(const rk_din_args_t* args, const float* concat_all, const float* norm,
+               const float* att_w, const uint32_t* relu_masks, const float* g_concat,
+               const float* g_norm, float* g_row, float* g_hist, int32_t* err_flag,
+               rk_stream_t stream_) {
+    using namespace rk;
+    DinParams p;
+    if (int rc = din_pack(args, &p)) return rc;
+    RK_CHECK_ARG(concat_all && att_w && relu_masks && g_row && g_hist, "din_bwd: NULL pointer");
+    RK_CHECK_ARG(!g_norm || norm, "din_bwd: g_norm without the saved norms");
+    if (p.B == 0) return 0;
+    size_t smem;
+    if (int rc = din_smem(p.D, &smem, (const void*)din_bwd_kernel)) return rc;
+    const int grid = (int)ceil_div(p.B, kSamples);
+    din_bwd_kernel<<<grid, kDinThreads, smem, (cudaStream_t)stream_>>>(
+        p, concat_all, norm, att_w, relu_masks, g_concat, g_norm, g_row, g_hist, err_flag);
+    RK_LAUNCH_CHECK();
+    return 0;
+}
+
+}  // extern "C"

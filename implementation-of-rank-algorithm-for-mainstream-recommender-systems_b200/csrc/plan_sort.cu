@@ -19,6 +19,9 @@ constexpr int kBins        = 256;
 
 struct KeyBuild {
     const int64_t* idx[RK_MAX_FIELDS];
+    const int64_t* len[RK_MAX_FIELDS];        // sequence fields: per-sample length, else NULL
+    int32_t        T[RK_MAX_FIELDS];          // positions per sample of a sequence field
+    int32_t        mode[RK_MAX_FIELDS];       // RK_LIVE_*
     int64_t        start[RK_MAX_FIELDS + 1];  // first occurrence of field f in the flat order
     int64_t        rows[RK_MAX_FIELDS];
     uint32_t       key_base[RK_MAX_FIELDS];
@@ -35,7 +38,14 @@ build_keys_kernel(const __grid_constant__ KeyBuild kb, uint32_t* __restrict__ ke
 #pragma unroll 1
         while (f + 1 < kb.F && i >= kb.start[f + 1]) ++f;
         const int64_t o   = i - kb.start[f];
-        const int64_t row = checked_row(kb.idx[f][o], kb.rows[f], err_flag);
+        int64_t row = checked_row(kb.idx[f][o], kb.rows[f], err_flag);
+        if (kb.mode[f] != RK_LIVE_ALL) {
+            // padded history positions carry no gradient: park them on the field's sentinel row
+            const int64_t b = o / kb.T[f], t = o - b * kb.T[f];
+            const int64_t l = kb.len[f][b];
+            const bool dead = t >= l && !(kb.mode[f] == RK_LIVE_PREFIX_OR_EMPTY && l <= 0);
+            if (dead) row = kb.rows[f];
+        }
         keys[i] = kb.key_base[f] + (uint32_t)row;
         vals[i] = (uint32_t)o;
     }
@@ -167,6 +177,7 @@ size_t rk_plan_workspace_bytes(int64_t n_total) {
 }
 
 int rk_plan_build(const int64_t* const* idx, const int64_t* n, const int64_t* rows, int F,
+                  const int64_t* const* seq_len, const int32_t* seq_T, const int32_t* live_mode,
                   uint32_t* sorted_keys, uint32_t* perm, void* ws, size_t ws_bytes,
                   int32_t* err_flag, rk_stream_t stream_) {
     using namespace rk;
@@ -186,8 +197,17 @@ int rk_plan_build(const int64_t* const* idx, const int64_t* n, const int64_t* ro
         kb.start[f]    = total;
         kb.rows[f]     = rows[f];
         kb.key_base[f] = (uint32_t)space;
+        kb.mode[f]     = live_mode ? live_mode[f] : RK_LIVE_ALL;
+        if (kb.mode[f] != RK_LIVE_ALL) {
+            RK_CHECK_ARG(kb.mode[f] == RK_LIVE_PREFIX || kb.mode[f] == RK_LIVE_PREFIX_OR_EMPTY,
+                         "rk_plan_build: field %d live_mode %d", f, kb.mode[f]);
+            RK_CHECK_ARG(seq_len && seq_len[f] && seq_T && seq_T[f] > 0 && n[f] % seq_T[f] == 0,
+                         "rk_plan_build: field %d needs lengths and T dividing n", f);
+            kb.len[f] = seq_len[f];
+            kb.T[f]   = seq_T[f];
+        }
         total += n[f];
-        space += rows[f];
+        space += rows[f] + 1;   // +1: the sentinel row of dead occurrences sorts last in the field
     }
     kb.start[F] = total;
     RK_CHECK_ARG(total < (1ll << 31) && space < (1ll << 32),

@@ -23,7 +23,9 @@ struct ReduceJob {
     int64_t      seg_start;   // first sorted position of the field
     int64_t      n;           // occurrences of the field
     int64_t      thread_start;
+    int64_t      warp_start;  // combine pass: first warp of this table
     uint32_t     key_base;
+    uint32_t     dead_key;    // key_base + rows: occurrences that carry no gradient
     int32_t      dim;
     int32_t      lanes;
     int32_t      vec;
@@ -31,6 +33,7 @@ struct ReduceJob {
 struct ReduceParams {
     ReduceJob job[RK_MAX_TABLES];
     int64_t   total_threads;
+    int64_t   total_warps;
     int32_t   n_tables;
 };
 
@@ -44,6 +47,7 @@ __device__ __forceinline__ void reduce_chunk(const ReduceJob& jb, const uint32_t
     const uint32_t* K  = keys + pos0;
     const uint32_t* P  = perm + pos0;
     uint32_t cur  = K[0];
+    if (cur == jb.dead_key) return;   // sorted: the whole chunk is padding
     bool     lead = (c > 0) && (keys[pos0 - 1] == cur);
     Vec<V>   acc;
     vec_zero(acc);
@@ -68,6 +72,7 @@ __device__ __forceinline__ void reduce_chunk(const ReduceJob& jb, const uint32_t
                     lead = false;
                     vec_zero(acc);
                     cur = kk[u];
+                    if (cur == jb.dead_key) return;   // rest of the chunk is padding
                 }
 #pragma unroll
                 for (int e = 0; e < V; ++e) acc.v[e] += vv[u].v[e];
@@ -100,8 +105,10 @@ segment_chunk_kernel(const __grid_constant__ ReduceParams p, const uint32_t* __r
     else                  reduce_chunk<1>(jb, keys, perm, c, lane);
 }
 
-// Second pass: the chunk that holds the head of a row spilling into later chunks adds their
-// lead partials, left to right.
+// Second pass, one warp per chunk: the chunk that holds the head of a row spilling into later
+// chunks adds their lead partials.  The end of the run is found by binary search on the sorted
+// keys; the partials are summed by RL row-lanes in a fixed interleaved order and folded with a
+// fixed shuffle tree, so the result does not depend on scheduling.
 template <int V>
 __device__ __forceinline__ void combine_chunk(const ReduceJob& jb, const uint32_t* __restrict__ keys,
                                               int64_t c, int lane) {
@@ -111,37 +118,59 @@ __device__ __forceinline__ void combine_chunk(const ReduceJob& jb, const uint32_
     const int64_t last     = pos0 + cnt - 1;
     if (c + 1 >= n_chunks) return;
     const uint32_t k = keys[last];
-    if (keys[last + 1] != k) return;  // last row of the chunk ends here
+    if (k == jb.dead_key || keys[last + 1] != k) return;   // nothing spills out of this chunk
     const bool head_here = (keys[pos0] != k) || c == 0 || keys[pos0 - 1] != k;
     if (!head_here) return;
-    const int col = lane * V;
-    float*    out = jb.dw + (int64_t)(k - jb.key_base) * jb.dim + col;
-    Vec<V>    acc;
-    acc.load_plain(out);
-#pragma unroll 1
-    for (int64_t cc = c + 1; cc < n_chunks; ++cc) {
-        const int64_t p0 = jb.seg_start + cc * kChunk;
-        if (keys[p0] != k) break;
-        Vec<V> part;
-        part.load_plain(jb.lead + cc * (int64_t)jb.dim + col);
-#pragma unroll
-        for (int e = 0; e < V; ++e) acc.v[e] += part.v[e];
-        const int64_t rem = jb.n - cc * kChunk;
-        const int64_t l2  = p0 + (rem < kChunk ? rem : kChunk) - 1;
-        if (keys[l2] != k) break;
+    // chunks c+1 .. c_last start with key k (predicate is monotone over the sorted keys)
+    int64_t lo = c + 1, hi = n_chunks - 1;
+    while (lo < hi) {
+        const int64_t mid = (lo + hi + 1) >> 1;
+        if (keys[jb.seg_start + mid * kChunk] == k) lo = mid; else hi = mid - 1;
     }
-    acc.store(out);
+    const int64_t c_last = lo;
+    const int CL = jb.lanes;                       // column lanes (dim / V)
+    int RL = 1;
+    while (RL * 2 * CL <= 32) RL *= 2;             // row lanes, power of two
+    const int rl = lane / CL, cl = lane - rl * CL;
+    const bool on = rl < RL;
+    Vec<V> acc;
+    vec_zero(acc);
+    if (on) {
+        for (int64_t cc = c + 1 + rl; cc <= c_last; cc += RL) {
+            Vec<V> part;
+            part.load_plain(jb.lead + cc * (int64_t)jb.dim + cl * V);
+#pragma unroll
+            for (int e = 0; e < V; ++e) acc.v[e] += part.v[e];
+        }
+    }
+    for (int o = RL >> 1; o > 0; o >>= 1) {
+#pragma unroll
+        for (int e = 0; e < V; ++e) {
+            const float other = __shfl_down_sync(kFull, acc.v[e], o * CL);
+            if (on && rl < o) acc.v[e] += other;
+        }
+    }
+    if (on && rl == 0) {
+        float* out = jb.dw + (int64_t)(k - jb.key_base) * jb.dim + cl * V;
+        Vec<V> own;
+        own.load_plain(out);
+#pragma unroll
+        for (int e = 0; e < V; ++e) own.v[e] += acc.v[e];
+        own.store(out);
+    }
 }
 
 __global__ void __launch_bounds__(256)
 segment_combine_kernel(const __grid_constant__ ReduceParams p, const uint32_t* __restrict__ keys) {
-    const int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
-    if (t >= p.total_threads) return;
-    const ReduceJob& jb = p.job[find_job(p, t)];
-    const int64_t local = t - jb.thread_start;
-    const int64_t c     = local / jb.lanes;
-    const int     lane  = (int)(local - c * jb.lanes);
+    const int64_t w = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
+    if (w >= p.total_warps) return;
+    int j = 0;
+#pragma unroll 1
+    while (j + 1 < p.n_tables && w >= p.job[j + 1].warp_start) ++j;
+    const ReduceJob& jb = p.job[j];
+    const int64_t c = w - jb.warp_start;
     if (c * kChunk >= jb.n) return;
+    const int lane = threadIdx.x & 31;
     if (jb.vec == 4)      combine_chunk<4>(jb, keys, c, lane);
     else if (jb.vec == 2) combine_chunk<2>(jb, keys, c, lane);
     else                  combine_chunk<1>(jb, keys, c, lane);
@@ -184,7 +213,7 @@ int rk_embgrad_segment_reduce(const uint32_t* sorted_keys, const uint32_t* perm,
         start[f] = tot;
         base[f]  = (uint32_t)space;
         tot += n[f];
-        space += rows[f];
+        space += rows[f] + 1;   // same key space as rk_plan_build (one sentinel row per field)
     }
     if (tot == 0) return 0;
     RK_CHECK_ARG(sorted_keys && perm && ws, "segment_reduce: NULL device pointer");
@@ -192,7 +221,7 @@ int rk_embgrad_segment_reduce(const uint32_t* sorted_keys, const uint32_t* perm,
     ReduceParams p;
     memset(&p, 0, sizeof(p));
     p.n_tables = 0;
-    int64_t threads = 0;
+    int64_t threads = 0, warps = 0;
     size_t  ws_off  = 0;
     for (int t = 0; t < n_tables; ++t) {
         const rk_grad_table_t& tb = tables[t];
@@ -213,21 +242,25 @@ int rk_embgrad_segment_reduce(const uint32_t* sorted_keys, const uint32_t* perm,
         jb.dim          = tb.dim;
         jb.vec          = v;
         jb.lanes        = tb.dim / v;
+        RK_CHECK_ARG(jb.lanes <= 32, "segment_reduce: table %d dim %d too wide", t, tb.dim);
         jb.seg_start    = start[f];
         jb.n            = n[f];
         jb.key_base     = base[f];
+        jb.dead_key     = base[f] + (uint32_t)rows[f];
+        jb.warp_start   = warps;
         jb.lead         = (float*)((char*)ws + ws_off);
         jb.thread_start = threads;
         const int64_t chunks = ceil_div(n[f], kChunk);
         ws_off += ((size_t)chunks * tb.dim * 4 + 255) & ~(size_t)255;
         threads += ceil_div(chunks * jb.lanes, 32) * 32;  // keep warps inside one table
+        warps += chunks;
     }
     p.total_threads = threads;
+    p.total_warps   = warps;
     if (threads == 0) return 0;
-    const int grid = (int)ceil_div(threads, 256);
-    segment_chunk_kernel<<<grid, 256, 0, s>>>(p, sorted_keys, perm);
+    segment_chunk_kernel<<<(int)ceil_div(threads, 256), 256, 0, s>>>(p, sorted_keys, perm);
     RK_LAUNCH_CHECK();
-    segment_combine_kernel<<<grid, 256, 0, s>>>(p, sorted_keys);
+    segment_combine_kernel<<<(int)ceil_div(warps * 32, 256), 256, 0, s>>>(p, sorted_keys);
     RK_LAUNCH_CHECK();
     return 0;
 }

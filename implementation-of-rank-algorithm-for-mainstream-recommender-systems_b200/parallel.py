@@ -31,10 +31,12 @@ class GradientAllReducer:
     def world_size(self):
         return dist.get_world_size(self.group)
 
-    def allreduce(self):
-        """Average every parameter's .grad over the ranks (call after backward)."""
-        have = [(v, p.grad) for v, p in zip(self.views, self.params) if p.grad is not None]
-        missing = [v for v, p in zip(self.views, self.params) if p.grad is None]
+    def allreduce(self, grads=None):
+        """Average every parameter's gradient over the ranks (call after backward).  `grads`
+        (default: each parameter's .grad) lets a CUDA-graph step pass its static tensors."""
+        grads = [p.grad for p in self.params] if grads is None else list(grads)
+        have = [(v, g) for v, g in zip(self.views, grads) if g is not None]
+        missing = [v for v, g in zip(self.views, grads) if g is None]
         if have:
             torch._foreach_copy_([v for v, _ in have], [g for _, g in have])
         for v in missing:

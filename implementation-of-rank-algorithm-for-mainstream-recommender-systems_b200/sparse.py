@@ -57,7 +57,9 @@ class GradSource:
 class OccurrencePlan:
     """Sorted order of all index occurrences of a batch (one entry per field)."""
 
-    def __init__(self, indices: list[torch.Tensor], rows: list[int]):
+    def __init__(self, indices: list[torch.Tensor], rows: list[int], seq_len=None, live_mode=None):
+        """`seq_len[f]` (int64 [B]) and `live_mode[f]` (_lib.LIVE_*) mark field f as a padded
+        sequence field whose dead positions are left out of the reduction."""
         lib = _lib.load()
         self.F = len(indices)
         if not 1 <= self.F <= _lib.RK_MAX_FIELDS:
@@ -74,8 +76,17 @@ class OccurrencePlan:
         ws_bytes = lib.rk_plan_workspace_bytes(total)
         ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
         idx_ptrs = (C.c_void_p * self.F)(*[i.data_ptr() for i in self.indices])
+        len_ptrs = seq_T = modes = None
+        if live_mode is not None and any(live_mode):
+            lens = [None if m == _lib.LIVE_ALL else _lib.require_cuda(l, f"seq_len[{k}]", torch.int64)
+                    for k, (l, m) in enumerate(zip(seq_len, live_mode))]
+            self._lens = lens
+            len_ptrs = (C.c_void_p * self.F)(*[None if l is None else l.data_ptr() for l in lens])
+            seq_T = (C.c_int32 * self.F)(*[0 if l is None else self.n[k] // max(int(l.numel()), 1)
+                                           for k, l in enumerate(lens)])
+            modes = (C.c_int32 * self.F)(*[int(m) for m in live_mode])
         rc = lib.rk_plan_build(idx_ptrs, _i64_array(self.n), _i64_array(self.rows), self.F,
-                               self.sorted_keys.data_ptr(), self.perm.data_ptr(),
+                               len_ptrs, seq_T, modes, self.sorted_keys.data_ptr(), self.perm.data_ptr(),
                                ws.data_ptr(), ws_bytes, _lib.err_flag(dev).data_ptr(),
                                _lib.stream_ptr())
         _lib.check(rc, "rk_plan_build")

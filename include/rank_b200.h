@@ -56,6 +56,9 @@ typedef struct rk_grad_table {
 int         rk_version(void);
 const char* rk_last_error(void);
 int         rk_device_sm_count(void);
+/* Measurement aid (bench.py): occupy `stream` for `us` microseconds (<= 100 ms) so the host can
+ * queue a step behind it and CUDA events around each call then see device time only. */
+int         rk_debug_spin(int us, rk_stream_t stream);
 long long   rk_launch_count(void);   /* kernels launched through this library so far (process-wide) */
 
 /* ---- sparse embedding-gradient reduction (autograd of nn.Embedding: embedding_dense_backward,
@@ -64,9 +67,17 @@ long long   rk_launch_count(void);   /* kernels launched through this library so
  * later reduction sums each row's gradients in occurrence order: deterministic, no atomics.
  *   idx[f]  device pointer to n[f] int64 indices, rows[f] = table height      (host arrays)
  *   sorted_keys[n_total], perm[n_total] : outputs (uint32); perm holds the occurrence number
- *   inside its field.  ws: scratch of rk_plan_workspace_bytes(n_total). */
+ *   inside its field.  ws: scratch of rk_plan_workspace_bytes(n_total).
+ *   Sequence fields may drop padded positions, whose gradient is identically zero, from the
+ *   reduction: live_mode[f] = RK_LIVE_PREFIX keeps t < seq_len[f][b] of every sample b (n[f] =
+ *   B*seq_T[f]); RK_LIVE_PREFIX_OR_EMPTY also keeps every t of samples with length 0 (DIN's
+ *   softmax mode gives those uniform weights).  seq_len/seq_T/live_mode may be NULL (all live). */
+#define RK_LIVE_ALL 0
+#define RK_LIVE_PREFIX 1
+#define RK_LIVE_PREFIX_OR_EMPTY 2
 size_t rk_plan_workspace_bytes(int64_t n_total);
 int rk_plan_build(const int64_t* const* idx, const int64_t* n, const int64_t* rows, int F,
+                  const int64_t* const* seq_len, const int32_t* seq_T, const int32_t* live_mode,
                   uint32_t* sorted_keys, uint32_t* perm, void* ws, size_t ws_bytes,
                   int32_t* err_flag, rk_stream_t stream);
 /* ws for the reduction: rk_reduce_workspace_bytes(sum over tables of ceil(n/16)*dim floats). */
@@ -113,6 +124,47 @@ int rk_cross_layer_fwd(const float* x0, const float* xl, const float* w, const f
                        int64_t B, float* out, rk_stream_t stream);
 int rk_cross_layer_bwd(const float* x0, const float* xl, const float* w, int d, int64_t B,
                        const float* g_out, float* g_x0, float* g_xl, rk_stream_t stream);
+
+/* ---- DIN (DIN.forward DIN/din.py:294-323, din_attention :42-84) ----------------------------
+ * One launch does every gather, the local activation unit on the history positions t < len,
+ * the masked raw / scaled-softmax pooling, the concat and the per-sample L2 norm.
+ *   concat_all[B,width] = [dense | cat rows | target row q | attention output]
+ *   norm[B]   = || concat_all[b, l2_from:] ||_2      (l2_reg = lambda * mean(norm), DIN/din.py:322)
+ *   att_w[B,T] = the attention weights w_t (raw masked scores or softmax), saved for backward
+ *   relu_masks[B,T,3] = sign bits of the two hidden layers (64 + 32) for positions t < len
+ * mlp: the per-call weights of att_net (DIN/din.py:61-67) packed as rk_din_mlp_floats(D) floats:
+ *   [W1^T 4D x 64][b1 64][W2^T 64 x 32][b2 32][w3 32][b3 1, pad 3][W1 64 x 4D][W2 32 x 64]. */
+typedef struct rk_din_args {
+    const rk_field_t*   cat;          /* category fields; out_off = column in concat_all */
+    int32_t             n_cat;
+    int32_t             n_dense;
+    const float* const* dense_cols;   /* host array of n_dense device pointers; value (b,c) at
+                                         dense_cols[c][b * dense_stride] (the reference passes a
+                                         dict of [B] tensors, DIN/din.py:296) */
+    int64_t             dense_stride;
+    rk_field_t          target;       /* feedid table, idx [B]; out_off = column of q */
+    rk_field_t          history;      /* his_read_comment_7d_seq table, idx [B,T] */
+    const int64_t*      hist_len;     /* [B] */
+    int32_t             T;
+    int32_t             att_off;      /* column of the attention output */
+    int32_t             width;        /* row width of concat_all */
+    int32_t             l2_from;      /* first column under the L2 norm */
+    int32_t             use_softmax;
+    const float*        mlp;
+    int64_t             B;
+} rk_din_args_t;
+
+int rk_din_mlp_floats(int D);
+int rk_din_fwd(const rk_din_args_t* args, float* concat_all, float* norm, float* att_w,
+               uint32_t* relu_masks, int32_t* err_flag, rk_stream_t stream);
+/* g_row[B,width]: per-occurrence gradients of every concat column (tower gradient g_concat + L2
+ * term through g_norm[B] + the attention's d/dq on the target columns); g_hist[B,T,D]: per-
+ * occurrence gradients of the history rows, written only where the position is live (t < len,
+ * or every t of a len == 0 sample in softmax mode). */
+int rk_din_bwd(const rk_din_args_t* args, const float* concat_all, const float* norm,
+               const float* att_w, const uint32_t* relu_masks, const float* g_concat,
+               const float* g_norm, float* g_row, float* g_hist, int32_t* err_flag,
+               rk_stream_t stream);
 
 #ifdef __cplusplus
 }

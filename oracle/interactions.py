@@ -45,15 +45,19 @@ def dense_embedding_grad(idx: np.ndarray, g_rows: np.ndarray, rows: int) -> np.n
     return out
 
 
-def stable_occurrence_order(idx_columns, rows):
+def stable_occurrence_order(idx_columns, rows, dead=None):
     """(sorted_keys, perm) of every occurrence by (field, row), ties in occurrence order —
-    the order rk_plan_build must produce.  perm = occurrence number inside its field."""
+    the order rk_plan_build must produce.  perm = occurrence number inside its field.  Every
+    field owns rows+1 keys: the last one is the sentinel of `dead` occurrences (padded history
+    positions, whose gradient is identically zero), which therefore sort last in their field."""
     keys, perm, base = [], [], 0
-    for col, r in zip(idx_columns, rows):
-        col = np.asarray(col).reshape(-1).astype(np.int64)
+    for f, (col, r) in enumerate(zip(idx_columns, rows)):
+        col = np.asarray(col).reshape(-1).astype(np.int64).copy()
+        if dead is not None and dead[f] is not None:
+            col[np.asarray(dead[f]).reshape(-1)] = r
         keys.append(col + base)
         perm.append(np.arange(col.shape[0], dtype=np.int64))
-        base += r
+        base += r + 1
     keys = np.concatenate(keys)
     perm = np.concatenate(perm)
     order = np.argsort(keys, kind="stable")

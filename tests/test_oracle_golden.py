@@ -60,7 +60,7 @@ def test_dense_embedding_grad_matches_autograd():
 def test_stable_occurrence_order():
     cols = [np.array([2, 0, 2, 1]), np.array([0, 0])]
     keys, perm = X.stable_occurrence_order(cols, [3, 5])
-    assert keys.tolist() == [0, 1, 2, 2, 3, 3]
+    assert keys.tolist() == [0, 1, 2, 2, 4, 4]      # field 1 starts after field 0's sentinel key (3)
     assert perm.tolist() == [1, 3, 0, 2, 0, 1]
 
 
