@@ -98,8 +98,8 @@ class OracleDCN(nn.Module):             # DCN/dcn.py:114-180
         for _ in range(self.num_cross_layer):                      # draws of DCN/dcn.py:37-41
             w = torch.zeros(x0.shape[-1], 1)
             nn.init.xavier_normal_(w)
-            ws.append(w)
-            bs.append(torch.zeros(x0.shape[-1], 1))
+            ws.append(w.to(x0.dtype))
+            bs.append(torch.zeros(x0.shape[-1], 1, dtype=x0.dtype))
         cross = X.cross_network(x0, ws, bs)
         logit = self.output_layer(torch.cat([cross, self.dnn(x0)], dim=1))
         return torch.sigmoid(logit), logit
@@ -122,7 +122,7 @@ class OracleDeepCrossing(nn.Module):    # DeepCrossing/deepcrossing.py:106-163
         for _ in range(self.residual_network_num):                 # draws of deepcrossing.py:37,39
             l1 = nn.Linear(x.shape[-1], self.residual_internal_dim)
             l2 = nn.Linear(self.residual_internal_dim, x.shape[-1])
-            units.append((l1.weight.detach(), l1.bias.detach(), l2.weight.detach(), l2.bias.detach()))
+            units.append(tuple(t.detach().to(x.dtype) for t in (l1.weight, l1.bias, l2.weight, l2.bias)))
         logit = self.output_layer(X.residual_units(x, units))
         return torch.sigmoid(logit), logit
 
@@ -191,8 +191,8 @@ class OracleDIN(nn.Module):             # DIN/din.py:225-323
                              sequence["his_read_comment_7d_seq"])
         att_net = nn.Sequential(nn.Linear(4 * keys.shape[-1], 64), nn.ReLU(), nn.Linear(64, 32), nn.ReLU(),
                                 nn.Linear(32, 1))                   # draws of DIN/din.py:61-67
-        mlp = tuple(t.detach() for t in (att_net[0].weight, att_net[0].bias, att_net[2].weight,
-                                         att_net[2].bias, att_net[4].weight, att_net[4].bias))
+        mlp = tuple(t.detach().to(keys.dtype) for t in (att_net[0].weight, att_net[0].bias, att_net[2].weight,
+                                                        att_net[2].bias, att_net[4].weight, att_net[4].bias))
         att = X.din_local_activation(tgt, keys, sequence["his_read_comment_7d_seq_length"], mlp,
                                      self.use_softmax)
         net = torch.cat([dense_input] + cat_rows + [tgt, att], dim=1)

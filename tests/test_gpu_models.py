@@ -2,6 +2,7 @@
 fixtures), and against the oracle on WeChat-sized synthetic batches.
 Tolerances (north star): gathered rows bit-exact; logits and gradients within 1e-5 relative
 (fp32 paths), 2e-2 on the bf16 tensor-core paths (named where used)."""
+import copy
 import os
 
 import pytest
@@ -21,7 +22,11 @@ IMPLEMENTED = {n for n in ("DeepFM", "DCNModel", "DeepCrossingModel", "AFM", "DI
 FIXTURES = [p for p in golden_files() if "smoke" not in p]
 
 
-def compare(outs, grads, ref_outs, ref_grads, tol):
+def compare(outs, grads, ref_outs, ref_grads, tol, grads64=None):
+    """`grads64`: the same gradients from the oracle run in float64.  A table row hit by tens of
+    thousands of occurrences carries ~sqrt(n)*eps of summation-order noise in the fp32 reference
+    itself (it adds them one by one); where the fp32 comparison exceeds `tol`, being within `tol`
+    of the float64 value is accepted instead."""
     assert len(outs) == len(ref_outs)
     for i, (o, r) in enumerate(zip(outs, ref_outs)):
         if torch.is_tensor(r):
@@ -39,6 +44,8 @@ def compare(outs, grads, ref_outs, ref_grads, tol):
             assert err <= 1e-7 * gmax, f"grad {k} (numerically zero): abs err {err:.3e} vs scale {gmax:.3e}"
         else:
             e = rel_err(grads[k], g)
+            if e > tol and grads64 is not None:
+                e = rel_err(grads[k], grads64[k])
             assert e <= tol, f"grad {k}: {e:.3e}"
 
 
@@ -76,13 +83,23 @@ def _run_both(ours, ref, fx_model, batch, seed=3):
     r_outs, r_grads = golden_cases.replay(ref, fx, inputs, cots)
     o_outs, o_grads = golden_cases.replay(ours, fx, to_device(inputs, DEV), to_device(cots, DEV))
     rank_b200.check_index_errors()
-    return o_outs, o_grads, r_outs, r_grads
+    ref64 = copy.deepcopy(ref).double()
+    _, grads64 = golden_cases.replay(ref64, fx, _to_double(inputs), _to_double(cots))
+    return o_outs, o_grads, r_outs, r_grads, FP32_TOL, grads64
+
+
+def _to_double(obj):
+    if torch.is_tensor(obj):
+        return obj.double() if obj.is_floating_point() else obj
+    if isinstance(obj, dict):
+        return {k: _to_double(v) for k, v in obj.items()}
+    return [_to_double(v) for v in obj]
 
 
 @pytest.mark.parametrize("B,D", [(1024, 16), (8192, 8), (333, 10)])
 def test_deepfm_vs_oracle_wechat_sizes(wechat_vocab_dir, B, D):
     ours, ref = _pair("DeepFM", "OracleDeepFM", wechat_vocab_dir, embedding_dim=D, dropout_rate=0.0)
-    compare(*_run_both(ours, ref, "DeepFM", synthetic.deepfm_batch(B)), FP32_TOL)
+    compare(*_run_both(ours, ref, "DeepFM", synthetic.deepfm_batch(B)))
 
 
 def test_deepfm_gathered_rows_are_bit_exact(wechat_vocab_dir):
@@ -101,7 +118,7 @@ def test_deepfm_gathered_rows_are_bit_exact(wechat_vocab_dir):
 @pytest.mark.parametrize("B,L", [(8192, 3), (1000, 1), (64, 0), (2048, 6)])
 def test_dcn_vs_oracle_wechat_sizes(wechat_vocab_dir, B, L):
     ours, ref = _pair("DCNModel", "OracleDCN", wechat_vocab_dir, num_cross_layer=L)
-    compare(*_run_both(ours, ref, "DCNModel", synthetic.side_batch(B)), FP32_TOL)
+    compare(*_run_both(ours, ref, "DCNModel", synthetic.side_batch(B)))
 
 
 def test_dcn_loads_reference_state_dict_keys(wechat_vocab_dir):
@@ -134,7 +151,7 @@ def test_cross_layer_function(wechat_vocab_dir):
 @pytest.mark.parametrize("B,T,soft", [(2048, 50, False), (2048, 50, True), (777, 13, True), (64, 128, False)])
 def test_din_vs_oracle_wechat_sizes(wechat_vocab_dir, B, T, soft):
     ours, ref = _pair("DIN", "OracleDIN", wechat_vocab_dir, dropout_rate=0.0, use_softmax=soft)
-    compare(*_run_both(ours, ref, "DIN", synthetic.din_batch(B, T)), FP32_TOL)
+    compare(*_run_both(ours, ref, "DIN", synthetic.din_batch(B, T)))
 
 
 def test_din_attention_reference_smoke_on_gpu():
