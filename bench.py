@@ -91,7 +91,52 @@ class DCNWorkload(Workload):
         return F.binary_cross_entropy_with_logits(logit.squeeze(), batch["label"])
 
 
-WORKLOADS = {"deepfm": DeepFMWorkload, "dcn": DCNWorkload}
+class AFMWorkload(Workload):
+    # 10 fields, D=32, A=128: compute-bound on the fp32 FMA pipe once fused
+    name, batch, bytes_per_sample, flops_per_sample = "afm_f10_d32_a128", 8192, 6816, 1_150_000
+    hot_calls = ("rk_afm_fwd", "rk_plan_build", "rk_afm_bwd", "rk_embgrad_segment_reduce")
+
+    def __init__(self):
+        from rank_b200 import synthetic
+        self.fc = synthetic.afm_feature_columns(10)
+
+    def model(self, ns, oracle, vocab_dir):
+        cls = ns.OracleAFM if oracle else ns.AFM
+        return cls(self.fc, 32, 128)
+
+    def make_batch(self, B, seed):
+        from rank_b200 import synthetic
+        return synthetic.afm_batch(B, self.fc, seed)
+
+    def loss(self, model, batch):
+        prob = model(batch["dense"], batch["category"])[0]
+        return F.binary_cross_entropy(prob.squeeze(), batch["label"])
+
+
+class DINWorkload(Workload):
+    name, batch, bytes_per_sample, flops_per_sample = "din_t50_raw", 8192, 18648, 1_240_000
+    hot_calls = ("rk_din_fwd", "rk_plan_build", "rk_din_bwd", "rk_embgrad_segment_reduce")
+    use_softmax = False
+
+    def model(self, ns, oracle, vocab_dir):
+        cls = ns.OracleDIN if oracle else ns.DIN
+        return cls(vocab_dir, dropout_rate=0.0, use_softmax=self.use_softmax, l2_lambda=0.2)
+
+    def make_batch(self, B, seed):
+        from rank_b200 import synthetic
+        return synthetic.din_batch(B, 50, seed)
+
+    def loss(self, model, batch):
+        prob, _, l2 = model(batch["dense"], batch["category"], batch["sequence"], batch["target"])
+        return F.binary_cross_entropy(prob.squeeze(), batch["label"]) + l2
+
+
+class DINSoftmaxWorkload(DINWorkload):
+    name, use_softmax = "din_t50_softmax", True
+
+
+WORKLOADS = {"deepfm": DeepFMWorkload, "dcn": DCNWorkload, "afm": AFMWorkload, "din": DINWorkload,
+             "din_softmax": DINSoftmaxWorkload}
 
 
 # ------------------------------------------------------------------------------- helpers
@@ -194,7 +239,7 @@ def cpu_reference_run(wl, steps, warmup, batch_size, budget_s=None):
             break
     ms = 1e3 * sum(times) / len(times)
     return dict(value=batch_size / (ms / 1e3), ms_per_step=ms, steps=len(times), cores=threads,
-                loss=float(loss))
+                loss=float(loss.detach()))
 
 
 # ------------------------------------------------------------------------------- reference arm

@@ -17,10 +17,12 @@ from .sparse import GradSource, OccurrencePlan, gather_concat
 from .deepfm import DeepFM
 from .dcn import DCNModel, cross_layer
 from .din import DIN, Dice, din_attention, din_collate_fn
+from .afm import AFM, create_feature_columns
 
 __all__ = [
     "RankB200Error", "check_index_errors", "library_path",
     "VOCAB_FILE", "WECHAT_VOCAB_LINES", "table_heights", "write_vocab_dir",
     "GradSource", "OccurrencePlan", "gather_concat",
     "DeepFM", "DCNModel", "cross_layer", "DIN", "Dice", "din_attention", "din_collate_fn",
+    "AFM", "create_feature_columns",
 ]

@@ -1,70 +1,183 @@
 // plan_sort.cu — rk_plan_build: stable LSD radix sort of every index occurrence of a batch
 // by (field, row).  Replaces the sort inside ATen's embedding_dense_backward (reached from
-// loss.backward(), e.g. DeepFM/deepfm.py:170, DIN/din.py:346) with one composite-key sort for
-// all tables of the model; the order it produces makes the later segment reduction sum each
-// row's gradients in occurrence order (deterministic, atomics-free).
+// loss.backward(), e.g. DeepFM/deepfm.py:170, DIN/din.py:346); the order it produces makes the
+// later segment reduction sum each row's gradients in occurrence order (deterministic,
+// atomics-free).  Keys are uint32 = key_base[field] + row, where every field owns rows+1 keys
+// (the last one parks padded history positions that carry no gradient); payload = occurrence
+// number inside its field.  Fields sort independently into their own slice of the output.
 //
-// HBM-bound integer work: 8-bit digits, 3 kernels per pass (tile histogram, scan, stable
-// scatter).  Keys are uint32 = key_base[field] + row; payload = occurrence number in its field.
+// HBM/latency-bound integer work, two paths:
+//   * fields with <= 8192 occurrences (every per-sample column at batch <= 8192): ONE launch,
+//     one 1024-thread CTA per field, the whole sort in shared memory (packed key|occurrence
+//     words, up to 9-bit digits, warp-match ranking) — no global round trips between passes;
+//   * larger fields (DIN/BST history columns): multi-CTA passes of tile histogram, scan and
+//     stable scatter with up to 10-bit digits.
 #include <string.h>
 #include "common.cuh"
 
 namespace rk {
 
-constexpr int kSortThreads = 256;
-constexpr int kSortWarps   = kSortThreads / 32;
-constexpr int kSortRounds  = 16;
-constexpr int kSortTile    = kSortThreads * kSortRounds;  // 4096 keys per CTA
-constexpr int kBins        = 256;
-
-struct KeyBuild {
-    const int64_t* idx[RK_MAX_FIELDS];
-    const int64_t* len[RK_MAX_FIELDS];        // sequence fields: per-sample length, else NULL
-    int32_t        T[RK_MAX_FIELDS];          // positions per sample of a sequence field
-    int32_t        mode[RK_MAX_FIELDS];       // RK_LIVE_*
-    int64_t        start[RK_MAX_FIELDS + 1];  // first occurrence of field f in the flat order
-    int64_t        rows[RK_MAX_FIELDS];
-    uint32_t       key_base[RK_MAX_FIELDS];
-    int32_t        F;
+// --------------------------------------------------------------------------- shared pieces
+struct FieldKeys {              // how to turn occurrence o of one field into its key
+    const int64_t* idx;
+    const int64_t* len;         // sequence fields: per-sample length, else NULL
+    int64_t        n;           // occurrences
+    int64_t        rows;
+    int64_t        start;       // first slot of the field in sorted_keys / perm
+    uint32_t       key_base;
+    int32_t        T;
+    int32_t        mode;        // RK_LIVE_*
+    int32_t        bits;        // bits of rows (+ sentinel)
 };
 
-__global__ void __launch_bounds__(256)
-build_keys_kernel(const __grid_constant__ KeyBuild kb, uint32_t* __restrict__ keys,
-                  uint32_t* __restrict__ vals, int32_t* err_flag) {
-    const int64_t n = kb.start[kb.F];
-    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n;
-         i += (int64_t)gridDim.x * blockDim.x) {
-        int f = 0;
-#pragma unroll 1
-        while (f + 1 < kb.F && i >= kb.start[f + 1]) ++f;
-        const int64_t o   = i - kb.start[f];
-        int64_t row = checked_row(kb.idx[f][o], kb.rows[f], err_flag);
-        if (kb.mode[f] != RK_LIVE_ALL) {
-            // padded history positions carry no gradient: park them on the field's sentinel row
-            const int64_t b = o / kb.T[f], t = o - b * kb.T[f];
-            const int64_t l = kb.len[f][b];
-            const bool dead = t >= l && !(kb.mode[f] == RK_LIVE_PREFIX_OR_EMPTY && l <= 0);
-            if (dead) row = kb.rows[f];
+__device__ __forceinline__ uint32_t local_key(const FieldKeys& f, int64_t o, int32_t* err_flag) {
+    int64_t row = checked_row(f.idx[o], f.rows, err_flag);
+    if (f.mode != RK_LIVE_ALL) {
+        // padded history positions carry no gradient: park them on the field's sentinel row
+        const int64_t b = o / f.T, t = o - b * f.T;
+        const int64_t l = f.len[b];
+        const bool dead = t >= l && !(f.mode == RK_LIVE_PREFIX_OR_EMPTY && l <= 0);
+        if (dead) row = f.rows;
+    }
+    return (uint32_t)row;
+}
+
+// --------------------------------------------------------------------------- small fields
+constexpr int kSmallN       = 8192;
+constexpr int kSmallThreads = 1024;
+constexpr int kSmallWarps   = kSmallThreads / 32;
+constexpr int kSmallRounds  = kSmallN / kSmallThreads;   // 8 keys per thread
+constexpr int kSmallOccBits = 13;                        // occurrence number packed under the key
+constexpr int kSmallMaxBits = 18;                       // key < 2^18: a packed word is never all ones
+constexpr int kSmallBins    = 512;                       // up to 9-bit digits
+
+struct SmallBatch {
+    FieldKeys f[RK_MAX_FIELDS];
+};
+
+__global__ void __launch_bounds__(kSmallThreads, 1)
+small_field_sort_kernel(const __grid_constant__ SmallBatch batch, uint32_t* __restrict__ sorted_keys,
+                        uint32_t* __restrict__ perm, int32_t* err_flag) {
+    extern __shared__ __align__(16) uint32_t sm_u32[];
+    uint32_t* buf0 = sm_u32;                       // [kSmallN] packed (key << 13 | occurrence)
+    uint32_t* buf1 = sm_u32 + kSmallN;
+    uint16_t* cnt  = reinterpret_cast<uint16_t*>(sm_u32 + 2 * kSmallN);   // [warps][bins]
+    __shared__ uint32_t digit_base[kSmallBins];
+    __shared__ uint32_t warp_tot[32];
+
+    const FieldKeys& f = batch.f[blockIdx.x];
+    const int tid = threadIdx.x, w = tid >> 5, lane = tid & 31;
+    const int n = (int)f.n;
+    for (int i = tid; i < kSmallN; i += kSmallThreads)
+        buf0[i] = i < n ? ((local_key(f, i, err_flag) << kSmallOccBits) | (uint32_t)i) : 0xffffffffu;
+
+    const int passes = (f.bits + 8) / 9;
+    const int dbits  = (f.bits + passes - 1) / passes;
+    const int bins   = 1 << dbits;
+    const unsigned lt = (1u << lane) - 1u;
+    uint32_t* in = buf0;
+    uint32_t* out = buf1;
+    for (int p = 0; p < passes; ++p) {
+        const int shift = kSmallOccBits + p * dbits;
+        for (int i = tid; i < kSmallWarps * bins / 2; i += kSmallThreads)
+            reinterpret_cast<uint32_t*>(cnt)[i] = 0;
+        __syncthreads();
+        uint32_t key[kSmallRounds];
+        uint16_t rank[kSmallRounds];
+        const int wbase = w * (kSmallRounds * 32);
+#pragma unroll
+        for (int r = 0; r < kSmallRounds; ++r) key[r] = in[wbase + r * 32 + lane];
+#pragma unroll
+        for (int r = 0; r < kSmallRounds; ++r) {
+            const bool     valid = key[r] != 0xffffffffu;
+            const uint32_t d     = (key[r] >> shift) & (bins - 1);
+            const uint32_t tag   = valid ? d : (kSmallBins | lane);   // padding matches nobody
+            const unsigned m     = __match_any_sync(kFull, tag);
+            const uint32_t old   = valid ? cnt[w * bins + d] : 0u;
+            __syncwarp();
+            if (valid && (m & lt) == 0) cnt[w * bins + d] = (uint16_t)(old + __popc(m));
+            __syncwarp();
+            rank[r] = (uint16_t)(old + __popc(m & lt));
         }
-        keys[i] = kb.key_base[f] + (uint32_t)row;
-        vals[i] = (uint32_t)o;
+        __syncthreads();
+        // per digit: exclusive prefix over the warps, then exclusive scan over the digits
+        uint32_t tot = 0;
+        if (tid < bins) {
+            for (int ww = 0; ww < kSmallWarps; ++ww) {
+                const uint32_t c = cnt[ww * bins + tid];
+                cnt[ww * bins + tid] = (uint16_t)tot;
+                tot += c;
+            }
+        }
+        uint32_t inc = tot;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const uint32_t v = __shfl_up_sync(kFull, inc, o);
+            if (lane >= o) inc += v;
+        }
+        if (lane == 31) warp_tot[w] = inc;
+        __syncthreads();
+        if (w == 0) {
+            const uint32_t t = warp_tot[lane];
+            uint32_t winc = t;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const uint32_t v = __shfl_up_sync(kFull, winc, o);
+                if (lane >= o) winc += v;
+            }
+            warp_tot[lane] = winc - t;
+        }
+        __syncthreads();
+        if (tid < bins) digit_base[tid] = warp_tot[w] + inc - tot;
+        __syncthreads();
+#pragma unroll
+        for (int r = 0; r < kSmallRounds; ++r) {
+            if (key[r] != 0xffffffffu) {
+                const uint32_t d = (key[r] >> shift) & (bins - 1);
+                out[digit_base[d] + cnt[w * bins + d] + rank[r]] = key[r];
+            }
+        }
+        __syncthreads();
+        uint32_t* t = in; in = out; out = t;
+    }
+    for (int i = tid; i < n; i += kSmallThreads) {
+        const uint32_t v = in[i];
+        sorted_keys[f.start + i] = f.key_base + (v >> kSmallOccBits);
+        perm[f.start + i]        = v & ((1u << kSmallOccBits) - 1u);
+    }
+}
+
+// --------------------------------------------------------------------------- large fields
+constexpr int kSortThreads = 256;
+constexpr int kSortWarps   = kSortThreads / 32;
+constexpr int kSortRounds  = 8;
+constexpr int kSortTile    = kSortThreads * kSortRounds;   // 2048 keys per CTA
+constexpr int kMaxBins     = 1024;                         // up to 10-bit digits
+
+__global__ void __launch_bounds__(256)
+build_keys_kernel(const __grid_constant__ FieldKeys f, uint32_t* __restrict__ keys,
+                  uint32_t* __restrict__ vals, int32_t* err_flag) {
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < f.n;
+         i += (int64_t)gridDim.x * blockDim.x) {
+        keys[i] = local_key(f, i, err_flag);
+        vals[i] = (uint32_t)i;
     }
 }
 
 __global__ void __launch_bounds__(kSortThreads)
-tile_hist_kernel(const uint32_t* __restrict__ keys, int64_t n, int shift, int n_tiles,
+tile_hist_kernel(const uint32_t* __restrict__ keys, int64_t n, int shift, int bins, int n_tiles,
                  uint32_t* __restrict__ hist) {
-    __shared__ uint32_t h[kBins];
-    for (int i = threadIdx.x; i < kBins; i += kSortThreads) h[i] = 0;
+    __shared__ uint32_t h[kMaxBins];
+    for (int i = threadIdx.x; i < bins; i += kSortThreads) h[i] = 0;
     __syncthreads();
     const int64_t base = (int64_t)blockIdx.x * kSortTile;
-#pragma unroll 4
+#pragma unroll
     for (int r = 0; r < kSortRounds; ++r) {
         const int64_t i = base + r * kSortThreads + threadIdx.x;
-        if (i < n) atomicAdd(&h[(keys[i] >> shift) & (kBins - 1)], 1u);
+        if (i < n) atomicAdd(&h[(keys[i] >> shift) & (bins - 1)], 1u);
     }
     __syncthreads();
-    for (int d = threadIdx.x; d < kBins; d += kSortThreads)
+    for (int d = threadIdx.x; d < bins; d += kSortThreads)
         hist[(int64_t)d * n_tiles + blockIdx.x] = h[d];
 }
 
@@ -78,7 +191,6 @@ scan_kernel(uint32_t* __restrict__ data, int64_t m) {
     const int64_t hi   = lo + per < m ? lo + per : m;
     uint32_t      sum  = 0;
     for (int64_t i = lo; i < hi; ++i) sum += data[i];
-    // block-wide exclusive scan of `sum`
     uint32_t inc = sum;
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) {
@@ -105,14 +217,16 @@ scan_kernel(uint32_t* __restrict__ data, int64_t m) {
     }
 }
 
-// Stable scatter of one 4096-key tile: ranks are taken in (warp, round, lane) = input order.
+// Stable scatter of one tile: ranks are taken in (warp, round, lane) = input order.  On the
+// last pass the keys get their field base and land in the caller's slice.
 __global__ void __launch_bounds__(kSortThreads)
 scatter_kernel(const uint32_t* __restrict__ keys_in, const uint32_t* __restrict__ vals_in,
                uint32_t* __restrict__ keys_out, uint32_t* __restrict__ vals_out, int64_t n,
-               int shift, int n_tiles, const uint32_t* __restrict__ hist_scanned) {
-    __shared__ uint32_t cnt[kSortWarps][kBins];
+               int shift, int bins, int n_tiles, const uint32_t* __restrict__ hist_scanned,
+               uint32_t add_base) {
+    extern __shared__ uint32_t cnt[];   // [kSortWarps][bins]
     const int t = threadIdx.x, w = t >> 5, lane = t & 31;
-    for (int i = t; i < kSortWarps * kBins; i += kSortThreads) (&cnt[0][0])[i] = 0;
+    for (int i = t; i < kSortWarps * bins; i += kSortThreads) cnt[i] = 0;
     __syncthreads();
 
     const int64_t  wbase = (int64_t)blockIdx.x * kSortTile + (int64_t)w * (kSortRounds * 32);
@@ -128,23 +242,22 @@ scatter_kernel(const uint32_t* __restrict__ keys_in, const uint32_t* __restrict_
     for (int r = 0; r < kSortRounds; ++r) {
         const int64_t  i     = wbase + r * 32 + lane;
         const bool     valid = i < n;
-        const uint32_t d     = (key[r] >> shift) & (kBins - 1);
-        const uint32_t tag   = valid ? d : (kBins | lane);  // invalid lanes match nobody
+        const uint32_t d     = (key[r] >> shift) & (bins - 1);
+        const uint32_t tag   = valid ? d : (kMaxBins | lane);   // invalid lanes match nobody
         const unsigned m     = __match_any_sync(kFull, tag);
-        const uint32_t old   = valid ? cnt[w][d] : 0u;
+        const uint32_t old   = valid ? cnt[w * bins + d] : 0u;
         __syncwarp();
-        if (valid && (m & lt) == 0) cnt[w][d] = old + __popc(m);
+        if (valid && (m & lt) == 0) cnt[w * bins + d] = old + __popc(m);
         __syncwarp();
         rank[r] = (uint16_t)(old + __popc(m & lt));
     }
     __syncthreads();
-    // per digit: turn the per-warp counts into global bases (exclusive over warps)
-    for (int d = t; d < kBins; d += kSortThreads) {
+    for (int d = t; d < bins; d += kSortThreads) {
         uint32_t run = hist_scanned[(int64_t)d * n_tiles + blockIdx.x];
 #pragma unroll
         for (int ww = 0; ww < kSortWarps; ++ww) {
-            uint32_t c = cnt[ww][d];
-            cnt[ww][d] = run;
+            uint32_t c = cnt[ww * bins + d];
+            cnt[ww * bins + d] = run;
             run += c;
         }
     }
@@ -153,15 +266,21 @@ scatter_kernel(const uint32_t* __restrict__ keys_in, const uint32_t* __restrict_
     for (int r = 0; r < kSortRounds; ++r) {
         const int64_t i = wbase + r * 32 + lane;
         if (i < n) {
-            const uint32_t d   = (key[r] >> shift) & (kBins - 1);
-            const uint32_t pos = cnt[w][d] + rank[r];
-            keys_out[pos] = key[r];
+            const uint32_t d   = (key[r] >> shift) & (bins - 1);
+            const uint32_t pos = cnt[w * bins + d] + rank[r];
+            keys_out[pos] = key[r] + add_base;
             vals_out[pos] = vals_in[i];
         }
     }
 }
 
-static int n_tiles_of(int64_t n) { return (int)ceil_div(n > 0 ? n : 1, kSortTile); }
+static int bits_for(int64_t rows_plus_sentinel) {
+    int bits = 1;
+    while (bits < 32 && (1ull << bits) < (unsigned long long)rows_plus_sentinel) ++bits;
+    return bits;
+}
+static bool is_small(int64_t n, int bits) { return n <= kSmallN && bits <= kSmallMaxBits; }
+static size_t al256(size_t b) { return (b + 255) & ~(size_t)255; }
 
 }  // namespace rk
 
@@ -169,11 +288,11 @@ extern "C" {
 
 size_t rk_plan_workspace_bytes(int64_t n_total) {
     if (n_total < 0) n_total = 0;
+    // sized for the large-field path: ping-pong keys + vals (n_total bounds the largest field)
+    // and the tile histograms
     const size_t n     = (size_t)n_total;
-    const size_t tiles = (size_t)rk::n_tiles_of(n_total);
-    // ping-pong keys + vals, then the tile histograms; each region 256-byte aligned
-    auto al = [](size_t b) { return (b + 255) & ~(size_t)255; };
-    return al(n * 4) * 2 + al(tiles * rk::kBins * 4);
+    const size_t tiles = (size_t)rk::ceil_div(n_total > 0 ? n_total : 1, rk::kSortTile);
+    return 4 * rk::al256(n * 4) + rk::al256(tiles * rk::kMaxBins * 4);
 }
 
 int rk_plan_build(const int64_t* const* idx, const int64_t* n, const int64_t* rows, int F,
@@ -185,31 +304,31 @@ int rk_plan_build(const int64_t* const* idx, const int64_t* n, const int64_t* ro
     RK_CHECK_ARG(F >= 1 && F <= RK_MAX_FIELDS, "rk_plan_build: F=%d outside [1,%d]", F,
                  RK_MAX_FIELDS);
     RK_CHECK_ARG(idx && n && rows, "rk_plan_build: NULL host array");
-    KeyBuild kb;
-    memset(&kb, 0, sizeof(kb));
-    kb.F = F;
+    FieldKeys fk[RK_MAX_FIELDS];
+    memset(fk, 0, sizeof(fk));
     int64_t total = 0, space = 0;
     for (int f = 0; f < F; ++f) {
         RK_CHECK_ARG(n[f] >= 0 && rows[f] > 0, "rk_plan_build: field %d n=%lld rows=%lld", f,
                      (long long)n[f], (long long)rows[f]);
         RK_CHECK_ARG(idx[f] != nullptr || n[f] == 0, "rk_plan_build: field %d idx is NULL", f);
-        kb.idx[f]      = idx[f];
-        kb.start[f]    = total;
-        kb.rows[f]     = rows[f];
-        kb.key_base[f] = (uint32_t)space;
-        kb.mode[f]     = live_mode ? live_mode[f] : RK_LIVE_ALL;
-        if (kb.mode[f] != RK_LIVE_ALL) {
-            RK_CHECK_ARG(kb.mode[f] == RK_LIVE_PREFIX || kb.mode[f] == RK_LIVE_PREFIX_OR_EMPTY,
-                         "rk_plan_build: field %d live_mode %d", f, kb.mode[f]);
+        fk[f].idx      = idx[f];
+        fk[f].n        = n[f];
+        fk[f].rows     = rows[f];
+        fk[f].start    = total;
+        fk[f].key_base = (uint32_t)space;
+        fk[f].bits     = bits_for(rows[f] + 1);
+        fk[f].mode     = live_mode ? live_mode[f] : RK_LIVE_ALL;
+        if (fk[f].mode != RK_LIVE_ALL) {
+            RK_CHECK_ARG(fk[f].mode == RK_LIVE_PREFIX || fk[f].mode == RK_LIVE_PREFIX_OR_EMPTY,
+                         "rk_plan_build: field %d live_mode %d", f, fk[f].mode);
             RK_CHECK_ARG(seq_len && seq_len[f] && seq_T && seq_T[f] > 0 && n[f] % seq_T[f] == 0,
                          "rk_plan_build: field %d needs lengths and T dividing n", f);
-            kb.len[f] = seq_len[f];
-            kb.T[f]   = seq_T[f];
+            fk[f].len = seq_len[f];
+            fk[f].T   = seq_T[f];
         }
         total += n[f];
         space += rows[f] + 1;   // +1: the sentinel row of dead occurrences sorts last in the field
     }
-    kb.start[F] = total;
     RK_CHECK_ARG(total < (1ll << 31) && space < (1ll << 32),
                  "rk_plan_build: %lld occurrences / %lld rows exceed the 32-bit key space",
                  (long long)total, (long long)space);
@@ -219,38 +338,60 @@ int rk_plan_build(const int64_t* const* idx, const int64_t* n, const int64_t* ro
                  "rk_plan_build: workspace %zu < %zu bytes", ws_bytes,
                  rk_plan_workspace_bytes(total));
 
-    int bits = 1;
-    while (bits < 32 && (1ull << bits) < (unsigned long long)space) ++bits;
-    const int passes = (bits + 7) / 8;
-
-    auto al = [](size_t b) { return (b + 255) & ~(size_t)255; };
-    char*     base  = (char*)ws;
-    uint32_t* keysY = (uint32_t*)base;
-    uint32_t* valsY = (uint32_t*)(base + al((size_t)total * 4));
-    uint32_t* hist  = (uint32_t*)(base + 2 * al((size_t)total * 4));
-    uint32_t *kin, *vin, *kout, *vout;
-    if (passes & 1) { kin = keysY; vin = valsY; kout = sorted_keys; vout = perm; }
-    else            { kin = sorted_keys; vin = perm; kout = keysY; vout = valsY; }
-
-    const int tiles = n_tiles_of(total);
-    {
-        int grid = (int)ceil_div(total, 256);
-        const int cap = sm_count() * 8;
-        if (grid > cap) grid = cap;
-        build_keys_kernel<<<grid, 256, 0, s>>>(kb, kin, vin, err_flag);
+    // ---- small fields: one CTA each, a single launch
+    SmallBatch small;
+    int n_small = 0;
+    for (int f = 0; f < F; ++f)
+        if (n[f] > 0 && is_small(n[f], fk[f].bits)) small.f[n_small++] = fk[f];
+    if (n_small) {
+        const size_t smem = 2 * (size_t)kSmallN * 4 + (size_t)kSmallWarps * kSmallBins * 2;
+        static bool attr_set = false;
+        if (!attr_set) {
+            RK_CUDA(cudaFuncSetAttribute(small_field_sort_kernel,
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            attr_set = true;
+        }
+        small_field_sort_kernel<<<n_small, kSmallThreads, smem, s>>>(small, sorted_keys, perm, err_flag);
         RK_LAUNCH_CHECK();
     }
-    for (int p = 0; p < passes; ++p) {
-        const int shift = 8 * p;
-        tile_hist_kernel<<<tiles, kSortThreads, 0, s>>>(kin, total, shift, tiles, hist);
-        RK_LAUNCH_CHECK();
-        scan_kernel<<<1, 1024, 0, s>>>(hist, (int64_t)tiles * kBins);
-        RK_LAUNCH_CHECK();
-        scatter_kernel<<<tiles, kSortThreads, 0, s>>>(kin, vin, kout, vout, total, shift, tiles,
-                                                      hist);
-        RK_LAUNCH_CHECK();
-        uint32_t* tk = kin; kin = kout; kout = tk;
-        uint32_t* tv = vin; vin = vout; vout = tv;
+
+    // ---- large fields: multi-CTA passes, one field at a time
+    char* base = (char*)ws;
+    const size_t arr = al256((size_t)total * 4);
+    uint32_t* kA = (uint32_t*)base;
+    uint32_t* vA = (uint32_t*)(base + arr);
+    uint32_t* kB = (uint32_t*)(base + 2 * arr);
+    uint32_t* vB = (uint32_t*)(base + 3 * arr);
+    uint32_t* hist = (uint32_t*)(base + 4 * arr);
+    for (int f = 0; f < F; ++f) {
+        if (n[f] == 0 || is_small(n[f], fk[f].bits)) continue;
+        const int64_t nf     = n[f];
+        const int     passes = (fk[f].bits + 9) / 10;
+        const int     dbits  = (fk[f].bits + passes - 1) / passes;
+        const int     bins   = 1 << dbits;
+        const int     tiles  = (int)ceil_div(nf, kSortTile);
+        {
+            int grid = (int)ceil_div(nf, 256);
+            const int cap = sm_count() * 8;
+            if (grid > cap) grid = cap;
+            build_keys_kernel<<<grid, 256, 0, s>>>(fk[f], kA, vA, err_flag);
+            RK_LAUNCH_CHECK();
+        }
+        uint32_t *kin = kA, *vin = vA;
+        for (int p = 0; p < passes; ++p) {
+            const bool last = p == passes - 1;
+            uint32_t* kout = last ? sorted_keys + fk[f].start : (kin == kA ? kB : kA);
+            uint32_t* vout = last ? perm + fk[f].start : (vin == vA ? vB : vA);
+            tile_hist_kernel<<<tiles, kSortThreads, 0, s>>>(kin, nf, p * dbits, bins, tiles, hist);
+            RK_LAUNCH_CHECK();
+            scan_kernel<<<1, 1024, 0, s>>>(hist, (int64_t)tiles * bins);
+            RK_LAUNCH_CHECK();
+            scatter_kernel<<<tiles, kSortThreads, (size_t)kSortWarps * bins * 4, s>>>(
+                kin, vin, kout, vout, nf, p * dbits, bins, tiles, hist, last ? fk[f].key_base : 0u);
+            RK_LAUNCH_CHECK();
+            kin = kout;
+            vin = vout;
+        }
     }
     return 0;
 }

@@ -166,6 +166,20 @@ int rk_din_bwd(const rk_din_args_t* args, const float* concat_all, const float* 
                const float* g_norm, float* g_row, float* g_hist, int32_t* err_flag,
                rk_stream_t stream);
 
+/* ---- AFM pairwise-interaction attention pooling (AFM/afm.py:92-115, attention net :84-88) ---
+ * fields: F tables of equal dim D (4..32, multiple of 4), 2 <= F <= 16; w1 [A,D], b1 [A],
+ * w2 [A] (attention.2.weight is [1,A]), b2 [1]; A <= 128.  out[B,D] = sum_p softmax_p(s) v_p.
+ * bwd: g_rows[B,F*D] per-occurrence embedding gradients; the gradients of the four registered
+ * attention tensors are written to ONE contiguous buffer g_w1|g_b1|g_w2|g_b2; partials is scratch
+ * of n_ctas * (A*D + 2A + 1) floats with n_ctas = rk_afm_bwd_ctas(B, F). */
+int rk_afm_bwd_ctas(int64_t B, int F);
+int rk_afm_fwd(const rk_field_t* fields, int F, const float* w1, const float* b1, const float* w2,
+               const float* b2, int A, int64_t B, float* out, int32_t* err_flag, rk_stream_t stream);
+int rk_afm_bwd(const rk_field_t* fields, int F, const float* w1, const float* b1, const float* w2,
+               const float* b2, int A, int64_t B, const float* g_out, float* g_rows, float* g_w1,
+               float* g_b1, float* g_w2, float* g_b2, float* partials, int n_ctas,
+               int32_t* err_flag, rk_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -185,3 +185,20 @@ def test_din_attention_function_gradients():
         (got * cot.to(DEV)).sum().backward()
         assert rel_err(got, want) <= FP32_TOL
         assert rel_err(qa.grad, q.grad) <= FP32_TOL and rel_err(ka.grad, k.grad) <= FP32_TOL
+
+
+@pytest.mark.parametrize("B,F,D,A", [(2048, 10, 32, 128), (1000, 7, 16, 64), (513, 3, 8, 20), (300, 16, 4, 128)])
+def test_afm_vs_oracle(B, F, D, A):
+    fc = synthetic.afm_feature_columns(F, extra_vocab=5000)
+    torch.manual_seed(0)
+    ours = rank_b200.AFM(fc, D, A)
+    ref = oracle_models.OracleAFM(fc, D, A)
+    ref.load_state_dict(ours.state_dict(), strict=True)
+    ours.to(DEV)
+    compare(*_run_both(ours, ref, "AFM", synthetic.afm_batch(B, fc)))
+
+
+def test_afm_feature_columns_helper(wechat_vocab_dir):
+    fc, labels = rank_b200.create_feature_columns(wechat_vocab_dir)
+    assert labels == ["read_comment"] and len(fc["dense"]) == 16
+    assert [len(fc["vocab"][c]) for c in fc["category"]] == [19626, 106444, 2, 18789, 25159, 17500, 350]
