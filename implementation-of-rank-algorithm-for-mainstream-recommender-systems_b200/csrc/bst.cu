@@ -1,0 +1,703 @@
+// bst.cu — BST behaviour-sequence transformer block (BSTTransformer.forward, BST/bst.py:66-91)
+// with the sequence gather (BST/bst.py:224) and the pooling over all T positions (:238-241),
+// forward and backward, fp32 SIMT, d_model = 16.
+//
+// One thread owns one (sample, position) row: its 16-wide activations live in registers, the
+// six 16x16 weight matrices sit in shared memory in both orientations and are read with 16-byte
+// broadcast loads (one load per four FMAs).  Keys/values of the CTA's samples are exchanged
+// through shared memory; scores, the masked softmax (key padding mask t >= len -> -inf) and the
+// context are computed per head in registers (d_head = 16/nhead is far too small for tensor
+// cores).  The backward recomputes the forward in-kernel, keeps no [B,heads,T,T] tensor, and
+// reduces the gradients of the REGISTERED block weights (w_q..w_o, ffn, both LayerNorms, the
+// position table) per persistent CTA in registers; a second kernel adds the per-CTA partials in
+// fixed order (no atomics).
+#include <string.h>
+#include "common.cuh"
+
+namespace rk {
+
+constexpr int kBstThreads = 128;
+constexpr int kBstRows    = 128;   // (sample, position) rows per CTA tile
+constexpr int kBstD       = 16;
+constexpr int kBstLd      = 20;    // padded row stride of the row-major shared arrays
+constexpr float kLnEps    = 1e-5f;
+
+struct BstParams {
+    const float* w[6];      // wq wk wv wo w1 w2, each [16][16] as registered (out, in)
+    const float* vec[10];   // bq bk bv bo ln1_g ln1_b b1 b2 ln2_g ln2_b
+    const float* pos;       // [max_len][16]
+    const float* table;  const int64_t* idx;  int64_t table_rows;   // x = table[idx]  (first block)
+    const float* x_in;                                              // or x = x_in[B,T,16]
+    const int64_t* seq_len;
+    int64_t B, n_tiles;
+    int32_t T, S, pool_mean;
+};
+enum { VBQ = 0, VBK, VBV, VBO, VG1, VBE1, VB1, VB2, VG2, VBE2 };
+enum { MQ = 0, MK, MV, MO, M1, M2 };
+
+// out[n] += sum_i in[i] * M[i*16 + n]   (M k-major -> W.in ; M as registered -> W^T.in)
+__device__ __forceinline__ void matvec16(const float* __restrict__ M, const float (&in)[16], float (&out)[16]) {
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+#pragma unroll
+        for (int n4 = 0; n4 < 4; ++n4) {
+            const float4 w = *reinterpret_cast<const float4*>(M + i * 16 + n4 * 4);
+            out[4 * n4 + 0] = fmaf(in[i], w.x, out[4 * n4 + 0]);
+            out[4 * n4 + 1] = fmaf(in[i], w.y, out[4 * n4 + 1]);
+            out[4 * n4 + 2] = fmaf(in[i], w.z, out[4 * n4 + 2]);
+            out[4 * n4 + 3] = fmaf(in[i], w.w, out[4 * n4 + 3]);
+        }
+    }
+}
+__device__ __forceinline__ void load_row(const float* __restrict__ p, float (&v)[16]) {
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+        const float4 t = *reinterpret_cast<const float4*>(p + 4 * c);
+        v[4 * c] = t.x; v[4 * c + 1] = t.y; v[4 * c + 2] = t.z; v[4 * c + 3] = t.w;
+    }
+}
+__device__ __forceinline__ void store_row(float* __restrict__ p, const float (&v)[16]) {
+#pragma unroll
+    for (int c = 0; c < 4; ++c)
+        *reinterpret_cast<float4*>(p + 4 * c) = make_float4(v[4 * c], v[4 * c + 1], v[4 * c + 2], v[4 * c + 3]);
+}
+__device__ __forceinline__ void set_vec(float (&v)[16], const float* __restrict__ src) {
+#pragma unroll
+    for (int i = 0; i < 16; ++i) v[i] = src[i];
+}
+
+// LayerNorm over 16 values: zh = (z - mean) * rstd, y = zh * g + b.
+__device__ __forceinline__ float layer_norm16(const float (&z)[16], const float* g, const float* b,
+                                              float (&zh)[16], float (&y)[16]) {
+    float mean = 0.f;
+#pragma unroll
+    for (int i = 0; i < 16; ++i) mean += z[i];
+    mean *= (1.0f / 16.0f);
+    float var = 0.f;
+#pragma unroll
+    for (int i = 0; i < 16; ++i) { const float d = z[i] - mean; var = fmaf(d, d, var); }
+    const float rstd = rsqrtf(var * (1.0f / 16.0f) + kLnEps);
+#pragma unroll
+    for (int i = 0; i < 16; ++i) { zh[i] = (z[i] - mean) * rstd; y[i] = fmaf(zh[i], g[i], b[i]); }
+    return rstd;
+}
+// dz from dy: gh = dy*g ; dz = rstd * (gh - mean(gh) - zh * mean(gh*zh))
+__device__ __forceinline__ void layer_norm16_bwd(const float (&dy)[16], const float* g, const float (&zh)[16],
+                                                 float rstd, float (&dz)[16]) {
+    float a = 0.f, b = 0.f;
+#pragma unroll
+    for (int i = 0; i < 16; ++i) { const float gh = dy[i] * g[i]; a += gh; b = fmaf(gh, zh[i], b); }
+    a *= (1.0f / 16.0f); b *= (1.0f / 16.0f);
+#pragma unroll
+    for (int i = 0; i < 16; ++i) dz[i] = rstd * (dy[i] * g[i] - a - zh[i] * b);
+}
+
+struct BstSmem {
+    float *wt, *w, *vec, *pos;            // [6][256] k-major, [6][256] registered, [10][16], [T][16]
+    float *ks, *vs, *qs, *dc, *gs, *as, *xs, *qks, *cs;   // [rows][20] each
+    float *mrow, *lrow, *delta;           // [rows][H]
+    __device__ BstSmem(float* base, int T, int H, bool bwd) {
+        float* p = base;
+        wt = p;  p += 6 * 256;
+        w = p;   p += bwd ? 6 * 256 : 0;
+        vec = p; p += 160;
+        pos = p; p += T * 16;
+        ks = p;  p += kBstRows * kBstLd;
+        vs = p;  p += kBstRows * kBstLd;
+        gs = p;  p += kBstRows * kBstLd;     // forward: the block output rows (for pooling)
+        if (bwd) {
+            qs = p;  p += kBstRows * kBstLd;
+            dc = p;  p += kBstRows * kBstLd;
+            as = p;  p += kBstRows * kBstLd;
+            xs = p;  p += kBstRows * kBstLd;
+            qks = p; p += kBstRows * kBstLd;
+            cs = p;  p += kBstRows * kBstLd;
+            mrow = p;  p += kBstRows * H;
+            lrow = p;  p += kBstRows * H;
+            delta = p; p += kBstRows * H;
+        }
+    }
+    static size_t bytes(int T, int H, bool bwd) {
+        size_t n = 6 * 256 + (bwd ? 6 * 256 : 0) + 160 + (size_t)T * 16 + (size_t)(bwd ? 9 : 3) * kBstRows * kBstLd +
+                   (bwd ? (size_t)3 * kBstRows * H : 0);
+        return n * sizeof(float);
+    }
+};
+
+__device__ __forceinline__ void bst_stage_weights(const BstParams& p, const BstSmem& sm, bool bwd) {
+    for (int i = threadIdx.x; i < 6 * 256; i += kBstThreads) {
+        const int m = i >> 8, e = i & 255, k = e >> 4, n = e & 15;
+        sm.wt[i] = __ldg(p.w[m] + n * 16 + k);          // wt[k][n] = W[n][k]
+        if (bwd) sm.w[i] = __ldg(p.w[m] + e);
+    }
+    for (int i = threadIdx.x; i < 160; i += kBstThreads) sm.vec[i] = __ldg(p.vec[i >> 4] + (i & 15));
+    for (int i = threadIdx.x; i < p.T * 16; i += kBstThreads) sm.pos[i] = __ldg(p.pos + i);
+}
+
+__device__ __forceinline__ void bst_load_x(const BstParams& p, int64_t b, int t, float (&x)[16], int32_t* err_flag) {
+    const float* src;
+    if (p.x_in) {
+        src = p.x_in + (b * p.T + t) * 16;
+    } else {
+        const int64_t row = checked_row(__ldg(p.idx + b * p.T + t), p.table_rows, err_flag);
+        src = p.table + row * 16;
+    }
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+        const float4 v = __ldg(reinterpret_cast<const float4*>(src) + c);
+        x[4 * c] = v.x; x[4 * c + 1] = v.y; x[4 * c + 2] = v.z; x[4 * c + 3] = v.w;
+    }
+}
+
+// Scores, masked softmax and context of one query row against the L live keys of its sample.
+template <int H>
+__device__ __forceinline__ void bst_attend(const float (&q)[16], const float* __restrict__ ks,
+                                           const float* __restrict__ vs, int row0, int L, float (&ctx)[16],
+                                           float (&m_out)[H], float (&l_out)[H]) {
+    constexpr int DH = 16 / H;
+    const float scale = rsqrtf((float)DH);
+#pragma unroll
+    for (int h = 0; h < H; ++h) {
+        float m = -INFINITY;
+        for (int u = 0; u < L; ++u) {
+            const float* kr = ks + (row0 + u) * kBstLd + h * DH;
+            float s = 0.f;
+#pragma unroll
+            for (int j = 0; j < DH; ++j) s = fmaf(q[h * DH + j], kr[j], s);
+            m = fmaxf(m, s * scale);
+        }
+        float l = 0.f, c[DH];
+#pragma unroll
+        for (int j = 0; j < DH; ++j) c[j] = 0.f;
+        for (int u = 0; u < L; ++u) {
+            const float* kr = ks + (row0 + u) * kBstLd + h * DH;
+            const float* vr = vs + (row0 + u) * kBstLd + h * DH;
+            float s = 0.f;
+#pragma unroll
+            for (int j = 0; j < DH; ++j) s = fmaf(q[h * DH + j], kr[j], s);
+            const float pr = expf(s * scale - m);
+            l += pr;
+#pragma unroll
+            for (int j = 0; j < DH; ++j) c[j] = fmaf(pr, vr[j], c[j]);
+        }
+        // L == 0: every key masked -> 0/0 = NaN, exactly as softmax over all -inf in the reference
+#pragma unroll
+        for (int j = 0; j < DH; ++j) ctx[h * DH + j] = c[j] / l;
+        m_out[h] = m;
+        l_out[h] = l;
+    }
+}
+
+__device__ __forceinline__ int bst_len(const BstParams& p, int64_t b) {
+    const int64_t l = __ldg(p.seq_len + b);
+    return l < 0 ? 0 : (l > p.T ? p.T : (int)l);
+}
+
+template <int H>
+__global__ void __launch_bounds__(kBstThreads)
+bst_fwd_kernel(const __grid_constant__ BstParams p, float* __restrict__ y_out, float* __restrict__ pool_out,
+               int pool_ld, int32_t* err_flag) {
+    extern __shared__ __align__(16) float smem_raw[];
+    BstSmem sm(smem_raw, p.T, H, false);
+    bst_stage_weights(p, sm, false);
+    __syncthreads();
+    const int r = threadIdx.x, T = p.T;
+    for (int64_t tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
+        const int64_t b0 = tile * p.S;
+        const int ns = (int)((p.B - b0) < p.S ? (p.B - b0) : p.S);
+        const int rows = ns * T;
+        const bool on = r < rows;
+        const int s = on ? r / T : 0, t = on ? r - s * T : 0;
+        const int64_t b = b0 + s;
+        float x[16], qk[16], q[16];
+        int L = 0;
+        if (on) {
+            L = bst_len(p, b);
+            bst_load_x(p, b, t, x, err_flag);
+            float k[16], v[16];
+#pragma unroll
+            for (int i = 0; i < 16; ++i) qk[i] = x[i] + sm.pos[t * 16 + i];
+            set_vec(q, sm.vec + VBQ * 16); set_vec(k, sm.vec + VBK * 16); set_vec(v, sm.vec + VBV * 16);
+            matvec16(sm.wt + MQ * 256, qk, q);
+            matvec16(sm.wt + MK * 256, qk, k);
+            matvec16(sm.wt + MV * 256, x, v);
+            store_row(sm.ks + r * kBstLd, k);
+            store_row(sm.vs + r * kBstLd, v);
+        }
+        __syncthreads();
+        if (on) {
+            float ctx[16], mh[H], lh[H];
+            bst_attend<H>(q, sm.ks, sm.vs, s * T, L, ctx, mh, lh);
+            float z[16], zh[16], o1[16], hp[16], f[16], y[16];
+            set_vec(z, sm.vec + VBO * 16);
+            matvec16(sm.wt + MO * 256, ctx, z);
+#pragma unroll
+            for (int i = 0; i < 16; ++i) z[i] += qk[i];
+            layer_norm16(z, sm.vec + VG1 * 16, sm.vec + VBE1 * 16, zh, o1);
+            set_vec(hp, sm.vec + VB1 * 16);
+            matvec16(sm.wt + M1 * 256, o1, hp);
+#pragma unroll
+            for (int i = 0; i < 16; ++i) hp[i] = hp[i] > 0.f ? hp[i] : 0.01f * hp[i];
+            set_vec(f, sm.vec + VB2 * 16);
+            matvec16(sm.wt + M2 * 256, hp, f);
+#pragma unroll
+            for (int i = 0; i < 16; ++i) z[i] = o1[i] + f[i];
+            layer_norm16(z, sm.vec + VG2 * 16, sm.vec + VBE2 * 16, zh, y);
+            if (y_out) store_row(y_out + (b * T + t) * 16, y);
+            store_row(sm.gs + r * kBstLd, y);
+        }
+        __syncthreads();
+        if (pool_out) {
+            for (int item = r; item < ns * 16; item += kBstThreads) {
+                const int ss = item >> 4, n = item & 15;
+                float a = 0.f;
+                for (int tt = 0; tt < T; ++tt) a += sm.gs[(ss * T + tt) * kBstLd + n];
+                if (p.pool_mean) a /= (float)__ldg(p.seq_len + b0 + ss);
+                pool_out[(b0 + ss) * pool_ld + n] = a;
+            }
+        }
+        __syncthreads();
+    }
+}
+
+// dW[n][k] += sum_rows G[row][n] * A[row][k]: thread owns (n, k), (n, k+1)
+__device__ __forceinline__ void bst_outer(const float* __restrict__ gs, const float* __restrict__ as, int rows,
+                                          float (&acc)[2]) {
+    const int e = threadIdx.x * 2, n = e >> 4, k = e & 15;
+    float a0 = acc[0], a1 = acc[1];
+    for (int row = 0; row < rows; ++row) {
+        const float g = gs[row * kBstLd + n];
+        const float2 a = *reinterpret_cast<const float2*>(as + row * kBstLd + k);
+        a0 = fmaf(g, a.x, a0);
+        a1 = fmaf(g, a.y, a1);
+    }
+    acc[0] = a0; acc[1] = a1;
+}
+// column sums of one or two staged arrays: threads 0..15 -> gs, 16..31 -> as (if used)
+__device__ __forceinline__ void bst_colsum(const float* __restrict__ gs, const float* __restrict__ as, int rows,
+                                           float& acc) {
+    const int tid = threadIdx.x;
+    if (tid < 16 || (as != nullptr && tid < 32)) {
+        const float* src = (tid < 16 ? gs : as) + (tid & 15);
+        float a = acc;
+        for (int row = 0; row < rows; ++row) a += src[row * kBstLd];
+        acc = a;
+    }
+}
+
+// partial layout (floats): [pos T*16][wq 256][bq 16][wk][bk][wv][bv][wo][bo][g1][be1][w1][b1][w2][b2][g2][be2]
+template <int H>
+__global__ void __launch_bounds__(kBstThreads)
+bst_bwd_kernel(const __grid_constant__ BstParams p, const float* __restrict__ g_y, const float* __restrict__ g_pool,
+               int g_pool_ld, float* __restrict__ g_x, float* __restrict__ partials, int32_t* err_flag) {
+    constexpr int DH = 16 / H;
+    extern __shared__ __align__(16) float smem_raw[];
+    BstSmem sm(smem_raw, p.T, H, true);
+    bst_stage_weights(p, sm, true);
+    __syncthreads();
+    const int r = threadIdx.x, T = p.T;
+    const float scale = rsqrtf((float)DH);
+    float macc[6][2];
+#pragma unroll
+    for (int m = 0; m < 6; ++m) { macc[m][0] = 0.f; macc[m][1] = 0.f; }
+    float vacc[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) vacc[i] = 0.f;
+    float pacc[16];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) pacc[i] = 0.f;
+
+    for (int64_t tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
+        const int64_t b0 = tile * p.S;
+        const int ns = (int)((p.B - b0) < p.S ? (p.B - b0) : p.S);
+        const int rows = ns * T;
+        const bool on = r < rows;
+        const int s = on ? r / T : 0, t = on ? r - s * T : 0;
+        const int64_t b = b0 + s;
+        const int row0 = s * T;
+        int L = 0;
+        float zh1[16], zh2[16], act[16], rstd1 = 0.f, rstd2 = 0.f;
+        unsigned hmask = 0;
+        float zero16[16];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) zero16[i] = 0.f;
+        // ---- A. recompute the forward, parking what other rows / later phases need in smem
+        if (on) {
+            L = bst_len(p, b);
+            float x[16], qk[16], q[16], k[16], v[16];
+            bst_load_x(p, b, t, x, err_flag);
+#pragma unroll
+            for (int i = 0; i < 16; ++i) qk[i] = x[i] + sm.pos[t * 16 + i];
+            set_vec(q, sm.vec + VBQ * 16); set_vec(k, sm.vec + VBK * 16); set_vec(v, sm.vec + VBV * 16);
+            matvec16(sm.wt + MQ * 256, qk, q);
+            matvec16(sm.wt + MK * 256, qk, k);
+            matvec16(sm.wt + MV * 256, x, v);
+            store_row(sm.xs + r * kBstLd, x);
+            store_row(sm.qks + r * kBstLd, qk);
+            store_row(sm.qs + r * kBstLd, q);
+            store_row(sm.ks + r * kBstLd, k);
+            store_row(sm.vs + r * kBstLd, v);
+        } else {
+            store_row(sm.xs + r * kBstLd, zero16);
+            store_row(sm.qks + r * kBstLd, zero16);
+        }
+        __syncthreads();
+        if (on) {
+            float q[16], qk[16], ctx[16], mh[H], lh[H];
+            load_row(sm.qs + r * kBstLd, q);
+            load_row(sm.qks + r * kBstLd, qk);
+            bst_attend<H>(q, sm.ks, sm.vs, row0, L, ctx, mh, lh);
+#pragma unroll
+            for (int h = 0; h < H; ++h) { sm.mrow[r * H + h] = mh[h]; sm.lrow[r * H + h] = lh[h]; }
+            store_row(sm.cs + r * kBstLd, ctx);
+            float z[16], o1[16], hp[16], f[16], y[16];
+            set_vec(z, sm.vec + VBO * 16);
+            matvec16(sm.wt + MO * 256, ctx, z);
+#pragma unroll
+            for (int i = 0; i < 16; ++i) z[i] += qk[i];
+            rstd1 = layer_norm16(z, sm.vec + VG1 * 16, sm.vec + VBE1 * 16, zh1, o1);
+            set_vec(hp, sm.vec + VB1 * 16);
+            matvec16(sm.wt + M1 * 256, o1, hp);
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+                if (hp[i] > 0.f) hmask |= 1u << i;
+                act[i] = hp[i] > 0.f ? hp[i] : 0.01f * hp[i];
+            }
+            set_vec(f, sm.vec + VB2 * 16);
+            matvec16(sm.wt + M2 * 256, act, f);
+#pragma unroll
+            for (int i = 0; i < 16; ++i) z[i] = o1[i] + f[i];
+            rstd2 = layer_norm16(z, sm.vec + VG2 * 16, sm.vec + VBE2 * 16, zh2, y);
+        } else {
+            store_row(sm.cs + r * kBstLd, zero16);
+        }
+        // ---- B. upstream gradient of this row, LayerNorm 2 backward
+        float dy[16], dz[16];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) dy[i] = 0.f;
+        if (on) {
+            if (g_y) load_row(g_y + (b * T + t) * 16, dy);
+            if (g_pool) {
+                const float inv = p.pool_mean ? 1.0f / (float)__ldg(p.seq_len + b) : 1.0f;
+#pragma unroll
+                for (int i = 0; i < 16; ++i) dy[i] = fmaf(g_pool[b * g_pool_ld + i], inv, dy[i]);
+            }
+        }
+        {
+            float t0[16];
+#pragma unroll
+            for (int i = 0; i < 16; ++i) t0[i] = on ? dy[i] * zh2[i] : 0.f;
+            store_row(sm.gs + r * kBstLd, t0);
+            store_row(sm.as + r * kBstLd, dy);
+        }
+        __syncthreads();
+        bst_colsum(sm.gs, sm.as, kBstRows, vacc[0]);                 // d ln2_g | d ln2_b
+        __syncthreads();
+        if (on) layer_norm16_bwd(dy, sm.vec + VG2 * 16, zh2, rstd2, dz);
+        else {
+#pragma unroll
+            for (int i = 0; i < 16; ++i) { dz[i] = 0.f; act[i] = 0.f; }
+        }
+        // ---- C. FFN backward
+        store_row(sm.gs + r * kBstLd, dz);
+        store_row(sm.as + r * kBstLd, act);
+        __syncthreads();
+        bst_outer(sm.gs, sm.as, kBstRows, macc[M2]);
+        bst_colsum(sm.gs, nullptr, kBstRows, vacc[1]);               // d b2
+        __syncthreads();
+        float dh[16], o1[16], do1[16];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) { dh[i] = 0.f; o1[i] = 0.f; }
+        if (on) {
+            matvec16(sm.w + M2 * 256, dz, dh);                       // W2^T dz
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+                dh[i] *= ((hmask >> i) & 1u) ? 1.0f : 0.01f;
+                o1[i] = fmaf(zh1[i], sm.vec[VG1 * 16 + i], sm.vec[VBE1 * 16 + i]);
+            }
+        }
+        store_row(sm.gs + r * kBstLd, dh);
+        store_row(sm.as + r * kBstLd, o1);
+        __syncthreads();
+        bst_outer(sm.gs, sm.as, kBstRows, macc[M1]);
+        bst_colsum(sm.gs, nullptr, kBstRows, vacc[2]);               // d b1
+        __syncthreads();
+#pragma unroll
+        for (int i = 0; i < 16; ++i) do1[i] = dz[i];
+        if (on) matvec16(sm.w + M1 * 256, dh, do1);                  // + W1^T dh
+        // ---- D. LayerNorm 1 backward, output projection backward
+        {
+            float t0[16];
+#pragma unroll
+            for (int i = 0; i < 16; ++i) t0[i] = on ? do1[i] * zh1[i] : 0.f;
+            store_row(sm.gs + r * kBstLd, t0);
+            store_row(sm.as + r * kBstLd, do1);
+        }
+        __syncthreads();
+        bst_colsum(sm.gs, sm.as, kBstRows, vacc[3]);                 // d ln1_g | d ln1_b
+        __syncthreads();
+        float dz1[16], dctx[16];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) { dz1[i] = 0.f; dctx[i] = 0.f; }
+        if (on) layer_norm16_bwd(do1, sm.vec + VG1 * 16, zh1, rstd1, dz1);
+        store_row(sm.gs + r * kBstLd, dz1);
+        __syncthreads();
+        bst_outer(sm.gs, sm.cs, kBstRows, macc[MO]);                 // d w_o = dz1 (x) ctx
+        bst_colsum(sm.gs, nullptr, kBstRows, vacc[4]);               // d b_o
+        if (on) {
+            matvec16(sm.w + MO * 256, dz1, dctx);                    // W_o^T dz1
+            float ctx[16];
+            load_row(sm.cs + r * kBstLd, ctx);
+#pragma unroll
+            for (int h = 0; h < H; ++h) {
+                float d = 0.f;
+#pragma unroll
+                for (int j = 0; j < DH; ++j) d = fmaf(dctx[h * DH + j], ctx[h * DH + j], d);
+                sm.delta[r * H + h] = d;
+            }
+        }
+        store_row(sm.dc + r * kBstLd, dctx);
+        __syncthreads();
+        // ---- E. attention backward: as a query (dq) and as a key (dk, dv)
+        float dq[16], dk[16], dv[16];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) { dq[i] = 0.f; dk[i] = 0.f; dv[i] = 0.f; }
+        if (on) {
+            float q[16], kme[16], vme[16];
+            load_row(sm.qs + r * kBstLd, q);
+            load_row(sm.ks + r * kBstLd, kme);
+            load_row(sm.vs + r * kBstLd, vme);
+#pragma unroll
+            for (int h = 0; h < H; ++h) {
+                const float m = sm.mrow[r * H + h], inv_l = 1.0f / sm.lrow[r * H + h], dl = sm.delta[r * H + h];
+                for (int u = 0; u < L; ++u) {
+                    const float* kr = sm.ks + (row0 + u) * kBstLd + h * DH;
+                    const float* vr = sm.vs + (row0 + u) * kBstLd + h * DH;
+                    float sc = 0.f, dA = 0.f;
+#pragma unroll
+                    for (int j = 0; j < DH; ++j) {
+                        sc = fmaf(q[h * DH + j], kr[j], sc);
+                        dA = fmaf(dctx[h * DH + j], vr[j], dA);
+                    }
+                    const float a  = expf(sc * scale - m) * inv_l;
+                    const float dS = a * (dA - dl) * scale;
+#pragma unroll
+                    for (int j = 0; j < DH; ++j) dq[h * DH + j] = fmaf(dS, kr[j], dq[h * DH + j]);
+                }
+                if (t < L) {   // this row is a live key: every position of the sample queries it
+                    for (int tq = 0; tq < T; ++tq) {
+                        const int rq = row0 + tq;
+                        const float* qr = sm.qs + rq * kBstLd + h * DH;
+                        const float* dr = sm.dc + rq * kBstLd + h * DH;
+                        float sc = 0.f, dA = 0.f;
+#pragma unroll
+                        for (int j = 0; j < DH; ++j) {
+                            sc = fmaf(qr[j], kme[h * DH + j], sc);
+                            dA = fmaf(dr[j], vme[h * DH + j], dA);
+                        }
+                        const float a  = expf(sc * scale - sm.mrow[rq * H + h]) / sm.lrow[rq * H + h];
+                        const float dS = a * (dA - sm.delta[rq * H + h]) * scale;
+#pragma unroll
+                        for (int j = 0; j < DH; ++j) {
+                            dv[h * DH + j] = fmaf(a, dr[j], dv[h * DH + j]);
+                            dk[h * DH + j] = fmaf(dS, qr[j], dk[h * DH + j]);
+                        }
+                    }
+                }
+            }
+        }
+        __syncthreads();
+        // ---- F. projection backward, input gradient, position-table gradient
+        store_row(sm.gs + r * kBstLd, dq);
+        __syncthreads();
+        bst_outer(sm.gs, sm.qks, kBstRows, macc[MQ]);
+        bst_colsum(sm.gs, nullptr, kBstRows, vacc[5]);               // d b_q
+        __syncthreads();
+        store_row(sm.gs + r * kBstLd, dk);
+        __syncthreads();
+        bst_outer(sm.gs, sm.qks, kBstRows, macc[MK]);
+        bst_colsum(sm.gs, nullptr, kBstRows, vacc[6]);               // d b_k
+        __syncthreads();
+        store_row(sm.gs + r * kBstLd, dv);
+        __syncthreads();
+        bst_outer(sm.gs, sm.xs, kBstRows, macc[MV]);
+        bst_colsum(sm.gs, nullptr, kBstRows, vacc[7]);               // d b_v
+        __syncthreads();
+        float dqk[16];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) dqk[i] = dz1[i];                // residual path of LayerNorm 1
+        if (on) {
+            matvec16(sm.w + MQ * 256, dq, dqk);
+            matvec16(sm.w + MK * 256, dk, dqk);
+            float dx[16];
+#pragma unroll
+            for (int i = 0; i < 16; ++i) dx[i] = dqk[i];
+            matvec16(sm.w + MV * 256, dv, dx);
+            store_row(g_x + (b * T + t) * 16, dx);
+        }
+        store_row(sm.gs + r * kBstLd, dqk);
+        __syncthreads();
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+            const int e = r + i * kBstThreads;
+            if (e < T * 16) {
+                const int tt = e >> 4, n = e & 15;
+                float a = pacc[i];
+                for (int ss = 0; ss < ns; ++ss) a += sm.gs[(ss * T + tt) * kBstLd + n];
+                pacc[i] = a;
+            }
+        }
+        __syncthreads();
+    }
+
+    // ---- per-CTA partials of the registered parameters
+    float* out = partials + (int64_t)blockIdx.x * (T * 16 + 6 * 256 + 160);
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+        const int e = r + i * kBstThreads;
+        if (e < T * 16) out[e] = pacc[i];
+    }
+    float* o = out + T * 16;
+    const int e2 = r * 2;
+    // order: wq bq wk bk wv bv wo bo g1 be1 w1 b1 w2 b2 g2 be2
+    const int mat_off[6] = {0, 272, 544, 816, 1120, 1392};   // wq wk wv wo w1 w2
+    o[mat_off[MQ] + e2] = macc[MQ][0]; o[mat_off[MQ] + e2 + 1] = macc[MQ][1];
+    o[mat_off[MK] + e2] = macc[MK][0]; o[mat_off[MK] + e2 + 1] = macc[MK][1];
+    o[mat_off[MV] + e2] = macc[MV][0]; o[mat_off[MV] + e2 + 1] = macc[MV][1];
+    o[mat_off[MO] + e2] = macc[MO][0]; o[mat_off[MO] + e2 + 1] = macc[MO][1];
+    o[mat_off[M1] + e2] = macc[M1][0]; o[mat_off[M1] + e2 + 1] = macc[M1][1];
+    o[mat_off[M2] + e2] = macc[M2][0]; o[mat_off[M2] + e2 + 1] = macc[M2][1];
+    if (r < 16) {
+        o[256 + r]  = vacc[5];    // bq
+        o[528 + r]  = vacc[6];    // bk
+        o[800 + r]  = vacc[7];    // bv
+        o[1072 + r] = vacc[4];    // bo
+        o[1088 + r] = vacc[3];    // ln1_g
+        o[1376 + r] = vacc[2];    // b1
+        o[1648 + r] = vacc[1];    // b2
+        o[1664 + r] = vacc[0];    // ln2_g
+    } else if (r < 32) {
+        o[1104 + r - 16] = vacc[3];   // ln1_b
+        o[1680 + r - 16] = vacc[0];   // ln2_b
+    }
+}
+
+__global__ void __launch_bounds__(256)
+bst_reduce_partials_kernel(const float* __restrict__ partials, int n_cta, int count, float* __restrict__ out) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= count) return;
+    float a = 0.f;
+    for (int c = 0; c < n_cta; ++c) a += partials[(int64_t)c * count + i];
+    out[i] = a;
+}
+
+static int bst_fill(const rk_bst_block_t* blk, const float* table, const int64_t* idx, int64_t table_rows,
+                    const float* x_in, const int64_t* seq_len, int64_t B, int T, int pool_mean, BstParams* p) {
+    RK_CHECK_ARG(blk, "bst: block is NULL");
+    const float* w[6]  = {blk->wq, blk->wk, blk->wv, blk->wo, blk->w1, blk->w2};
+    const float* v[10] = {blk->bq, blk->bk, blk->bv, blk->bo, blk->ln1_g, blk->ln1_b, blk->b1, blk->b2,
+                          blk->ln2_g, blk->ln2_b};
+    for (int i = 0; i < 6; ++i) { RK_CHECK_ARG(w[i], "bst: weight matrix %d is NULL", i); p->w[i] = w[i]; }
+    for (int i = 0; i < 10; ++i) { RK_CHECK_ARG(v[i], "bst: vector %d is NULL", i); p->vec[i] = v[i]; }
+    RK_CHECK_ARG(blk->pos && seq_len, "bst: NULL pos or seq_len");
+    RK_CHECK_ARG((x_in != nullptr) != (table != nullptr && idx != nullptr),
+                 "bst: pass either x_in or (table, idx)");
+    RK_CHECK_ARG(T >= 1 && T <= kBstRows, "bst: sequence length %d outside [1,%d]", T, kBstRows);
+    RK_CHECK_ARG(B >= 0, "bst: B=%lld", (long long)B);
+    const void* src = x_in ? (const void*)x_in : (const void*)table;
+    RK_CHECK_ARG(((uintptr_t)src % 16) == 0, "bst: input rows must be 16-byte aligned");
+    p->pos = blk->pos;
+    p->table = table; p->idx = idx; p->table_rows = table_rows; p->x_in = x_in;
+    p->seq_len = seq_len;
+    p->B = B; p->T = T; p->S = kBstRows / T; p->pool_mean = pool_mean;
+    p->n_tiles = ceil_div(B, p->S);
+    return 0;
+}
+
+template <int H>
+static int bst_launch_fwd(const BstParams& p, float* y_out, float* pool_out, int pool_ld, int32_t* err_flag,
+                          cudaStream_t s) {
+    const size_t smem = BstSmem::bytes(p.T, H, false);
+    RK_CUDA(cudaFuncSetAttribute(bst_fwd_kernel<H>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int64_t grid = p.n_tiles;
+    const int64_t cap = (int64_t)sm_count() * 4;
+    if (grid > cap) grid = cap;
+    bst_fwd_kernel<H><<<(int)grid, kBstThreads, smem, s>>>(p, y_out, pool_out, pool_ld, err_flag);
+    RK_LAUNCH_CHECK();
+    return 0;
+}
+template <int H>
+static int bst_launch_bwd(const BstParams& p, const float* g_y, const float* g_pool, int g_pool_ld, float* g_x,
+                          float* partials, int n_ctas, int32_t* err_flag, cudaStream_t s) {
+    const size_t smem = BstSmem::bytes(p.T, H, true);
+    RK_CHECK_ARG(smem <= 227 * 1024, "bst_bwd: %zu bytes of shared memory", smem);
+    RK_CUDA(cudaFuncSetAttribute(bst_bwd_kernel<H>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    bst_bwd_kernel<H><<<n_ctas, kBstThreads, smem, s>>>(p, g_y, g_pool, g_pool_ld, g_x, partials, err_flag);
+    RK_LAUNCH_CHECK();
+    return 0;
+}
+
+}  // namespace rk
+
+extern "C" {
+
+int rk_bst_grad_floats(int T) { return T * 16 + 6 * 256 + 160; }
+
+int rk_bst_bwd_ctas(int64_t B, int T) {
+    if (T < 1 || T > rk::kBstRows || B <= 0) return 1;
+    const int64_t tiles = rk::ceil_div(B, rk::kBstRows / T);
+    const int64_t cap = (int64_t)rk::sm_count() * 2;
+    return (int)(tiles < cap ? tiles : cap);
+}
+
+int rk_bst_block_fwd(const rk_bst_block_t* blk, int nhead, const float* table, const int64_t* idx,
+                     int64_t table_rows, const float* x_in, const int64_t* seq_len, int64_t B, int T,
+                     float* y_out, float* pool_out, int pool_ld, int pool_mean, int32_t* err_flag,
+                     rk_stream_t stream_) {
+    using namespace rk;
+    BstParams p;
+    memset(&p, 0, sizeof(p));
+    if (int rc = bst_fill(blk, table, idx, table_rows, x_in, seq_len, B, T, pool_mean, &p)) return rc;
+    RK_CHECK_ARG(y_out || pool_out, "bst_fwd: no output requested");
+    if (B == 0) return 0;
+    cudaStream_t s = (cudaStream_t)stream_;
+    switch (nhead) {
+        case 1:  return bst_launch_fwd<1>(p, y_out, pool_out, pool_ld, err_flag, s);
+        case 2:  return bst_launch_fwd<2>(p, y_out, pool_out, pool_ld, err_flag, s);
+        case 4:  return bst_launch_fwd<4>(p, y_out, pool_out, pool_ld, err_flag, s);
+        case 8:  return bst_launch_fwd<8>(p, y_out, pool_out, pool_ld, err_flag, s);
+        case 16: return bst_launch_fwd<16>(p, y_out, pool_out, pool_ld, err_flag, s);
+    }
+    RK_CHECK_ARG(false, "bst: nhead %d does not divide d_model 16 (the reference's view() fails too)", nhead);
+    return -1;
+}
+
+int rk_bst_block_bwd(const rk_bst_block_t* blk, int nhead, const float* table, const int64_t* idx,
+                     int64_t table_rows, const float* x_in, const int64_t* seq_len, int64_t B, int T,
+                     const float* g_y, const float* g_pool, int g_pool_ld, int pool_mean, float* g_x,
+                     float* g_params, float* partials, int n_ctas, int32_t* err_flag, rk_stream_t stream_) {
+    using namespace rk;
+    BstParams p;
+    memset(&p, 0, sizeof(p));
+    if (int rc = bst_fill(blk, table, idx, table_rows, x_in, seq_len, B, T, pool_mean, &p)) return rc;
+    RK_CHECK_ARG((g_y || g_pool) && g_x && g_params && partials, "bst_bwd: NULL pointer");
+    RK_CHECK_ARG(n_ctas == rk_bst_bwd_ctas(B, T), "bst_bwd: n_ctas %d != rk_bst_bwd_ctas", n_ctas);
+    if (B == 0) return 0;
+    cudaStream_t s = (cudaStream_t)stream_;
+    int rc = -1;
+    switch (nhead) {
+        case 1:  rc = bst_launch_bwd<1>(p, g_y, g_pool, g_pool_ld, g_x, partials, n_ctas, err_flag, s); break;
+        case 2:  rc = bst_launch_bwd<2>(p, g_y, g_pool, g_pool_ld, g_x, partials, n_ctas, err_flag, s); break;
+        case 4:  rc = bst_launch_bwd<4>(p, g_y, g_pool, g_pool_ld, g_x, partials, n_ctas, err_flag, s); break;
+        case 8:  rc = bst_launch_bwd<8>(p, g_y, g_pool, g_pool_ld, g_x, partials, n_ctas, err_flag, s); break;
+        case 16: rc = bst_launch_bwd<16>(p, g_y, g_pool, g_pool_ld, g_x, partials, n_ctas, err_flag, s); break;
+        default: RK_CHECK_ARG(false, "bst: nhead %d does not divide d_model 16", nhead);
+    }
+    if (rc) return rc;
+    const int count = rk_bst_grad_floats(T);
+    bst_reduce_partials_kernel<<<(count + 255) / 256, 256, 0, s>>>(partials, n_ctas, count, g_params);
+    RK_LAUNCH_CHECK();
+    return 0;
+}
+
+}  // extern "C"

@@ -48,7 +48,7 @@ constexpr int kSmallThreads = 1024;
 constexpr int kSmallWarps   = kSmallThreads / 32;
 constexpr int kSmallRounds  = kSmallN / kSmallThreads;   // 8 keys per thread
 constexpr int kSmallOccBits = 13;                        // occurrence number packed under the key
-constexpr int kSmallMaxBits = 18;                       // key < 2^18: a packed word is never all ones
+constexpr int kSmallMaxBits = 32 - kSmallOccBits;        // 19 key bits fit above the occurrence
 constexpr int kSmallBins    = 512;                       // up to 9-bit digits
 
 struct SmallBatch {
@@ -69,7 +69,7 @@ small_field_sort_kernel(const __grid_constant__ SmallBatch batch, uint32_t* __re
     const int tid = threadIdx.x, w = tid >> 5, lane = tid & 31;
     const int n = (int)f.n;
     for (int i = tid; i < kSmallN; i += kSmallThreads)
-        buf0[i] = i < n ? ((local_key(f, i, err_flag) << kSmallOccBits) | (uint32_t)i) : 0xffffffffu;
+        if (i < n) buf0[i] = (local_key(f, i, err_flag) << kSmallOccBits) | (uint32_t)i;
 
     const int passes = (f.bits + 8) / 9;
     const int dbits  = (f.bits + passes - 1) / passes;
@@ -86,10 +86,10 @@ small_field_sort_kernel(const __grid_constant__ SmallBatch batch, uint32_t* __re
         uint16_t rank[kSmallRounds];
         const int wbase = w * (kSmallRounds * 32);
 #pragma unroll
-        for (int r = 0; r < kSmallRounds; ++r) key[r] = in[wbase + r * 32 + lane];
+        for (int r = 0; r < kSmallRounds; ++r) key[r] = wbase + r * 32 + lane < n ? in[wbase + r * 32 + lane] : 0u;
 #pragma unroll
         for (int r = 0; r < kSmallRounds; ++r) {
-            const bool     valid = key[r] != 0xffffffffu;
+            const bool     valid = wbase + r * 32 + lane < n;   // the first n slots hold the keys
             const uint32_t d     = (key[r] >> shift) & (bins - 1);
             const uint32_t tag   = valid ? d : (kSmallBins | lane);   // padding matches nobody
             const unsigned m     = __match_any_sync(kFull, tag);
@@ -132,7 +132,7 @@ small_field_sort_kernel(const __grid_constant__ SmallBatch batch, uint32_t* __re
         __syncthreads();
 #pragma unroll
         for (int r = 0; r < kSmallRounds; ++r) {
-            if (key[r] != 0xffffffffu) {
+            if (wbase + r * 32 + lane < n) {
                 const uint32_t d = (key[r] >> shift) & (bins - 1);
                 out[digit_base[d] + cnt[w * bins + d] + rank[r]] = key[r];
             }
