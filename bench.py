@@ -135,8 +135,26 @@ class DINSoftmaxWorkload(DINWorkload):
     name, use_softmax = "din_t50_softmax", True
 
 
+class BSTWorkload(Workload):
+    name, batch, bytes_per_sample, flops_per_sample = "bst_t20_h4_b1", 8192, 7968, 261_000
+    hot_calls = ("rk_gather_concat_fwd", "rk_bst_block_fwd", "rk_plan_build", "rk_bst_block_bwd",
+                 "rk_embgrad_segment_reduce")
+
+    def model(self, ns, oracle, vocab_dir):
+        cls = ns.OracleBST if oracle else ns.BSTModel
+        return cls(vocab_dir, dropout_rate=0.0, nhead=4, num_transformer_blocks=1, max_seq_length=20)
+
+    def make_batch(self, B, seed):
+        from rank_b200 import synthetic
+        return synthetic.bst_batch(B, 20, seed)
+
+    def loss(self, model, batch):
+        logit = model(batch["dense"], batch["category"], batch["seq_feedid"], batch["seq_length"])[1]
+        return F.binary_cross_entropy_with_logits(logit.squeeze(), batch["label"])
+
+
 WORKLOADS = {"deepfm": DeepFMWorkload, "dcn": DCNWorkload, "afm": AFMWorkload, "din": DINWorkload,
-             "din_softmax": DINSoftmaxWorkload}
+             "din_softmax": DINSoftmaxWorkload, "bst": BSTWorkload}
 
 
 # ------------------------------------------------------------------------------- helpers

@@ -13,16 +13,17 @@ The directory name contains hyphens, so import it through the `rank_b200` alias 
 from . import _lib
 from ._lib import RankB200Error, check_index_errors, library_path
 from .vocab import VOCAB_FILE, WECHAT_VOCAB_LINES, table_heights, write_vocab_dir
-from .sparse import GradSource, OccurrencePlan, gather_concat
+from .sparse import GatherConcat, GradSource, OccurrencePlan, gather_concat
 from .deepfm import DeepFM
 from .dcn import DCNModel, cross_layer
 from .din import DIN, Dice, din_attention, din_collate_fn
 from .afm import AFM, create_feature_columns
+from .bst import BSTModel, BSTTransformer, leakyrelu, load_vocabulary
 
 __all__ = [
     "RankB200Error", "check_index_errors", "library_path",
     "VOCAB_FILE", "WECHAT_VOCAB_LINES", "table_heights", "write_vocab_dir",
     "GradSource", "OccurrencePlan", "gather_concat",
     "DeepFM", "DCNModel", "cross_layer", "DIN", "Dice", "din_attention", "din_collate_fn",
-    "AFM", "create_feature_columns",
+    "AFM", "create_feature_columns", "BSTModel", "BSTTransformer", "leakyrelu", "load_vocabulary",
 ]

@@ -40,6 +40,12 @@ class RkDinArgs(C.Structure):
                 ("B", C.c_int64)]
 
 
+class RkBstBlock(C.Structure):
+    _fields_ = [(n, C.c_void_p) for n in (
+        "pos", "wq", "bq", "wk", "bk", "wv", "bv", "wo", "bo", "ln1_g", "ln1_b", "w1", "b1", "w2", "b2",
+        "ln2_g", "ln2_b")]
+
+
 LIVE_ALL, LIVE_PREFIX, LIVE_PREFIX_OR_EMPTY = 0, 1, 2
 
 _P = C.c_void_p
@@ -68,6 +74,10 @@ PROTOTYPES = {
     "rk_afm_bwd_ctas": (_I, [_L, _I]),
     "rk_afm_fwd": (_I, [_P, _I, _P, _P, _P, _P, _I, _L, _P, _P, _P]),
     "rk_afm_bwd": (_I, [_P, _I, _P, _P, _P, _P, _I, _L, _P, _P, _P, _P, _P, _P, _P, _I, _P, _P]),
+    "rk_bst_grad_floats": (_I, [_I]),
+    "rk_bst_bwd_ctas": (_I, [_L, _I]),
+    "rk_bst_block_fwd": (_I, [_P, _I, _P, _P, _L, _P, _P, _L, _I, _P, _P, _I, _I, _P, _P]),
+    "rk_bst_block_bwd": (_I, [_P, _I, _P, _P, _L, _P, _P, _L, _I, _P, _P, _I, _I, _P, _P, _P, _I, _P, _P]),
     "rk_din_mlp_floats": (_I, [_I]),
     "rk_din_fwd": (_I, [_P, _P, _P, _P, _P, _P, _P]),
     "rk_din_bwd": (_I, [_P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P]),
@@ -109,7 +119,7 @@ class CallTimer:
     (bench.py's live per-call device times).  Use as a context manager; `summary()` after a
     synchronize gives {entry point: (calls, total ms)}."""
 
-    NO_KERNEL = ("rk_din_mlp_floats", "rk_afm_bwd_ctas", "rk_version", "rk_last_error", "rk_device_sm_count", "rk_launch_count", "rk_debug_spin",
+    NO_KERNEL = ("rk_din_mlp_floats", "rk_afm_bwd_ctas", "rk_bst_grad_floats", "rk_bst_bwd_ctas", "rk_version", "rk_last_error", "rk_device_sm_count", "rk_launch_count", "rk_debug_spin",
                  "rk_plan_workspace_bytes", "rk_reduce_workspace_bytes")
 
     def __init__(self):

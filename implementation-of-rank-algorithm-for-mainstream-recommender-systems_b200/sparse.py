@@ -125,6 +125,39 @@ class OccurrencePlan:
         return grads
 
 
+class GatherConcat(torch.autograd.Function):
+    """(dense[B,n] or None, idx_0.., table_0..) -> [dense | table_0[idx_0] | ...], differentiable
+    w.r.t. dense and the tables (dense gradients through the sorted segment reduction)."""
+
+    @staticmethod
+    def forward(ctx, F, dense, *args):
+        idx, tables = args[:F], args[F:2 * F]
+        offsets, off = [], 0 if dense is None else int(dense.shape[1])
+        n_dense = off
+        for t in tables:
+            offsets.append(off)
+            off += int(t.shape[1])
+        out = gather_concat(tables, idx, offsets, dense)
+        ctx.set_materialize_grads(False)
+        ctx.meta = (F, n_dense, offsets, off, [int(t.shape[0]) for t in tables], [int(t.shape[1]) for t in tables])
+        if any(ctx.needs_input_grad[2 + F:]):
+            ctx.plan = OccurrencePlan(list(idx), ctx.meta[4])
+        return out
+
+    @staticmethod
+    def backward(ctx, g_out):
+        F, n_dense, offsets, width, rows, dims = ctx.meta
+        if g_out is None:
+            return (None,) * (2 + 2 * F)
+        g_out = _lib.require_cuda(g_out, "g_out", torch.float32)
+        g_dense = g_out[:, :n_dense] if (n_dense and ctx.needs_input_grad[1]) else None
+        g_tables = [None] * F
+        if any(ctx.needs_input_grad[2 + F:]):
+            g_tables = ctx.plan.reduce_to_dense(
+                [GradSource(g_out, offsets[f], width, dims[f], rows[f], f) for f in range(F)])
+        return (None, g_dense, *([None] * F), *g_tables)
+
+
 def gather_concat(weights, indices, offsets, dense=None, width=None) -> torch.Tensor:
     """[dense | W_0[idx_0] | W_1[idx_1] | ...] in one launch (no autograd)."""
     lib = _lib.load()

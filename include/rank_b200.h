@@ -180,6 +180,38 @@ int rk_afm_bwd(const rk_field_t* fields, int F, const float* w1, const float* b1
                float* g_b1, float* g_w2, float* g_b2, float* partials, int n_ctas,
                int32_t* err_flag, rk_stream_t stream);
 
+/* ---- BST transformer block (BSTTransformer.forward BST/bst.py:66-91; gather :224; pooling
+ *      :238-241), d_model = 16, nhead in {1,2,4,8,16} ------------------------------------------
+ * Input rows x[b,t,:] come either from a table through idx[B,T] (first block: the feedid
+ * embedding) or from x_in[B,T,16] (a previous block's output).  Keys t >= seq_len[b] are masked
+ * with -inf (a length-0 sample yields NaN, as in the reference).  y_out[B,T,16] and/or the
+ * pooled row sum_t y[b,t,:] (divided by seq_len[b] when pool_mean) written to
+ * pool_out[b*pool_ld + 0..15] are produced.  Dropout inside the block is not applied (p = 0 or
+ * eval mode only). */
+typedef struct rk_bst_block {
+    const float* pos;                                  /* position_embedding.weight [max_len,16] */
+    const float *wq, *bq, *wk, *bk, *wv, *bv, *wo, *bo; /* w_q/w_k/w_v/w_o .weight [16,16], .bias [16] */
+    const float *ln1_g, *ln1_b;                        /* norm1 */
+    const float *w1, *b1, *w2, *b2;                    /* ffn.0, ffn.3 */
+    const float *ln2_g, *ln2_b;                        /* norm2 */
+} rk_bst_block_t;
+
+int rk_bst_grad_floats(int T);            /* T*16 + 6*256 + 10*16 */
+int rk_bst_bwd_ctas(int64_t B, int T);
+int rk_bst_block_fwd(const rk_bst_block_t* blk, int nhead, const float* table, const int64_t* idx,
+                     int64_t table_rows, const float* x_in, const int64_t* seq_len, int64_t B, int T,
+                     float* y_out, float* pool_out, int pool_ld, int pool_mean, int32_t* err_flag,
+                     rk_stream_t stream);
+/* g_y[B,T,16] and/or g_pool (row b at g_pool + b*g_pool_ld) -> g_x[B,T,16] and the gradients of the
+ * block's registered tensors in g_params, laid out
+ *   [pos T*16][wq 256][bq 16][wk][bk][wv][bv][wo][bo][ln1_g][ln1_b][w1][b1][w2][b2][ln2_g][ln2_b];
+ * partials: scratch of rk_bst_bwd_ctas(B,T) * rk_bst_grad_floats(T) floats. */
+int rk_bst_block_bwd(const rk_bst_block_t* blk, int nhead, const float* table, const int64_t* idx,
+                     int64_t table_rows, const float* x_in, const int64_t* seq_len, int64_t B, int T,
+                     const float* g_y, const float* g_pool, int g_pool_ld, int pool_mean, float* g_x,
+                     float* g_params, float* partials, int n_ctas, int32_t* err_flag,
+                     rk_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -202,3 +202,26 @@ def test_afm_feature_columns_helper(wechat_vocab_dir):
     fc, labels = rank_b200.create_feature_columns(wechat_vocab_dir)
     assert labels == ["read_comment"] and len(fc["dense"]) == 16
     assert [len(fc["vocab"][c]) for c in fc["category"]] == [19626, 106444, 2, 18789, 25159, 17500, 350]
+
+
+@pytest.mark.parametrize("B,T,nhead,blocks,pool", [(2048, 20, 4, 1, "sum"), (1000, 20, 2, 2, "mean"),
+                                                     (300, 50, 8, 1, "sum"), (257, 7, 1, 3, "mean"),
+                                                     (64, 128, 16, 1, "sum")])
+def test_bst_vs_oracle_wechat_sizes(wechat_vocab_dir, B, T, nhead, blocks, pool):
+    kw = dict(dropout_rate=0.0, nhead=nhead, num_transformer_blocks=blocks, max_seq_length=T, pooling_method=pool)
+    ours, ref = _pair("BSTModel", "OracleBST", wechat_vocab_dir, **kw)
+    compare(*_run_both(ours, ref, "BSTModel", synthetic.bst_batch(B, T)))
+
+
+def test_bst_rejects_training_dropout_and_bad_heads(wechat_vocab_dir):
+    m = rank_b200.BSTModel(wechat_vocab_dir, dropout_rate=0.1, max_seq_length=20).to(DEV)
+    batch = to_device(synthetic.bst_batch(32, 20), DEV)
+    with pytest.raises(NotImplementedError):
+        m(batch["dense"], batch["category"], batch["seq_feedid"], batch["seq_length"])
+    m.eval()
+    with torch.no_grad():
+        p, _ = m(batch["dense"], batch["category"], batch["seq_feedid"], batch["seq_length"])
+    assert p.shape == (32, 1) and torch.isfinite(p).all()
+    bad = rank_b200.BSTModel(wechat_vocab_dir, dropout_rate=0.0, nhead=3, max_seq_length=20).to(DEV)
+    with pytest.raises(RuntimeError):      # the reference's view() raises for nhead 3 / 5 as well
+        bad(batch["dense"], batch["category"], batch["seq_feedid"], batch["seq_length"])
