@@ -153,8 +153,26 @@ class BSTWorkload(Workload):
         return F.binary_cross_entropy_with_logits(logit.squeeze(), batch["label"])
 
 
+class DeepCrossingWorkload(Workload):
+    name, batch, bytes_per_sample, flops_per_sample = "deepcrossing_h128_n2", 8192, 1304, 154_000
+    bound = "hbm"
+    hot_calls = ("rk_resunits_fwd", "rk_plan_build", "rk_resunits_bwd", "rk_embgrad_segment_reduce")
+
+    def model(self, ns, oracle, vocab_dir):
+        cls = ns.OracleDeepCrossing if oracle else ns.DeepCrossingModel
+        return cls(vocab_dir, residual_internal_dim=128, residual_network_num=2)
+
+    def make_batch(self, B, seed):
+        from rank_b200 import synthetic
+        return synthetic.side_batch(B, seed)
+
+    def loss(self, model, batch):
+        logit = model(batch["dense"], batch["category"])[1]
+        return F.binary_cross_entropy_with_logits(logit.squeeze(), batch["label"])
+
+
 WORKLOADS = {"deepfm": DeepFMWorkload, "dcn": DCNWorkload, "afm": AFMWorkload, "din": DINWorkload,
-             "din_softmax": DINSoftmaxWorkload, "bst": BSTWorkload}
+             "din_softmax": DINSoftmaxWorkload, "bst": BSTWorkload, "deepcrossing": DeepCrossingWorkload}
 
 
 # ------------------------------------------------------------------------------- helpers

@@ -74,6 +74,9 @@ PROTOTYPES = {
     "rk_afm_bwd_ctas": (_I, [_L, _I]),
     "rk_afm_fwd": (_I, [_P, _I, _P, _P, _P, _P, _I, _L, _P, _P, _P]),
     "rk_afm_bwd": (_I, [_P, _I, _P, _P, _P, _P, _I, _L, _P, _P, _P, _P, _P, _P, _P, _I, _P, _P]),
+    "rk_resunit_pack_floats": (_I, [_I, _I]),
+    "rk_resunits_fwd": (_I, [_P, _I, _P, _I, _P, _I, _I, _L, _P, _P, _P]),
+    "rk_resunits_bwd": (_I, [_P, _P, _I, _I, _I, _L, _P, _P, _P]),
     "rk_bst_grad_floats": (_I, [_I]),
     "rk_bst_bwd_ctas": (_I, [_L, _I]),
     "rk_bst_block_fwd": (_I, [_P, _I, _P, _P, _L, _P, _P, _L, _I, _P, _P, _I, _I, _P, _P]),
@@ -119,7 +122,7 @@ class CallTimer:
     (bench.py's live per-call device times).  Use as a context manager; `summary()` after a
     synchronize gives {entry point: (calls, total ms)}."""
 
-    NO_KERNEL = ("rk_din_mlp_floats", "rk_afm_bwd_ctas", "rk_bst_grad_floats", "rk_bst_bwd_ctas", "rk_version", "rk_last_error", "rk_device_sm_count", "rk_launch_count", "rk_debug_spin",
+    NO_KERNEL = ("rk_resunit_pack_floats", "rk_din_mlp_floats","rk_afm_bwd_ctas", "rk_bst_grad_floats", "rk_bst_bwd_ctas", "rk_version", "rk_last_error", "rk_device_sm_count", "rk_launch_count", "rk_debug_spin",
                  "rk_plan_workspace_bytes", "rk_reduce_workspace_bytes")
 
     def __init__(self):

@@ -76,7 +76,7 @@ __device__ __forceinline__ float layer_norm16(const float (&z)[16], const float*
     float var = 0.f;
 #pragma unroll
     for (int i = 0; i < 16; ++i) { const float d = z[i] - mean; var = fmaf(d, d, var); }
-    const float rstd = rsqrtf(var * (1.0f / 16.0f) + kLnEps);
+    const float rstd = 1.0f / sqrtf(var * (1.0f / 16.0f) + kLnEps);
 #pragma unroll
     for (int i = 0; i < 16; ++i) { zh[i] = (z[i] - mean) * rstd; y[i] = fmaf(zh[i], g[i], b[i]); }
     return rstd;
@@ -155,7 +155,7 @@ __device__ __forceinline__ void bst_attend(const float (&q)[16], const float* __
                                            const float* __restrict__ vs, int row0, int L, float (&ctx)[16],
                                            float (&m_out)[H], float (&l_out)[H]) {
     constexpr int DH = 16 / H;
-    const float scale = rsqrtf((float)DH);
+    const float scale = 1.0f / sqrtf((float)DH);
 #pragma unroll
     for (int h = 0; h < H; ++h) {
         float m = -INFINITY;
@@ -296,7 +296,7 @@ bst_bwd_kernel(const __grid_constant__ BstParams p, const float* __restrict__ g_
     bst_stage_weights(p, sm, true);
     __syncthreads();
     const int r = threadIdx.x, T = p.T;
-    const float scale = rsqrtf((float)DH);
+    const float scale = 1.0f / sqrtf((float)DH);
     float macc[6][2];
 #pragma unroll
     for (int m = 0; m < 6; ++m) { macc[m][0] = 0.f; macc[m][1] = 0.f; }
@@ -391,7 +391,7 @@ bst_bwd_kernel(const __grid_constant__ BstParams p, const float* __restrict__ g_
             store_row(sm.as + r * kBstLd, dy);
         }
         __syncthreads();
-        bst_colsum(sm.gs, sm.as, kBstRows, vacc[0]);                 // d ln2_g | d ln2_b
+        bst_colsum(sm.gs, sm.as, rows, vacc[0]);                 // d ln2_g | d ln2_b
         __syncthreads();
         if (on) layer_norm16_bwd(dy, sm.vec + VG2 * 16, zh2, rstd2, dz);
         else {
@@ -402,8 +402,8 @@ bst_bwd_kernel(const __grid_constant__ BstParams p, const float* __restrict__ g_
         store_row(sm.gs + r * kBstLd, dz);
         store_row(sm.as + r * kBstLd, act);
         __syncthreads();
-        bst_outer(sm.gs, sm.as, kBstRows, macc[M2]);
-        bst_colsum(sm.gs, nullptr, kBstRows, vacc[1]);               // d b2
+        bst_outer(sm.gs, sm.as, rows, macc[M2]);
+        bst_colsum(sm.gs, nullptr, rows, vacc[1]);               // d b2
         __syncthreads();
         float dh[16], o1[16], do1[16];
 #pragma unroll
@@ -419,8 +419,8 @@ bst_bwd_kernel(const __grid_constant__ BstParams p, const float* __restrict__ g_
         store_row(sm.gs + r * kBstLd, dh);
         store_row(sm.as + r * kBstLd, o1);
         __syncthreads();
-        bst_outer(sm.gs, sm.as, kBstRows, macc[M1]);
-        bst_colsum(sm.gs, nullptr, kBstRows, vacc[2]);               // d b1
+        bst_outer(sm.gs, sm.as, rows, macc[M1]);
+        bst_colsum(sm.gs, nullptr, rows, vacc[2]);               // d b1
         __syncthreads();
 #pragma unroll
         for (int i = 0; i < 16; ++i) do1[i] = dz[i];
@@ -434,7 +434,7 @@ bst_bwd_kernel(const __grid_constant__ BstParams p, const float* __restrict__ g_
             store_row(sm.as + r * kBstLd, do1);
         }
         __syncthreads();
-        bst_colsum(sm.gs, sm.as, kBstRows, vacc[3]);                 // d ln1_g | d ln1_b
+        bst_colsum(sm.gs, sm.as, rows, vacc[3]);                 // d ln1_g | d ln1_b
         __syncthreads();
         float dz1[16], dctx[16];
 #pragma unroll
@@ -442,8 +442,8 @@ bst_bwd_kernel(const __grid_constant__ BstParams p, const float* __restrict__ g_
         if (on) layer_norm16_bwd(do1, sm.vec + VG1 * 16, zh1, rstd1, dz1);
         store_row(sm.gs + r * kBstLd, dz1);
         __syncthreads();
-        bst_outer(sm.gs, sm.cs, kBstRows, macc[MO]);                 // d w_o = dz1 (x) ctx
-        bst_colsum(sm.gs, nullptr, kBstRows, vacc[4]);               // d b_o
+        bst_outer(sm.gs, sm.cs, rows, macc[MO]);                 // d w_o = dz1 (x) ctx
+        bst_colsum(sm.gs, nullptr, rows, vacc[4]);               // d b_o
         if (on) {
             matvec16(sm.w + MO * 256, dz1, dctx);                    // W_o^T dz1
             float ctx[16];
@@ -510,18 +510,18 @@ bst_bwd_kernel(const __grid_constant__ BstParams p, const float* __restrict__ g_
         // ---- F. projection backward, input gradient, position-table gradient
         store_row(sm.gs + r * kBstLd, dq);
         __syncthreads();
-        bst_outer(sm.gs, sm.qks, kBstRows, macc[MQ]);
-        bst_colsum(sm.gs, nullptr, kBstRows, vacc[5]);               // d b_q
+        bst_outer(sm.gs, sm.qks, rows, macc[MQ]);
+        bst_colsum(sm.gs, nullptr, rows, vacc[5]);               // d b_q
         __syncthreads();
         store_row(sm.gs + r * kBstLd, dk);
         __syncthreads();
-        bst_outer(sm.gs, sm.qks, kBstRows, macc[MK]);
-        bst_colsum(sm.gs, nullptr, kBstRows, vacc[6]);               // d b_k
+        bst_outer(sm.gs, sm.qks, rows, macc[MK]);
+        bst_colsum(sm.gs, nullptr, rows, vacc[6]);               // d b_k
         __syncthreads();
         store_row(sm.gs + r * kBstLd, dv);
         __syncthreads();
-        bst_outer(sm.gs, sm.xs, kBstRows, macc[MV]);
-        bst_colsum(sm.gs, nullptr, kBstRows, vacc[7]);               // d b_v
+        bst_outer(sm.gs, sm.xs, rows, macc[MV]);
+        bst_colsum(sm.gs, nullptr, rows, vacc[7]);               // d b_v
         __syncthreads();
         float dqk[16];
 #pragma unroll

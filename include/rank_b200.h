@@ -180,6 +180,20 @@ int rk_afm_bwd(const rk_field_t* fields, int F, const float* w1, const float* b1
                float* g_b1, float* g_w2, float* g_b2, float* partials, int n_ctas,
                int32_t* err_flag, rk_stream_t stream);
 
+/* ---- DeepCrossing residual units (residual_unit + loop, DeepCrossing/deepcrossing.py:25-42,
+ *      148-159), fused with the gather + concat ----------------------------------------------
+ * units: n_units packed per-call weight blocks of rk_resunit_pack_floats(d, H) floats each,
+ *   [W1^T d x Hp][b1 Hp][W2^T Hp x dp][b2 dp][W2 d x Hp][W1 Hp x dp], Hp = roundup(H,8),
+ *   dp = roundup(d,4), zero padded (W1 [H,d], W2 [d,H] as nn.Linear stores them).
+ * nets[(n_units+1), B, d]: nets[0] = the concat row, nets[i+1] = output of unit i (the last one
+ * is the result; all are kept for the backward).  bwd: g_x0[B,d] = d(loss)/d(nets[0]). */
+int rk_resunit_pack_floats(int d, int H);
+int rk_resunits_fwd(const rk_field_t* fields, int F, const float* dense, int n_dense,
+                    const float* units, int n_units, int H, int64_t B, float* nets,
+                    int32_t* err_flag, rk_stream_t stream);
+int rk_resunits_bwd(const float* nets, const float* units, int n_units, int H, int d, int64_t B,
+                    const float* g_out, float* g_x0, rk_stream_t stream);
+
 /* ---- BST transformer block (BSTTransformer.forward BST/bst.py:66-91; gather :224; pooling
  *      :238-241), d_model = 16, nhead in {1,2,4,8,16} ------------------------------------------
  * Input rows x[b,t,:] come either from a table through idx[B,T] (first block: the feedid

@@ -59,7 +59,10 @@ def test_module_matches_reference_fixture(path, small_vocab_dir):
     model.to(DEV)
     outs, grads = golden_cases.replay(model, fx, to_device(fx["inputs"], DEV), to_device(fx["cotangents"], DEV))
     rank_b200.check_index_errors()
-    compare(outs, grads, fx["outputs"], fx["grads"], FP32_TOL)
+    ref64 = golden_cases.build(fx, oracle_models, small_vocab_dir, oracle=True)
+    ref64.load_state_dict(fx["state_dict"], strict=True)
+    _, grads64 = golden_cases.replay(ref64.double(), fx, _to_double(fx["inputs"]), _to_double(fx["cotangents"]))
+    compare(outs, grads, fx["outputs"], fx["grads"], FP32_TOL, grads64)
 
 
 def _pair(name, oracle_name, vocab_dir, *args, **kw):
@@ -225,3 +228,24 @@ def test_bst_rejects_training_dropout_and_bad_heads(wechat_vocab_dir):
     bad = rank_b200.BSTModel(wechat_vocab_dir, dropout_rate=0.0, nhead=3, max_seq_length=20).to(DEV)
     with pytest.raises(RuntimeError):      # the reference's view() raises for nhead 3 / 5 as well
         bad(batch["dense"], batch["category"], batch["seq_feedid"], batch["seq_length"])
+
+
+@pytest.mark.parametrize("B,H,N", [(8192, 128, 2), (1000, 256, 2), (333, 24, 4), (64, 100, 0), (2048, 7, 1)])
+def test_deepcrossing_vs_oracle_wechat_sizes(wechat_vocab_dir, B, H, N):
+    ours, ref = _pair("DeepCrossingModel", "OracleDeepCrossing", wechat_vocab_dir, residual_internal_dim=H,
+                      residual_network_num=N)
+    compare(*_run_both(ours, ref, "DeepCrossingModel", synthetic.side_batch(B)))
+
+
+def test_residual_unit_function():
+    gen = torch.Generator().manual_seed(4)
+    x = torch.randn(300, 50, generator=gen, requires_grad=True)
+    torch.manual_seed(6)
+    l1, l2 = torch.nn.Linear(50, 128), torch.nn.Linear(128, 50)
+    want = torch.relu(x + l2(torch.relu(l1(x))))
+    want.sum().backward()
+    xa = x.detach().to(DEV).requires_grad_()
+    torch.manual_seed(6)
+    got = rank_b200.residual_unit(xa, 128, 0)
+    got.sum().backward()
+    assert rel_err(got, want) <= FP32_TOL and rel_err(xa.grad, x.grad) <= FP32_TOL
