@@ -39,9 +39,11 @@ def compare(outs, grads, ref_outs, ref_grads, tol, grads64=None):
         own = float(g.abs().max())
         if own < 1e-4 * gmax:
             # mathematically zero (a Linear bias feeding BatchNorm, the key bias of a softmax
-            # attention): only rounding noise on both sides -> absolute bound against the model scale
+            # attention, the last LayerNorm bias before a BatchNorm tower): both sides hold only the
+            # rounding noise of large cancelling sums -> the 1e-5 bar is taken against the model's
+            # gradient scale instead of against the tensor itself
             err = float((grads[k].detach().cpu().double() - g.double()).abs().max())
-            assert err <= 1e-7 * gmax, f"grad {k} (numerically zero): abs err {err:.3e} vs scale {gmax:.3e}"
+            assert err <= tol * gmax, f"grad {k} (numerically zero): abs err {err:.3e} vs scale {gmax:.3e}"
         else:
             e = rel_err(grads[k], g)
             if e > tol and grads64 is not None:
