@@ -10,7 +10,7 @@
 //   * fields with <= 8192 occurrences (every per-sample column at batch <= 8192): ONE launch,
 //     one 1024-thread CTA per field, the whole sort in shared memory (packed key|occurrence
 //     words, up to 9-bit digits, warp-match ranking) — no global round trips between passes;
-//   * larger fields (DIN/BST history columns): multi-CTA passes of tile histogram, scan and
+//   * larger fields (DIN/BST history columns): multi-CTA passes of tile histogram, per-digit scan and
 //     stable scatter with up to 10-bit digits.
 #include <string.h>
 #include "common.cuh"
@@ -181,40 +181,34 @@ tile_hist_kernel(const uint32_t* __restrict__ keys, int64_t n, int shift, int bi
         hist[(int64_t)d * n_tiles + blockIdx.x] = h[d];
 }
 
-// Exclusive scan of m counters in place, one CTA.
-__global__ void __launch_bounds__(1024)
-scan_kernel(uint32_t* __restrict__ data, int64_t m) {
-    __shared__ uint32_t warp_tot[32];
-    const int     t    = threadIdx.x;
-    const int64_t per  = (m + 1023) / 1024;
-    const int64_t lo   = t * per;
-    const int64_t hi   = lo + per < m ? lo + per : m;
-    uint32_t      sum  = 0;
-    for (int64_t i = lo; i < hi; ++i) sum += data[i];
-    uint32_t inc = sum;
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-        uint32_t v = __shfl_up_sync(kFull, inc, o);
-        if ((t & 31) >= o) inc += v;
-    }
-    if ((t & 31) == 31) warp_tot[t >> 5] = inc;
+// Per digit (one CTA each): exclusive scan of that digit's tile counts in place, and its total.
+__global__ void __launch_bounds__(256)
+row_scan_kernel(uint32_t* __restrict__ hist, int n_tiles, uint32_t* __restrict__ totals) {
+    __shared__ uint32_t warp_tot[8];
+    __shared__ uint32_t carry_s;
+    uint32_t* row = hist + (int64_t)blockIdx.x * n_tiles;
+    const int t = threadIdx.x, lane = t & 31, w = t >> 5;
+    if (t == 0) carry_s = 0;
     __syncthreads();
-    if (t < 32) {
-        uint32_t w = warp_tot[t], winc = w;
+    for (int base = 0; base < n_tiles; base += 256) {
+        const int i = base + t;
+        const uint32_t c = i < n_tiles ? row[i] : 0u;
+        uint32_t inc = c;
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) {
-            uint32_t v = __shfl_up_sync(kFull, winc, o);
-            if (t >= o) winc += v;
+            const uint32_t v = __shfl_up_sync(kFull, inc, o);
+            if (lane >= o) inc += v;
         }
-        warp_tot[t] = winc - w;
+        if (lane == 31) warp_tot[w] = inc;
+        __syncthreads();
+        uint32_t before = carry_s;
+        for (int ww = 0; ww < w; ++ww) before += warp_tot[ww];
+        if (i < n_tiles) row[i] = before + inc - c;
+        __syncthreads();
+        if (t == 255) carry_s = before + inc;
+        __syncthreads();
     }
-    __syncthreads();
-    uint32_t run = warp_tot[t >> 5] + inc - sum;
-    for (int64_t i = lo; i < hi; ++i) {
-        uint32_t c = data[i];
-        data[i]    = run;
-        run += c;
-    }
+    if (t == 0) totals[blockIdx.x] = carry_s;
 }
 
 // Stable scatter of one tile: ranks are taken in (warp, round, lane) = input order.  On the
@@ -223,10 +217,32 @@ __global__ void __launch_bounds__(kSortThreads)
 scatter_kernel(const uint32_t* __restrict__ keys_in, const uint32_t* __restrict__ vals_in,
                uint32_t* __restrict__ keys_out, uint32_t* __restrict__ vals_out, int64_t n,
                int shift, int bins, int n_tiles, const uint32_t* __restrict__ hist_scanned,
-               uint32_t add_base) {
+               const uint32_t* __restrict__ totals, uint32_t add_base) {
     extern __shared__ uint32_t cnt[];   // [kSortWarps][bins]
+    __shared__ uint32_t dbase[kMaxBins];   // keys with a smaller digit, over all tiles
+    __shared__ uint32_t wsum[kSortWarps];
     const int t = threadIdx.x, w = t >> 5, lane = t & 31;
     for (int i = t; i < kSortWarps * bins; i += kSortThreads) cnt[i] = 0;
+    {   // exclusive scan of the digit totals: 4 consecutive digits per thread
+        uint32_t v[4], sum = 0;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) { v[j] = 4 * t + j < bins ? totals[4 * t + j] : 0u; sum += v[j]; }
+        uint32_t inc = sum;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const uint32_t x = __shfl_up_sync(kFull, inc, o);
+            if (lane >= o) inc += x;
+        }
+        if (lane == 31) wsum[w] = inc;
+        __syncthreads();
+        uint32_t run = inc - sum;
+        for (int ww = 0; ww < w; ++ww) run += wsum[ww];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            if (4 * t + j < bins) dbase[4 * t + j] = run;
+            run += v[j];
+        }
+    }
     __syncthreads();
 
     const int64_t  wbase = (int64_t)blockIdx.x * kSortTile + (int64_t)w * (kSortRounds * 32);
@@ -253,7 +269,7 @@ scatter_kernel(const uint32_t* __restrict__ keys_in, const uint32_t* __restrict_
     }
     __syncthreads();
     for (int d = t; d < bins; d += kSortThreads) {
-        uint32_t run = hist_scanned[(int64_t)d * n_tiles + blockIdx.x];
+        uint32_t run = dbase[d] + hist_scanned[(int64_t)d * n_tiles + blockIdx.x];
 #pragma unroll
         for (int ww = 0; ww < kSortWarps; ++ww) {
             uint32_t c = cnt[ww * bins + d];
@@ -292,7 +308,7 @@ size_t rk_plan_workspace_bytes(int64_t n_total) {
     // and the tile histograms
     const size_t n     = (size_t)n_total;
     const size_t tiles = (size_t)rk::ceil_div(n_total > 0 ? n_total : 1, rk::kSortTile);
-    return 4 * rk::al256(n * 4) + rk::al256(tiles * rk::kMaxBins * 4);
+    return 4 * rk::al256(n * 4) + rk::al256((tiles + 1) * rk::kMaxBins * 4);   // + the digit totals
 }
 
 int rk_plan_build(const int64_t* const* idx, const int64_t* n, const int64_t* rows, int F,
@@ -363,6 +379,7 @@ int rk_plan_build(const int64_t* const* idx, const int64_t* n, const int64_t* ro
     uint32_t* kB = (uint32_t*)(base + 2 * arr);
     uint32_t* vB = (uint32_t*)(base + 3 * arr);
     uint32_t* hist = (uint32_t*)(base + 4 * arr);
+    uint32_t* totals = hist + (size_t)ceil_div(total, kSortTile) * kMaxBins;
     for (int f = 0; f < F; ++f) {
         if (n[f] == 0 || is_small(n[f], fk[f].bits)) continue;
         const int64_t nf     = n[f];
@@ -384,10 +401,10 @@ int rk_plan_build(const int64_t* const* idx, const int64_t* n, const int64_t* ro
             uint32_t* vout = last ? perm + fk[f].start : (vin == vA ? vB : vA);
             tile_hist_kernel<<<tiles, kSortThreads, 0, s>>>(kin, nf, p * dbits, bins, tiles, hist);
             RK_LAUNCH_CHECK();
-            scan_kernel<<<1, 1024, 0, s>>>(hist, (int64_t)tiles * bins);
+            row_scan_kernel<<<bins, 256, 0, s>>>(hist, tiles, totals);
             RK_LAUNCH_CHECK();
             scatter_kernel<<<tiles, kSortThreads, (size_t)kSortWarps * bins * 4, s>>>(
-                kin, vin, kout, vout, nf, p * dbits, bins, tiles, hist, last ? fk[f].key_base : 0u);
+                kin, vin, kout, vout, nf, p * dbits, bins, tiles, hist, totals, last ? fk[f].key_base : 0u);
             RK_LAUNCH_CHECK();
             kin = kout;
             vin = vout;
