@@ -17,7 +17,8 @@ from .sparse import GatherConcat, GradSource, OccurrencePlan, gather_concat
 from .deepfm import DeepFM
 from .dcn import DCNModel, cross_layer
 from .deepcrossing import DeepCrossingModel, residual_unit
-from .din import DIN, Dice, din_attention, din_collate_fn
+from .din import (DIN, Dice, din_attention, din_collate_fn, get_activation_unit_precision,
+                  set_activation_unit_precision)
 from .afm import AFM, create_feature_columns
 from .bst import BSTModel, BSTTransformer, leakyrelu, load_vocabulary
 
@@ -25,6 +26,7 @@ __all__ = [
     "RankB200Error", "check_index_errors", "library_path",
     "VOCAB_FILE", "WECHAT_VOCAB_LINES", "table_heights", "write_vocab_dir",
     "GradSource", "OccurrencePlan", "gather_concat",
-    "DeepFM", "DCNModel", "cross_layer", "DeepCrossingModel", "residual_unit", "DIN", "Dice", "din_attention", "din_collate_fn",
+    "DeepFM", "DCNModel", "cross_layer", "DeepCrossingModel", "residual_unit", "DIN", "Dice", "din_attention", "din_collate_fn", "set_activation_unit_precision",
+    "get_activation_unit_precision",
     "AFM", "create_feature_columns", "BSTModel", "BSTTransformer", "leakyrelu", "load_vocabulary",
 ]

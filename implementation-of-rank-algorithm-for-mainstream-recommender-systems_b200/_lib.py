@@ -36,7 +36,8 @@ class RkDinArgs(C.Structure):
                 ("dense_cols", C.c_void_p), ("dense_stride", C.c_int64),
                 ("target", RkField), ("history", RkField), ("hist_len", C.c_void_p),
                 ("T", C.c_int32), ("att_off", C.c_int32), ("width", C.c_int32),
-                ("l2_from", C.c_int32), ("use_softmax", C.c_int32), ("mlp", C.c_void_p),
+                ("l2_from", C.c_int32), ("use_softmax", C.c_int32), ("precision", C.c_int32),
+                ("mlp", C.c_void_p),
                 ("B", C.c_int64)]
 
 

@@ -517,6 +517,407 @@ din_bwd_kernel(const __grid_constant__ DinParams p, const float* __restrict__ co
     }
 }
 
+// ===========================================================================================
+// Tensor-core forward (D = 16): the activation-unit MLP on tcgen05, bf16 operands, fp32
+// accumulators in TMEM.  One thread = one (b,t) row = one TMEM lane; 128 rows per tile.
+//   A1[128x64] = [q,k,q-k,q*k] (bf16, K-major, 128-byte swizzle, built by the row's thread)
+//   D1 = A1 . W1^T (4 x tcgen05.mma M128 N64 K16) -> tcgen05.ld -> +b1, ReLU, mask bits, bf16
+//   A2 = relu(D1) rewritten in place over A1;  D2 = A2 . W2^T (M128 N32) -> +b2, ReLU, . w3
+// Gathered K rows stay in fp32 registers for the pooling.  Everything outside the two GEMMs is
+// the same math as din_fwd_kernel; tolerance of this path is the bf16 bar (2e-2).
+// ===========================================================================================
+namespace tc {
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+// Bounded wait: a faulted MMA must trap, not hang the GPU.
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    const uint32_t addr = smem_u32(bar);
+    for (uint32_t spin = 0; spin < (1u << 26); ++spin) {
+        uint32_t ok;
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(ok) : "r"(addr), "r"(parity) : "memory");
+        if (ok) return;
+    }
+    __trap();
+}
+__device__ __forceinline__ void tmem_alloc(uint32_t* dst_smem, uint32_t cols) {   // one full warp
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)), "r"(cols));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t cols) {     // same warp
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(cols));
+}
+__device__ __forceinline__ void fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+// K-major, 128-byte-swizzled operand: rows of 64 bf16 (128 B), 8-row groups 1024 B apart.
+__device__ __forceinline__ uint64_t umma_desc(uint32_t smem_addr) {
+    uint64_t d = 0;
+    d |= (uint64_t)((smem_addr & 0x3ffff) >> 4);      // start address   [0,14)
+    d |= (uint64_t)1 << 16;                           // leading byte offset (unused for swizzled K-major)
+    d |= (uint64_t)(1024 >> 4) << 32;                 // stride byte offset  [32,46)
+    d |= (uint64_t)1 << 46;                           // descriptor version (Blackwell)
+    d |= (uint64_t)2 << 61;                           // SWIZZLE_128B
+    return d;
+}
+// kind::f16, A = B = bf16 (K-major), D = f32, M = 128
+__host__ __device__ constexpr uint32_t umma_idesc(int N) {
+    return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+}
+__device__ __forceinline__ void umma_bf16(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
+                                          uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+// 32 consecutive fp32 columns of this thread's TMEM lane
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
+    uint32_t r[32];
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+          "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+          "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+          "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr));
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+    for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+}
+__device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
+    uint32_t r;
+    asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+    return r;
+}
+// Write 8 consecutive K elements (one 16-byte chunk c) of row r into a swizzled operand tile.
+__device__ __forceinline__ void store_chunk(uint8_t* tile, int r, int c, const float (&v)[8]) {
+    uint4 w;
+    w.x = pack_bf16(v[0], v[1]); w.y = pack_bf16(v[2], v[3]);
+    w.z = pack_bf16(v[4], v[5]); w.w = pack_bf16(v[6], v[7]);
+    *reinterpret_cast<uint4*>(tile + r * 128 + ((c ^ (r & 7)) << 4)) = w;
+}
+
+constexpr int kTcThreads  = 128;
+constexpr int kTcTmemCols = 128;     // 64 (layer 1) + 32 (layer 2), power of two
+
+struct TcSmem {
+    uint8_t *a, *w1, *w2;              // swizzled bf16 tiles: [128][64], [64][64], [32][64]
+    float *vec, *q, *att, *score, *wt, *pool;
+    int *row_s, *row_t, *len, *start;
+    uint64_t* bar;
+    uint32_t* tmem_slot;
+    __device__ explicit TcSmem(uint8_t* base) {
+        uint8_t* p = base;
+        a = p;   p += 128 * 128;
+        w1 = p;  p += 64 * 128;
+        w2 = p;  p += 32 * 128;
+        vec = (float*)p;    p += sizeof(float) * (kH1 + 2 * kH2 + 4);
+        q = (float*)p;      p += sizeof(float) * kSamples * 16;
+        att = (float*)p;    p += sizeof(float) * kSamples * 16;
+        score = (float*)p;  p += sizeof(float) * kRows;
+        wt = (float*)p;     p += sizeof(float) * kRows;
+        pool = (float*)p;   p += sizeof(float) * kRows * 17;
+        row_s = (int*)p;    p += sizeof(int) * kRows;
+        row_t = (int*)p;    p += sizeof(int) * kRows;
+        len = (int*)p;      p += sizeof(int) * kSamples;
+        start = (int*)p;    p += sizeof(int) * (kSamples + 4);
+        bar = (uint64_t*)p; p += 8;
+        tmem_slot = (uint32_t*)p;
+    }
+    static size_t bytes() {
+        return 1024 /* alignment slack */ + 128 * 128 + 64 * 128 + 32 * 128 +
+               sizeof(float) * (kH1 + 2 * kH2 + 4 + 2 * kSamples * 16 + 2 * kRows + kRows * 17) +
+               sizeof(int) * (2 * kRows + 2 * kSamples + 4) + 16;
+    }
+};
+
+__global__ void __launch_bounds__(kTcThreads)
+din_fwd_tc_kernel(const __grid_constant__ DinParams p, float* __restrict__ concat_all,
+                  float* __restrict__ norm_out, float* __restrict__ att_w, uint32_t* __restrict__ masks,
+                  int32_t* err_flag) {
+    extern __shared__ uint8_t smem_raw_tc[];
+    uint8_t* base = smem_raw_tc + ((1024u - (smem_u32(smem_raw_tc) & 1023u)) & 1023u);   // swizzle atoms need 1024 B
+    TcSmem sm(base);
+    constexpr int D = 16;
+    const int T = p.T;
+    const MlpLayout L(D);
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int64_t b0 = (int64_t)blockIdx.x * kSamples;
+    const int n_samples = (int)((p.B - b0) < kSamples ? (p.B - b0) : kSamples);
+
+    // ---- one-time setup: barrier, TMEM, weights (fp32 -> bf16, swizzled, K-major = as registered)
+    if (tid == 0) mbar_init(sm.bar, 1);
+    if (warp == 0) tmem_alloc(sm.tmem_slot, kTcTmemCols);
+    for (int item = tid; item < 64 * 8; item += kTcThreads) {         // W1[n][k]: 64 rows x 8 chunks
+        const int n = item >> 3, c = item & 7;
+        float v[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) v[j] = __ldg(p.mlp + L.w1 + n * 64 + c * 8 + j);
+        store_chunk(sm.w1, n, c, v);
+    }
+    for (int item = tid; item < 32 * 8; item += kTcThreads) {         // W2[n][k]: 32 rows x 8 chunks
+        const int n = item >> 3, c = item & 7;
+        float v[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) v[j] = __ldg(p.mlp + L.w2 + n * 64 + c * 8 + j);
+        store_chunk(sm.w2, n, c, v);
+    }
+    for (int i = tid; i < kH1; i += kTcThreads) sm.vec[i] = __ldg(p.mlp + L.b1 + i);
+    for (int i = tid; i < kH2; i += kTcThreads) {
+        sm.vec[kH1 + i]       = __ldg(p.mlp + L.b2 + i);
+        sm.vec[kH1 + kH2 + i] = __ldg(p.mlp + L.w3 + i);
+    }
+    if (tid == 0) sm.vec[kH1 + 2 * kH2] = __ldg(p.mlp + L.b3);
+    for (int i = tid; i < n_samples * D; i += kTcThreads) {
+        const int s = i / D, e = i - s * D;
+        const int64_t row = checked_row(__ldg(p.tgt_idx + b0 + s), p.tgt_rows, err_flag);
+        sm.q[i] = __ldg(p.tgt_w + row * D + e);
+    }
+    if (tid < kSamples) sm.len[tid] = tid < n_samples ? clip_len(__ldg(p.his_len + b0 + tid), T) : 0;
+    fence_async_smem();
+    fence_before();
+    __syncthreads();
+    fence_after();
+    const uint32_t tmem = *sm.tmem_slot;
+    const float* b1 = sm.vec;
+    const float* b2 = sm.vec + kH1;
+    const float* w3 = sm.vec + kH1 + kH2;
+    const float  b3 = sm.vec[kH1 + 2 * kH2];
+    const float  inv_sqrt_d = 0.25f;
+    const uint64_t a_desc  = umma_desc(smem_u32(sm.a));
+    const uint64_t w1_desc = umma_desc(smem_u32(sm.w1));
+    const uint64_t w2_desc = umma_desc(smem_u32(sm.w2));
+    const uint32_t my_tmem = tmem + ((uint32_t)(warp * 32) << 16);
+    uint32_t phase = 0;
+
+    int s_begin = 0;
+    while (s_begin < n_samples) {
+        int s_end;
+        int n_rows = 0;
+        {
+            int s = s_begin;
+            while (s < n_samples && n_rows + sm.len[s] <= kRows) { n_rows += sm.len[s]; ++s; }
+            s_end = s;
+        }
+        if (tid < kSamples + 1) {
+            int acc = 0;
+            for (int s = s_begin; s < s_begin + tid && s < s_end; ++s) acc += sm.len[s];
+            sm.start[tid] = acc;
+        }
+        __syncthreads();
+        {
+            int s = s_begin;
+            while (s + 1 < s_end && tid >= sm.start[s + 1 - s_begin]) ++s;
+            sm.row_s[tid] = s;
+            sm.row_t[tid] = tid - sm.start[s - s_begin];
+        }
+        const bool on = tid < n_rows;
+        const int  my_s = sm.row_s[tid], my_t = sm.row_t[tid];
+        float k[16];
+#pragma unroll
+        for (int e = 0; e < 16; ++e) k[e] = 0.f;
+        if (n_rows > 0) {
+            // ---- build this thread's row of A1 = [q, k, q-k, q*k]
+            float qv[16];
+#pragma unroll
+            for (int e = 0; e < 16; ++e) qv[e] = 0.f;
+            if (on) {
+                const int64_t row = checked_row(__ldg(p.his_idx + (b0 + my_s) * T + my_t), p.his_rows, err_flag);
+                const float4* src = reinterpret_cast<const float4*>(p.his_w + row * D);
+#pragma unroll
+                for (int c = 0; c < 4; ++c) {
+                    const float4 v = __ldg(src + c);
+                    k[4 * c] = v.x; k[4 * c + 1] = v.y; k[4 * c + 2] = v.z; k[4 * c + 3] = v.w;
+                }
+#pragma unroll
+                for (int e = 0; e < 16; ++e) qv[e] = sm.q[my_s * D + e];
+            }
+#pragma unroll
+            for (int half = 0; half < 2; ++half) {
+                float a[8], b[8], c[8], d[8];
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    a[j] = qv[8 * half + j];
+                    b[j] = k[8 * half + j];
+                    c[j] = a[j] - b[j];
+                    d[j] = a[j] * b[j];
+                }
+                store_chunk(sm.a, tid, 0 + half, a);
+                store_chunk(sm.a, tid, 2 + half, b);
+                store_chunk(sm.a, tid, 4 + half, c);
+                store_chunk(sm.a, tid, 6 + half, d);
+            }
+            fence_async_smem();
+            fence_before();
+            __syncthreads();
+            // ---- layer 1 on the tensor core
+            if (tid == 0) {
+                fence_after();
+#pragma unroll
+                for (int kk = 0; kk < 4; ++kk)      // K = 64 = 4 x 16; +32 B per step inside the swizzle atom
+                    umma_bf16(tmem, a_desc + 2 * kk, w1_desc + 2 * kk, umma_idesc(64), kk > 0);
+                umma_commit(sm.bar);
+            }
+            mbar_wait(sm.bar, phase);
+            phase ^= 1;
+            fence_after();
+            uint32_t m1a = 0, m1b = 0;
+#pragma unroll
+            for (int half = 0; half < 2; ++half) {
+                float v[32];
+                tmem_ld32(my_tmem + 32 * half, v);
+                uint32_t bits = 0;
+#pragma unroll
+                for (int j = 0; j < 32; ++j) {
+                    v[j] = fmaxf(v[j] + b1[32 * half + j], 0.f);
+                    bits |= (v[j] > 0.f ? 1u : 0u) << j;
+                }
+                if (half == 0) m1a = bits; else m1b = bits;
+#pragma unroll
+                for (int c = 0; c < 4; ++c) {
+                    float h8[8];
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) h8[j] = v[8 * c + j];
+                    store_chunk(sm.a, tid, 4 * half + c, h8);      // A2 = relu(layer 1), in place
+                }
+            }
+            fence_async_smem();
+            fence_before();
+            __syncthreads();
+            // ---- layer 2 on the tensor core
+            if (tid == 0) {
+                fence_after();
+#pragma unroll
+                for (int kk = 0; kk < 4; ++kk)
+                    umma_bf16(tmem + 64, a_desc + 2 * kk, w2_desc + 2 * kk, umma_idesc(32), kk > 0);
+                umma_commit(sm.bar);
+            }
+            mbar_wait(sm.bar, phase);
+            phase ^= 1;
+            fence_after();
+            {
+                float v[32];
+                tmem_ld32(my_tmem + 64, v);
+                float sc = b3;
+                uint32_t m2 = 0;
+#pragma unroll
+                for (int j = 0; j < 32; ++j) {
+                    const float h = fmaxf(v[j] + b2[j], 0.f);
+                    m2 |= (h > 0.f ? 1u : 0u) << j;
+                    sc = fmaf(h, w3[j], sc);
+                }
+                sm.score[tid] = sc;
+                if (on && masks) {
+                    uint32_t* mk = masks + ((b0 + my_s) * T + my_t) * 3;
+                    mk[0] = m1a; mk[1] = m1b; mk[2] = m2;
+                }
+            }
+            fence_before();
+            __syncthreads();
+        }
+        // ---- attention weights per sample (warp per sample), then weighted pooling through smem
+        for (int s = s_begin + warp; s < s_end; s += kTcThreads / 32) {
+            const int len = sm.len[s], r0 = sm.start[s - s_begin];
+            float* wrow = att_w + (b0 + s) * T;
+            if (len == 0) {
+                const float u = p.use_softmax ? 1.0f / (float)T : 0.f;
+                for (int t = lane; t < T; t += 32) wrow[t] = u;
+                continue;
+            }
+            float inv_sum = 1.f, mx = 0.f;
+            if (p.use_softmax) {
+                mx = -INFINITY;
+                for (int t = lane; t < len; t += 32) mx = fmaxf(mx, sm.score[r0 + t] * inv_sqrt_d);
+                mx = warp_max(mx);
+                float sum = 0.f;
+                for (int t = lane; t < len; t += 32) sum += expf(sm.score[r0 + t] * inv_sqrt_d - mx);
+                inv_sum = 1.0f / warp_sum(sum);
+            }
+            for (int t = lane; t < T; t += 32) {
+                float w = 0.f;
+                if (t < len) {
+                    w = p.use_softmax ? expf(sm.score[r0 + t] * inv_sqrt_d - mx) * inv_sum : sm.score[r0 + t];
+                    sm.wt[r0 + t] = w;
+                }
+                wrow[t] = w;
+            }
+        }
+        __syncthreads();
+        {
+            const float w = on ? sm.wt[tid] : 0.f;
+#pragma unroll
+            for (int e = 0; e < 16; ++e) sm.pool[tid * 17 + e] = w * k[e];
+        }
+        __syncthreads();
+        for (int item = tid; item < (s_end - s_begin) * 16; item += kTcThreads) {
+            const int s = s_begin + (item >> 4), e = item & 15;
+            const int len = sm.len[s], r0 = sm.start[s - s_begin];
+            float a = 0.f;
+            if (len > 0) {
+                for (int t = 0; t < len; ++t) a += sm.pool[(r0 + t) * 17 + e];
+            } else if (p.use_softmax) {      // uniform 1/T over ALL positions (they hold the padding score)
+                const float u = 1.0f / (float)T;
+                for (int t = 0; t < T; ++t) {
+                    const int64_t row = checked_row(__ldg(p.his_idx + (b0 + s) * T + t), p.his_rows, err_flag);
+                    a = fmaf(u, __ldg(p.his_w + row * D + e), a);
+                }
+            }
+            sm.att[s * 16 + e] = a;
+        }
+        __syncthreads();
+        s_begin = s_end;
+    }
+
+    // ---- assemble the concat row and the L2 norm: one warp per sample
+    for (int s = warp; s < n_samples; s += kTcThreads / 32) {
+        const int64_t b = b0 + s;
+        float* out = concat_all + b * p.width;
+        float ss = 0.f;
+        for (int c = lane; c < p.width; c += 32) {
+            float v;
+            if (c < p.n_dense) {
+                v = __ldg(p.dense_col[c] + b * p.dense_stride);
+            } else if (c >= p.att_off && c < p.att_off + D) {
+                v = sm.att[s * 16 + c - p.att_off];
+            } else if (c >= p.tgt_off && c < p.tgt_off + D) {
+                v = sm.q[s * D + c - p.tgt_off];
+            } else {
+                v = 0.f;
+                for (int f = 0; f < p.cat.F; ++f)
+                    if (c >= p.cat.off[f] && c < p.cat.off[f] + p.cat.dim[f]) {
+                        const int64_t row = checked_row(__ldg(p.cat.idx[f] + b), p.cat.rows[f], err_flag);
+                        v = __ldg(p.cat.weight[f] + row * p.cat.dim[f] + c - p.cat.off[f]);
+                    }
+            }
+            out[c] = v;
+            if (c >= p.l2_from) ss = fmaf(v, v, ss);
+        }
+        ss = warp_sum(ss);
+        if (lane == 0 && norm_out) norm_out[b] = sqrtf(ss);
+    }
+    fence_before();
+    __syncthreads();
+    if (warp == 0) tmem_dealloc(tmem, kTcTmemCols);
+}
+
+}  // namespace tc
+
 }  // namespace rk
 
 extern "C" {
@@ -568,9 +969,20 @@ int rk_din_fwd(const rk_din_args_t* args, float* concat_all, float* norm, float*
     if (int rc = din_pack(args, &p)) return rc;
     RK_CHECK_ARG(concat_all && att_w, "din_fwd: NULL output");
     if (p.B == 0) return 0;
+    const int grid = (int)ceil_div(p.B, kSamples);
+    if (args->precision == RK_DIN_BF16_TENSOR) {
+        RK_CHECK_ARG(p.D == 16, "din_fwd: the tensor-core activation unit is built for D = 16 (got %d)", p.D);
+        const size_t smem_tc = tc::TcSmem::bytes();
+        RK_CUDA(cudaFuncSetAttribute(tc::din_fwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     (int)smem_tc));
+        tc::din_fwd_tc_kernel<<<grid, tc::kTcThreads, smem_tc, (cudaStream_t)stream_>>>(
+            p, concat_all, norm, att_w, relu_masks, err_flag);
+        RK_LAUNCH_CHECK();
+        return 0;
+    }
+    RK_CHECK_ARG(args->precision == RK_DIN_FP32, "din_fwd: unknown precision %d", args->precision);
     size_t smem;
     if (int rc = din_smem(p.D, &smem, (const void*)din_fwd_kernel)) return rc;
-    const int grid = (int)ceil_div(p.B, kSamples);
     din_fwd_kernel<<<grid, kDinThreads, smem, (cudaStream_t)stream_>>>(p, concat_all, norm, att_w,
                                                                        relu_masks, err_flag);
     RK_LAUNCH_CHECK();

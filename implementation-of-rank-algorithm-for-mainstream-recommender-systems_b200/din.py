@@ -28,6 +28,21 @@ from .vocab import table_heights
 SEQ = "his_read_comment_7d_seq"
 SEQ_LEN = "his_read_comment_7d_seq_length"
 
+_PRECISION = "fp32"
+
+
+def set_activation_unit_precision(mode):
+    """'fp32': the activation-unit MLP in fp32 on the FMA pipe (parity 1e-5, the default).
+    'bf16': the MLP on tcgen05 tensor cores, bf16 operands, fp32 accumulation (parity 2e-2)."""
+    global _PRECISION
+    if mode not in ("fp32", "bf16"):
+        raise ValueError("precision must be 'fp32' or 'bf16'")
+    _PRECISION = mode
+
+
+def get_activation_unit_precision():
+    return _PRECISION
+
 
 class Dice(nn.Module):
     """Data-adaptive activation of the DIN tower (DIN/din.py:26-36) — torch, not on the hot path."""
@@ -77,7 +92,7 @@ def draw_attention_mlp(embedding_dim):
 
 
 def _din_args(cat_tables, cat_idx, cat_offsets, dense_cols, target_w, target_idx, tgt_off, his_w,
-              his_idx, his_len, att_off, width, l2_from, use_softmax, mlp):
+              his_idx, his_len, att_off, width, l2_from, use_softmax, mlp, precision=None):
     """rk_din_args_t + the objects that must outlive the call."""
     fields, keep = field_array(cat_tables, cat_idx, cat_offsets)
     a = _lib.RkDinArgs()
@@ -103,6 +118,9 @@ def _din_args(cat_tables, cat_idx, cat_offsets, dense_cols, target_w, target_idx
     a.hist_len = hl.data_ptr()
     a.T = int(hi.shape[1])
     a.att_off, a.width, a.l2_from, a.use_softmax = att_off, width, l2_from, int(bool(use_softmax))
+    precision = _PRECISION if precision is None else precision
+    # the tensor-core unit exists for D = 16 (the model's dim); other dims run the fp32 kernel
+    a.precision = 1 if (precision == "bf16" and int(his_w.shape[1]) == 16) else 0
     mlp = _lib.require_cuda(mlp, "attention mlp", torch.float32)
     if mlp.numel() != _lib.load().rk_din_mlp_floats(int(hw.shape[1])):
         raise ValueError("packed attention weights have the wrong size")
@@ -118,7 +136,7 @@ class _DinHotPath(torch.autograd.Function):
     @staticmethod
     def forward(ctx, cfg, mlp, *args):
         lib = _lib.load()
-        n_dense, F, offsets, use_softmax = cfg
+        n_dense, F, offsets, use_softmax, precision = cfg
         dense_cols = args[:n_dense]
         cat_idx = args[n_dense:n_dense + F]
         tgt_idx, his_idx, his_len = args[n_dense + F:n_dense + F + 3]
@@ -128,7 +146,7 @@ class _DinHotPath(torch.autograd.Function):
         tgt_off = (offsets[-1] + int(cat_tabs[-1].shape[1])) if F else n_dense
         att_off, width = tgt_off + D, tgt_off + 2 * D
         a, keep = _din_args(cat_tabs, cat_idx, offsets, dense_cols, tgt_w, tgt_idx, tgt_off, his_w, his_idx,
-                            his_len, att_off, width, n_dense, use_softmax, mlp)
+                            his_len, att_off, width, n_dense, use_softmax, mlp, precision)
         B, T = int(a.B), int(a.T)
         dev = his_w.device
         need_grad = any(ctx.needs_input_grad)
@@ -159,7 +177,7 @@ class _DinHotPath(torch.autograd.Function):
     @staticmethod
     def backward(ctx, g_concat, g_norm):
         lib = _lib.load()
-        n_dense, F, offsets, _ = ctx.cfg
+        n_dense, F, offsets = ctx.cfg[:3]
         concat_all, norm, att_w, masks = ctx.saved_tensors
         B, T, D, width, tgt_off = ctx.shape
         n_in = 2 + n_dense + 2 * F + 5
@@ -262,6 +280,7 @@ class DIN(nn.Module):
         self.output_layer = nn.Linear(width, 1)
         self._ephemeral = EphemeralBuffer()
         self.ephemeral_frozen = False
+        self.activation_unit_precision = None     # None: follow set_activation_unit_precision()
 
     def draw_ephemeral(self, device=None):
         """Replay one forward's CPU-generator draws (att_net, DIN/din.py:61-67) onto the GPU."""
@@ -281,7 +300,7 @@ class DIN(nn.Module):
             mlp = self._ephemeral.views([(_lib.load().rk_din_mlp_floats(self.embeddings[SEQ].embedding_dim),)])[0]
         else:
             mlp = self.draw_ephemeral(dev)
-        cfg = (len(dense_cols), len(cols), tuple(offsets), bool(self.use_softmax))
+        cfg = (len(dense_cols), len(cols), tuple(offsets), bool(self.use_softmax), self.activation_unit_precision)
         concat_all, norm = _DinHotPath.apply(
             cfg, mlp, *dense_cols, *[category[c] for c in cols], target['feedid'], sequence[SEQ],
             sequence[SEQ_LEN], *[self.embeddings[c].weight for c in cols],

@@ -150,9 +150,14 @@ typedef struct rk_din_args {
     int32_t             width;        /* row width of concat_all */
     int32_t             l2_from;      /* first column under the L2 norm */
     int32_t             use_softmax;
+    int32_t             precision;    /* RK_DIN_FP32: fp32 SIMT MLP (1e-5 parity);
+                                         RK_DIN_BF16_TENSOR: the activation-unit MLP on tcgen05 with
+                                         bf16 operands / fp32 TMEM accumulators (D = 16, 2e-2 bar) */
     const float*        mlp;
     int64_t             B;
 } rk_din_args_t;
+#define RK_DIN_FP32 0
+#define RK_DIN_BF16_TENSOR 1
 
 int rk_din_mlp_floats(int D);
 int rk_din_fwd(const rk_din_args_t* args, float* concat_all, float* norm, float* att_w,

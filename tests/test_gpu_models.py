@@ -257,3 +257,20 @@ def test_residual_unit_function():
     got = rank_b200.residual_unit(xa, 128, 0)
     got.sum().backward()
     assert rel_err(got, want) <= FP32_TOL and rel_err(xa.grad, x.grad) <= FP32_TOL
+
+
+BF16_TOL = 2e-2     # north star: tolerance of the bf16 tensor-core paths
+
+
+@pytest.mark.parametrize("B,T,soft", [(2048, 50, False), (2048, 50, True), (333, 20, False)])
+def test_din_tensor_core_activation_unit(wechat_vocab_dir, B, T, soft):
+    """The DIN activation-unit MLP on tcgen05 (bf16 operands, fp32 TMEM accumulation)."""
+    rank_b200.set_activation_unit_precision("bf16")
+    try:
+        ours, ref = _pair("DIN", "OracleDIN", wechat_vocab_dir, dropout_rate=0.0, use_softmax=soft)
+        o_outs, o_grads, r_outs, r_grads, _, g64 = _run_both(ours, ref, "DIN", synthetic.din_batch(B, T))
+    finally:
+        rank_b200.set_activation_unit_precision("fp32")
+    compare(o_outs, o_grads, r_outs, r_grads, BF16_TOL, g64)
+    # and it is a different kernel: fp32-exact agreement would mean the switch did nothing
+    assert rel_err(o_outs[1], r_outs[1]) > 1e-7
