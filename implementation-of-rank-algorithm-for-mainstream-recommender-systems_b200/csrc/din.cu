@@ -14,6 +14,7 @@
 // weights w_t; the backward is g_score -> 32 -> 64 -> 4D through the transposed weights.
 #include <string.h>
 #include "common.cuh"
+#include <cuda_bf16.h>
 #include "tile_gemm.cuh"
 
 namespace rk {
@@ -520,7 +521,7 @@ din_bwd_kernel(const __grid_constant__ DinParams p, const float* __restrict__ co
 // ===========================================================================================
 // Tensor-core forward (D = 16): the activation-unit MLP on tcgen05, bf16 operands, fp32
 // accumulators in TMEM.  One thread = one (b,t) row = one TMEM lane; 128 rows per tile.
-//   A1[128x64] = [q,k,q-k,q*k] (bf16, K-major, 128-byte swizzle, built by the row's thread)
+//   A1[128x64] = [q,k,q-k,q*k] (split bf16 hi+lo, K-major, 128-byte swizzle, built by the row's thread)
 //   D1 = A1 . W1^T (4 x tcgen05.mma M128 N64 K16) -> tcgen05.ld -> +b1, ReLU, mask bits, bf16
 //   A2 = relu(D1) rewritten in place over A1;  D2 = A2 . W2^T (M128 N32) -> +b2, ReLU, . w3
 // Gathered K rows stay in fp32 registers for the pooling.  Everything outside the two GEMMs is
@@ -613,20 +614,35 @@ __device__ __forceinline__ void store_chunk(uint8_t* tile, int r, int c, const f
     *reinterpret_cast<uint4*>(tile + r * 128 + ((c ^ (r & 7)) << 4)) = w;
 }
 
+// Split-bf16 operands: x = hi + lo with hi = bf16(x), lo = bf16(x - hi).  A.W is accumulated as
+// A_hi.W_hi + A_lo.W_hi + A_hi.W_lo on the tensor core (fp32 accumulation), which keeps ~16 bits
+// of every operand: the tensor pipe is nearly idle in this kernel, so the two extra MMAs are free.
+__device__ __forceinline__ void store_chunk_split(uint8_t* hi_tile, uint8_t* lo_tile, int r, int c,
+                                                  const float (&v)[8]) {
+    float lo[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) lo[j] = v[j] - __bfloat162float(__float2bfloat16_rn(v[j]));
+    store_chunk(hi_tile, r, c, v);
+    store_chunk(lo_tile, r, c, lo);
+}
+
 constexpr int kTcThreads  = 128;
 constexpr int kTcTmemCols = 128;     // 64 (layer 1) + 32 (layer 2), power of two
 
 struct TcSmem {
-    uint8_t *a, *w1, *w2;              // swizzled bf16 tiles: [128][64], [64][64], [32][64]
+    uint8_t *a, *a_lo, *w1, *w1_lo, *w2, *w2_lo;   // swizzled bf16 tiles: [128][64], [64][64], [32][64], hi + lo
     float *vec, *q, *att, *score, *wt, *pool;
     int *row_s, *row_t, *len, *start;
     uint64_t* bar;
     uint32_t* tmem_slot;
     __device__ explicit TcSmem(uint8_t* base) {
         uint8_t* p = base;
-        a = p;   p += 128 * 128;
-        w1 = p;  p += 64 * 128;
-        w2 = p;  p += 32 * 128;
+        a = p;      p += 128 * 128;
+        a_lo = p;   p += 128 * 128;
+        w1 = p;     p += 64 * 128;
+        w1_lo = p;  p += 64 * 128;
+        w2 = p;     p += 32 * 128;
+        w2_lo = p;  p += 32 * 128;
         vec = (float*)p;    p += sizeof(float) * (kH1 + 2 * kH2 + 4);
         q = (float*)p;      p += sizeof(float) * kSamples * 16;
         att = (float*)p;    p += sizeof(float) * kSamples * 16;
@@ -641,7 +657,7 @@ struct TcSmem {
         tmem_slot = (uint32_t*)p;
     }
     static size_t bytes() {
-        return 1024 /* alignment slack */ + 128 * 128 + 64 * 128 + 32 * 128 +
+        return 1024 /* alignment slack */ + 2 * (128 * 128 + 64 * 128 + 32 * 128) +
                sizeof(float) * (kH1 + 2 * kH2 + 4 + 2 * kSamples * 16 + 2 * kRows + kRows * 17) +
                sizeof(int) * (2 * kRows + 2 * kSamples + 4) + 16;
     }
@@ -669,14 +685,14 @@ din_fwd_tc_kernel(const __grid_constant__ DinParams p, float* __restrict__ conca
         float v[8];
 #pragma unroll
         for (int j = 0; j < 8; ++j) v[j] = __ldg(p.mlp + L.w1 + n * 64 + c * 8 + j);
-        store_chunk(sm.w1, n, c, v);
+        store_chunk_split(sm.w1, sm.w1_lo, n, c, v);
     }
     for (int item = tid; item < 32 * 8; item += kTcThreads) {         // W2[n][k]: 32 rows x 8 chunks
         const int n = item >> 3, c = item & 7;
         float v[8];
 #pragma unroll
         for (int j = 0; j < 8; ++j) v[j] = __ldg(p.mlp + L.w2 + n * 64 + c * 8 + j);
-        store_chunk(sm.w2, n, c, v);
+        store_chunk_split(sm.w2, sm.w2_lo, n, c, v);
     }
     for (int i = tid; i < kH1; i += kTcThreads) sm.vec[i] = __ldg(p.mlp + L.b1 + i);
     for (int i = tid; i < kH2; i += kTcThreads) {
@@ -700,9 +716,9 @@ din_fwd_tc_kernel(const __grid_constant__ DinParams p, float* __restrict__ conca
     const float* w3 = sm.vec + kH1 + kH2;
     const float  b3 = sm.vec[kH1 + 2 * kH2];
     const float  inv_sqrt_d = 0.25f;
-    const uint64_t a_desc  = umma_desc(smem_u32(sm.a));
-    const uint64_t w1_desc = umma_desc(smem_u32(sm.w1));
-    const uint64_t w2_desc = umma_desc(smem_u32(sm.w2));
+    const uint64_t a_desc[2]  = {umma_desc(smem_u32(sm.a)), umma_desc(smem_u32(sm.a_lo))};
+    const uint64_t w1_desc[2] = {umma_desc(smem_u32(sm.w1)), umma_desc(smem_u32(sm.w1_lo))};
+    const uint64_t w2_desc[2] = {umma_desc(smem_u32(sm.w2)), umma_desc(smem_u32(sm.w2_lo))};
     const uint32_t my_tmem = tmem + ((uint32_t)(warp * 32) << 16);
     uint32_t phase = 0;
 
@@ -758,10 +774,10 @@ din_fwd_tc_kernel(const __grid_constant__ DinParams p, float* __restrict__ conca
                     c[j] = a[j] - b[j];
                     d[j] = a[j] * b[j];
                 }
-                store_chunk(sm.a, tid, 0 + half, a);
-                store_chunk(sm.a, tid, 2 + half, b);
-                store_chunk(sm.a, tid, 4 + half, c);
-                store_chunk(sm.a, tid, 6 + half, d);
+                store_chunk_split(sm.a, sm.a_lo, tid, 0 + half, a);
+                store_chunk_split(sm.a, sm.a_lo, tid, 2 + half, b);
+                store_chunk_split(sm.a, sm.a_lo, tid, 4 + half, c);
+                store_chunk_split(sm.a, sm.a_lo, tid, 6 + half, d);
             }
             fence_async_smem();
             fence_before();
@@ -770,8 +786,11 @@ din_fwd_tc_kernel(const __grid_constant__ DinParams p, float* __restrict__ conca
             if (tid == 0) {
                 fence_after();
 #pragma unroll
-                for (int kk = 0; kk < 4; ++kk)      // K = 64 = 4 x 16; +32 B per step inside the swizzle atom
-                    umma_bf16(tmem, a_desc + 2 * kk, w1_desc + 2 * kk, umma_idesc(64), kk > 0);
+                for (int term = 0; term < 3; ++term)   // hi.hi + lo.hi + hi.lo
+#pragma unroll
+                    for (int kk = 0; kk < 4; ++kk)     // K = 64 = 4 x 16; +32 B per step inside the swizzle atom
+                        umma_bf16(tmem, a_desc[term == 1] + 2 * kk, w1_desc[term == 2] + 2 * kk, umma_idesc(64),
+                                  (term | kk) > 0);
                 umma_commit(sm.bar);
             }
             mbar_wait(sm.bar, phase);
@@ -794,7 +813,7 @@ din_fwd_tc_kernel(const __grid_constant__ DinParams p, float* __restrict__ conca
                     float h8[8];
 #pragma unroll
                     for (int j = 0; j < 8; ++j) h8[j] = v[8 * c + j];
-                    store_chunk(sm.a, tid, 4 * half + c, h8);      // A2 = relu(layer 1), in place
+                    store_chunk_split(sm.a, sm.a_lo, tid, 4 * half + c, h8);   // A2 = relu(layer 1), in place
                 }
             }
             fence_async_smem();
@@ -804,8 +823,11 @@ din_fwd_tc_kernel(const __grid_constant__ DinParams p, float* __restrict__ conca
             if (tid == 0) {
                 fence_after();
 #pragma unroll
-                for (int kk = 0; kk < 4; ++kk)
-                    umma_bf16(tmem + 64, a_desc + 2 * kk, w2_desc + 2 * kk, umma_idesc(32), kk > 0);
+                for (int term = 0; term < 3; ++term)
+#pragma unroll
+                    for (int kk = 0; kk < 4; ++kk)
+                        umma_bf16(tmem + 64, a_desc[term == 1] + 2 * kk, w2_desc[term == 2] + 2 * kk, umma_idesc(32),
+                                  (term | kk) > 0);
                 umma_commit(sm.bar);
             }
             mbar_wait(sm.bar, phase);
