@@ -45,6 +45,7 @@ class Workload:
     bytes_per_sample = 0          # fwd + bwd, algorithmic
     flops_per_sample = 0
     bound = "hbm"
+    dtype = "f32"
     hot_calls = ()                # ABI entry points that make up the hot path of a step
 
     def model(self, ns, oracle, vocab_dir):
@@ -118,9 +119,14 @@ class DINWorkload(Workload):
     hot_calls = ("rk_din_fwd", "rk_plan_build", "rk_din_bwd", "rk_embgrad_segment_reduce")
     use_softmax = False
 
+    precision = "fp32"
+
     def model(self, ns, oracle, vocab_dir):
         cls = ns.OracleDIN if oracle else ns.DIN
-        return cls(vocab_dir, dropout_rate=0.0, use_softmax=self.use_softmax, l2_lambda=0.2)
+        m = cls(vocab_dir, dropout_rate=0.0, use_softmax=self.use_softmax, l2_lambda=0.2)
+        if not oracle:
+            m.activation_unit_precision = self.precision
+        return m
 
     def make_batch(self, B, seed):
         from rank_b200 import synthetic
@@ -133,6 +139,15 @@ class DINWorkload(Workload):
 
 class DINSoftmaxWorkload(DINWorkload):
     name, use_softmax = "din_t50_softmax", True
+
+
+class DINTensorCoreWorkload(DINWorkload):
+    # activation-unit MLP on tcgen05 (split-bf16 operands, fp32 TMEM accumulation)
+    name, precision, dtype = "din_t50_raw_tcgen05", "bf16", "bf16x3 tensor-core MLP, f32 elsewhere"
+
+
+class DINSoftmaxTensorCoreWorkload(DINSoftmaxWorkload):
+    name, precision, dtype = "din_t50_softmax_tcgen05", "bf16", "bf16x3 tensor-core MLP, f32 elsewhere"
 
 
 class BSTWorkload(Workload):
@@ -172,7 +187,9 @@ class DeepCrossingWorkload(Workload):
 
 
 WORKLOADS = {"deepfm": DeepFMWorkload, "dcn": DCNWorkload, "afm": AFMWorkload, "din": DINWorkload,
-             "din_softmax": DINSoftmaxWorkload, "bst": BSTWorkload, "deepcrossing": DeepCrossingWorkload}
+             "din_softmax": DINSoftmaxWorkload, "din_tc": DINTensorCoreWorkload,
+             "din_softmax_tc": DINSoftmaxTensorCoreWorkload, "bst": BSTWorkload,
+             "deepcrossing": DeepCrossingWorkload}
 
 
 # ------------------------------------------------------------------------------- helpers
@@ -481,7 +498,7 @@ def run_ours(args, wl):
         line = {
             "metric": METRIC, "value": world * B * args.steps / (total_ms / 1e3), "unit": "samples/s",
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": total_ms / args.steps,
-            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": wl.dtype,
             "data": "synthetic",
             "config": {"workload": wl.name, "batch_per_gpu": B, "global_batch": world * B, "dropout": 0.0,
                        "parallelism": f"dp{world}", "l2": "256 MiB written between steps, outside the timed events",

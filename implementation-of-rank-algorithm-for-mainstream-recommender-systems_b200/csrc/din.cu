@@ -630,8 +630,8 @@ constexpr int kTcThreads  = 128;
 constexpr int kTcTmemCols = 128;     // 64 (layer 1) + 32 (layer 2), power of two
 
 struct TcSmem {
-    uint8_t *a, *a_lo, *w1, *w1_lo, *w2, *w2_lo;   // swizzled bf16 tiles: [128][64], [64][64], [32][64], hi + lo
-    float *vec, *q, *att, *score, *wt, *pool;
+    uint8_t *a, *a_lo, *w1, *w1_lo, *w2, *w2_lo;   // swizzled bf16 tiles: [128][64], [64][64], [<=64][64], hi + lo
+    float *vec, *q, *att, *gq, *dot, *score, *wt, *pool;
     int *row_s, *row_t, *len, *start;
     uint64_t* bar;
     uint32_t* tmem_slot;
@@ -641,11 +641,13 @@ struct TcSmem {
         a_lo = p;   p += 128 * 128;
         w1 = p;     p += 64 * 128;
         w1_lo = p;  p += 64 * 128;
-        w2 = p;     p += 32 * 128;
-        w2_lo = p;  p += 32 * 128;
+        w2 = p;     p += 64 * 128;
+        w2_lo = p;  p += 64 * 128;
         vec = (float*)p;    p += sizeof(float) * (kH1 + 2 * kH2 + 4);
         q = (float*)p;      p += sizeof(float) * kSamples * 16;
         att = (float*)p;    p += sizeof(float) * kSamples * 16;
+        gq = (float*)p;     p += sizeof(float) * kSamples * 16;
+        dot = (float*)p;    p += sizeof(float) * 8;
         score = (float*)p;  p += sizeof(float) * kRows;
         wt = (float*)p;     p += sizeof(float) * kRows;
         pool = (float*)p;   p += sizeof(float) * kRows * 17;
@@ -657,8 +659,8 @@ struct TcSmem {
         tmem_slot = (uint32_t*)p;
     }
     static size_t bytes() {
-        return 1024 /* alignment slack */ + 2 * (128 * 128 + 64 * 128 + 32 * 128) +
-               sizeof(float) * (kH1 + 2 * kH2 + 4 + 2 * kSamples * 16 + 2 * kRows + kRows * 17) +
+        return 1024 /* alignment slack */ + 2 * (128 * 128 + 64 * 128 + 64 * 128) +
+               sizeof(float) * (kH1 + 2 * kH2 + 4 + 3 * kSamples * 16 + 8 + 2 * kRows + kRows * 17) +
                sizeof(int) * (2 * kRows + 2 * kSamples + 4) + 16;
     }
 };
@@ -938,6 +940,237 @@ din_fwd_tc_kernel(const __grid_constant__ DinParams p, float* __restrict__ conca
     if (warp == 0) tmem_dealloc(tmem, kTcTmemCols);
 }
 
+// Tensor-core backward (D = 16): g_score -> (x W2) -> relu' -> (x W1) -> g_cross on tcgen05 with
+// split-bf16 operands; B operands are the transposed weights of the pack (W2^T [64][32] and
+// W1^T [64][64], both K-major for these products).  Same outputs as din_bwd_kernel.
+__global__ void __launch_bounds__(kTcThreads)
+din_bwd_tc_kernel(const __grid_constant__ DinParams p, const float* __restrict__ concat_all,
+                  const float* __restrict__ norm, const float* __restrict__ att_w,
+                  const uint32_t* __restrict__ masks, const float* __restrict__ g_concat,
+                  const float* __restrict__ g_norm, float* __restrict__ g_row,
+                  float* __restrict__ g_hist, int32_t* err_flag) {
+    extern __shared__ uint8_t smem_raw_tc[];
+    uint8_t* base = smem_raw_tc + ((1024u - (smem_u32(smem_raw_tc) & 1023u)) & 1023u);
+    TcSmem sm(base);
+    constexpr int D = 16;
+    const int T = p.T;
+    const MlpLayout L(D);
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int64_t b0 = (int64_t)blockIdx.x * kSamples;
+    const int n_samples = (int)((p.B - b0) < kSamples ? (p.B - b0) : kSamples);
+
+    if (tid == 0) mbar_init(sm.bar, 1);
+    if (warp == 0) tmem_alloc(sm.tmem_slot, kTcTmemCols);
+    for (int item = tid; item < 64 * 4; item += kTcThreads) {          // W2^T[n][k]: 64 rows x 32 k (4 chunks)
+        const int n = item >> 2, c = item & 3;
+        float v[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) v[j] = __ldg(p.mlp + L.w2t + n * 32 + c * 8 + j);
+        store_chunk_split(sm.w2, sm.w2_lo, n, c, v);
+    }
+    for (int item = tid; item < 64 * 8; item += kTcThreads) {          // W1^T[c][n]: 64 rows x 64 k
+        const int n = item >> 3, c = item & 7;
+        float v[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) v[j] = __ldg(p.mlp + L.w1t + n * 64 + c * 8 + j);
+        store_chunk_split(sm.w1, sm.w1_lo, n, c, v);
+    }
+    for (int i = tid; i < kH2; i += kTcThreads) sm.vec[i] = __ldg(p.mlp + L.w3 + i);
+    if (tid < kSamples) sm.len[tid] = tid < n_samples ? clip_len(__ldg(p.his_len + b0 + tid), T) : 0;
+    for (int i = tid; i < n_samples * D; i += kTcThreads) {
+        const int s = i / D, e = i - s * D;
+        const int64_t b = b0 + s;
+        sm.q[i] = concat_all[b * p.width + p.tgt_off + e];
+        float g = g_concat ? g_concat[b * p.width + p.att_off + e] : 0.f;
+        if (g_norm) {
+            const float nv = norm[b];
+            if (nv > 0.f) g = fmaf(g_norm[b] / nv, concat_all[b * p.width + p.att_off + e], g);
+        }
+        sm.att[i] = g;          // g_att: upstream gradient of the attention output
+        sm.gq[i]  = 0.f;
+    }
+    fence_async_smem();
+    fence_before();
+    __syncthreads();
+    fence_after();
+    const uint32_t tmem = *sm.tmem_slot;
+    const float* w3 = sm.vec;
+    const uint64_t a_desc[2]  = {umma_desc(smem_u32(sm.a)), umma_desc(smem_u32(sm.a_lo))};
+    const uint64_t w1_desc[2] = {umma_desc(smem_u32(sm.w1)), umma_desc(smem_u32(sm.w1_lo))};
+    const uint64_t w2_desc[2] = {umma_desc(smem_u32(sm.w2)), umma_desc(smem_u32(sm.w2_lo))};
+    const uint32_t my_tmem = tmem + ((uint32_t)(warp * 32) << 16);
+    uint32_t phase = 0;
+
+    int s_begin = 0;
+    while (s_begin < n_samples) {
+        int s_end, n_rows = 0;
+        {
+            int s = s_begin;
+            while (s < n_samples && n_rows + sm.len[s] <= kRows) { n_rows += sm.len[s]; ++s; }
+            s_end = s;
+        }
+        if (tid < kSamples + 1) {
+            int acc = 0;
+            for (int s = s_begin; s < s_begin + tid && s < s_end; ++s) acc += sm.len[s];
+            sm.start[tid] = acc;
+        }
+        __syncthreads();
+        int my_s = s_begin;
+        while (my_s + 1 < s_end && tid >= sm.start[my_s + 1 - s_begin]) ++my_s;
+        const int  my_t = tid - sm.start[my_s - s_begin];
+        const bool on = tid < n_rows;
+        if (n_rows > 0) {
+            float k[16], gatt[16];
+            float w = 0.f, gw = 0.f;
+            uint32_t m1a = 0, m1b = 0, m2 = 0;
+#pragma unroll
+            for (int e = 0; e < 16; ++e) { k[e] = 0.f; gatt[e] = 0.f; }
+            if (on) {
+                const int64_t row = checked_row(__ldg(p.his_idx + (b0 + my_s) * T + my_t), p.his_rows, err_flag);
+                const float4* src = reinterpret_cast<const float4*>(p.his_w + row * D);
+#pragma unroll
+                for (int c = 0; c < 4; ++c) {
+                    const float4 v = __ldg(src + c);
+                    k[4 * c] = v.x; k[4 * c + 1] = v.y; k[4 * c + 2] = v.z; k[4 * c + 3] = v.w;
+                }
+#pragma unroll
+                for (int e = 0; e < 16; ++e) { gatt[e] = sm.att[my_s * D + e]; gw = fmaf(gatt[e], k[e], gw); }
+                w = att_w[(b0 + my_s) * T + my_t];
+                const uint32_t* mk = masks + ((b0 + my_s) * T + my_t) * 3;
+                m1a = mk[0]; m1b = mk[1]; m2 = mk[2];
+            }
+            if (p.use_softmax) {          // g_s = w (g_w - sum_u w_u g_w_u) / sqrt(D)
+                sm.wt[tid] = w;
+                sm.score[tid] = gw;
+                __syncthreads();
+                for (int s = s_begin + warp; s < s_end; s += kTcThreads / 32) {
+                    const int len = sm.len[s], r0 = sm.start[s - s_begin];
+                    float dsum = 0.f;
+                    for (int t = lane; t < len; t += 32) dsum = fmaf(sm.wt[r0 + t], sm.score[r0 + t], dsum);
+                    dsum = warp_sum(dsum);
+                    if (lane == 0) sm.dot[s] = dsum;
+                }
+                __syncthreads();
+                gw = w * (gw - sm.dot[my_s]) * 0.25f;
+            }
+            if (!on) gw = 0.f;
+            // ---- A = g_z2 [128 x 32]
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+                float v[8];
+#pragma unroll
+                for (int j = 0; j < 8; ++j) v[j] = ((m2 >> (8 * c + j)) & 1u) ? gw * w3[8 * c + j] : 0.f;
+                store_chunk_split(sm.a, sm.a_lo, tid, c, v);
+            }
+            fence_async_smem();
+            fence_before();
+            __syncthreads();
+            if (tid == 0) {
+                fence_after();
+#pragma unroll
+                for (int term = 0; term < 3; ++term)
+#pragma unroll
+                    for (int kk = 0; kk < 2; ++kk)     // K = 32
+                        umma_bf16(tmem, a_desc[term == 1] + 2 * kk, w2_desc[term == 2] + 2 * kk, umma_idesc(64),
+                                  (term | kk) > 0);
+                umma_commit(sm.bar);
+            }
+            mbar_wait(sm.bar, phase);
+            phase ^= 1;
+            fence_after();
+            // ---- g_z1 = (g_z2 x W2) * relu1'  -> A [128 x 64]
+#pragma unroll
+            for (int half = 0; half < 2; ++half) {
+                float v[32];
+                tmem_ld32(my_tmem + 32 * half, v);
+                const uint32_t bits = half == 0 ? m1a : m1b;
+#pragma unroll
+                for (int c = 0; c < 4; ++c) {
+                    float h8[8];
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) h8[j] = ((bits >> (8 * c + j)) & 1u) ? v[8 * c + j] : 0.f;
+                    store_chunk_split(sm.a, sm.a_lo, tid, 4 * half + c, h8);
+                }
+            }
+            fence_async_smem();
+            fence_before();
+            __syncthreads();
+            if (tid == 0) {
+                fence_after();
+#pragma unroll
+                for (int term = 0; term < 3; ++term)
+#pragma unroll
+                    for (int kk = 0; kk < 4; ++kk)     // K = 64
+                        umma_bf16(tmem + 64, a_desc[term == 1] + 2 * kk, w1_desc[term == 2] + 2 * kk, umma_idesc(64),
+                                  (term | kk) > 0);
+                umma_commit(sm.bar);
+            }
+            mbar_wait(sm.bar, phase);
+            phase ^= 1;
+            fence_after();
+            // ---- g_cross = [gc_q | gc_k | gc_d | gc_p] -> g_k row, and this row's share of g_q
+            float gk[16], gqr[16];
+            {
+                float v[32];
+                tmem_ld32(my_tmem + 64, v);
+#pragma unroll
+                for (int e = 0; e < 16; ++e) { gqr[e] = v[e]; gk[e] = fmaf(w, gatt[e], v[16 + e]); }
+                tmem_ld32(my_tmem + 96, v);
+#pragma unroll
+                for (int e = 0; e < 16; ++e) {
+                    const float qe = sm.q[my_s * D + e];
+                    gqr[e] += v[e] + v[16 + e] * k[e];
+                    gk[e]  += v[16 + e] * qe - v[e];
+                }
+            }
+            if (on) {
+                float4* dst = reinterpret_cast<float4*>(g_hist + ((b0 + my_s) * T + my_t) * D);
+#pragma unroll
+                for (int c = 0; c < 4; ++c) dst[c] = make_float4(gk[4 * c], gk[4 * c + 1], gk[4 * c + 2], gk[4 * c + 3]);
+            }
+#pragma unroll
+            for (int e = 0; e < 16; ++e) sm.pool[tid * 17 + e] = on ? gqr[e] : 0.f;
+            fence_before();
+            __syncthreads();
+            for (int item = tid; item < (s_end - s_begin) * 16; item += kTcThreads) {
+                const int s = s_begin + (item >> 4), e = item & 15;
+                const int len = sm.len[s], r0 = sm.start[s - s_begin];
+                float a = 0.f;
+                for (int t = 0; t < len; ++t) a += sm.pool[(r0 + t) * 17 + e];
+                sm.gq[s * 16 + e] = a;
+            }
+        }
+        if (p.use_softmax) {      // no history: uniform weights, gradient g_att / T on every position
+            for (int s = s_begin; s < s_end; ++s) {
+                if (sm.len[s] != 0) continue;
+                const float u = 1.0f / (float)T;
+                for (int i = tid; i < T * D; i += kTcThreads)
+                    g_hist[(b0 + s) * T * D + i] = u * sm.att[s * D + (i % D)];
+            }
+        }
+        __syncthreads();
+        s_begin = s_end;
+    }
+
+    for (int s = warp; s < n_samples; s += kTcThreads / 32) {
+        const int64_t b = b0 + s;
+        float scale = 0.f;
+        if (g_norm) {
+            const float nv = norm[b];
+            scale = nv > 0.f ? g_norm[b] / nv : 0.f;
+        }
+        for (int c = lane; c < p.width; c += 32) {
+            float g = g_concat ? g_concat[b * p.width + c] : 0.f;
+            if (c >= p.l2_from) g = fmaf(scale, concat_all[b * p.width + c], g);
+            if (c >= p.tgt_off && c < p.tgt_off + D) g += sm.gq[s * D + c - p.tgt_off];
+            g_row[b * p.width + c] = g;
+        }
+    }
+    fence_before();
+    __syncthreads();
+    if (warp == 0) tmem_dealloc(tmem, kTcTmemCols);
+}
+
 }  // namespace tc
 
 }  // namespace rk
@@ -1021,9 +1254,19 @@ int rk_din_bwd(const rk_din_args_t* args, const float* concat_all, const float* 
     RK_CHECK_ARG(concat_all && att_w && relu_masks && g_row && g_hist, "din_bwd: NULL pointer");
     RK_CHECK_ARG(!g_norm || norm, "din_bwd: g_norm without the saved norms");
     if (p.B == 0) return 0;
+    const int grid = (int)ceil_div(p.B, kSamples);
+    if (args->precision == RK_DIN_BF16_TENSOR) {
+        RK_CHECK_ARG(p.D == 16, "din_bwd: the tensor-core activation unit is built for D = 16 (got %d)", p.D);
+        const size_t smem_tc = tc::TcSmem::bytes();
+        RK_CUDA(cudaFuncSetAttribute(tc::din_bwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     (int)smem_tc));
+        tc::din_bwd_tc_kernel<<<grid, tc::kTcThreads, smem_tc, (cudaStream_t)stream_>>>(
+            p, concat_all, norm, att_w, relu_masks, g_concat, g_norm, g_row, g_hist, err_flag);
+        RK_LAUNCH_CHECK();
+        return 0;
+    }
     size_t smem;
     if (int rc = din_smem(p.D, &smem, (const void*)din_bwd_kernel)) return rc;
-    const int grid = (int)ceil_div(p.B, kSamples);
     din_bwd_kernel<<<grid, kDinThreads, smem, (cudaStream_t)stream_>>>(
         p, concat_all, norm, att_w, relu_masks, g_concat, g_norm, g_row, g_hist, err_flag);
     RK_LAUNCH_CHECK();
