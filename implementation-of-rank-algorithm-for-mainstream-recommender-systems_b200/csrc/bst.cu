@@ -96,7 +96,7 @@ struct BstSmem {
     float *wt, *w, *vec, *pos;            // [6][256] k-major, [6][256] registered, [10][16], [T][16]
     float *ks, *vs, *qs, *dc, *gs, *as, *xs, *qks, *cs;   // [rows][20] each
     float *mrow, *lrow, *delta;           // [rows][H]
-    double* vsum;                         // [8][threads] column-sum accumulators (bias / LayerNorm gradients)
+    double* vsum;                         // [8][32] column-sum accumulators (bias / LayerNorm gradients)
     __device__ BstSmem(float* base, int T, int H, bool bwd) {
         float* p = base;
         wt = p;  p += 6 * 256;
@@ -116,12 +116,12 @@ struct BstSmem {
             mrow = p;  p += kBstRows * H;
             lrow = p;  p += kBstRows * H;
             delta = p; p += kBstRows * H;
-            vsum = reinterpret_cast<double*>(p); p += 2 * 8 * kBstThreads;
+            vsum = reinterpret_cast<double*>(p); p += 2 * 8 * 32;
         }
     }
     static size_t bytes(int T, int H, bool bwd) {
         size_t n = 6 * 256 + (bwd ? 6 * 256 : 0) + 160 + (size_t)T * 16 + (size_t)(bwd ? 9 : 3) * kBstRows * kBstLd +
-                   (bwd ? (size_t)3 * kBstRows * H + 2 * 8 * kBstThreads : 0);
+                   (bwd ? (size_t)3 * kBstRows * H + 2 * 8 * 32 : 0);
         return n * sizeof(float);
     }
 };
@@ -302,8 +302,10 @@ bst_bwd_kernel(const __grid_constant__ BstParams p, const float* __restrict__ g_
     float macc[6][2];
 #pragma unroll
     for (int m = 0; m < 6; ++m) { macc[m][0] = 0.f; macc[m][1] = 0.f; }
+    if (r < 32) {
 #pragma unroll
-    for (int i = 0; i < 8; ++i) sm.vsum[i * kBstThreads + r] = 0.0;
+        for (int i = 0; i < 8; ++i) sm.vsum[i * 32 + r] = 0.0;
+    }
     float pacc[16];
 #pragma unroll
     for (int i = 0; i < 16; ++i) pacc[i] = 0.f;
@@ -392,7 +394,7 @@ bst_bwd_kernel(const __grid_constant__ BstParams p, const float* __restrict__ g_
             store_row(sm.as + r * kBstLd, dy);
         }
         __syncthreads();
-        bst_colsum(sm.gs, sm.as, rows, sm.vsum[0 * kBstThreads + r]);                 // d ln2_g | d ln2_b
+        bst_colsum(sm.gs, sm.as, rows, sm.vsum[0 * 32 + (r & 31)]);                 // d ln2_g | d ln2_b
         __syncthreads();
         if (on) layer_norm16_bwd(dy, sm.vec + VG2 * 16, zh2, rstd2, dz);
         else {
@@ -404,7 +406,7 @@ bst_bwd_kernel(const __grid_constant__ BstParams p, const float* __restrict__ g_
         store_row(sm.as + r * kBstLd, act);
         __syncthreads();
         bst_outer(sm.gs, sm.as, rows, macc[M2]);
-        bst_colsum(sm.gs, nullptr, rows, sm.vsum[1 * kBstThreads + r]);               // d b2
+        bst_colsum(sm.gs, nullptr, rows, sm.vsum[1 * 32 + (r & 31)]);               // d b2
         __syncthreads();
         float dh[16], o1[16], do1[16];
 #pragma unroll
@@ -421,7 +423,7 @@ bst_bwd_kernel(const __grid_constant__ BstParams p, const float* __restrict__ g_
         store_row(sm.as + r * kBstLd, o1);
         __syncthreads();
         bst_outer(sm.gs, sm.as, rows, macc[M1]);
-        bst_colsum(sm.gs, nullptr, rows, sm.vsum[2 * kBstThreads + r]);               // d b1
+        bst_colsum(sm.gs, nullptr, rows, sm.vsum[2 * 32 + (r & 31)]);               // d b1
         __syncthreads();
 #pragma unroll
         for (int i = 0; i < 16; ++i) do1[i] = dz[i];
@@ -435,7 +437,7 @@ bst_bwd_kernel(const __grid_constant__ BstParams p, const float* __restrict__ g_
             store_row(sm.as + r * kBstLd, do1);
         }
         __syncthreads();
-        bst_colsum(sm.gs, sm.as, rows, sm.vsum[3 * kBstThreads + r]);                 // d ln1_g | d ln1_b
+        bst_colsum(sm.gs, sm.as, rows, sm.vsum[3 * 32 + (r & 31)]);                 // d ln1_g | d ln1_b
         __syncthreads();
         float dz1[16], dctx[16];
 #pragma unroll
@@ -444,7 +446,7 @@ bst_bwd_kernel(const __grid_constant__ BstParams p, const float* __restrict__ g_
         store_row(sm.gs + r * kBstLd, dz1);
         __syncthreads();
         bst_outer(sm.gs, sm.cs, rows, macc[MO]);                 // d w_o = dz1 (x) ctx
-        bst_colsum(sm.gs, nullptr, rows, sm.vsum[4 * kBstThreads + r]);               // d b_o
+        bst_colsum(sm.gs, nullptr, rows, sm.vsum[4 * 32 + (r & 31)]);               // d b_o
         if (on) {
             matvec16(sm.w + MO * 256, dz1, dctx);                    // W_o^T dz1
             float ctx[16];
@@ -512,17 +514,17 @@ bst_bwd_kernel(const __grid_constant__ BstParams p, const float* __restrict__ g_
         store_row(sm.gs + r * kBstLd, dq);
         __syncthreads();
         bst_outer(sm.gs, sm.qks, rows, macc[MQ]);
-        bst_colsum(sm.gs, nullptr, rows, sm.vsum[5 * kBstThreads + r]);               // d b_q
+        bst_colsum(sm.gs, nullptr, rows, sm.vsum[5 * 32 + (r & 31)]);               // d b_q
         __syncthreads();
         store_row(sm.gs + r * kBstLd, dk);
         __syncthreads();
         bst_outer(sm.gs, sm.qks, rows, macc[MK]);
-        bst_colsum(sm.gs, nullptr, rows, sm.vsum[6 * kBstThreads + r]);               // d b_k
+        bst_colsum(sm.gs, nullptr, rows, sm.vsum[6 * 32 + (r & 31)]);               // d b_k
         __syncthreads();
         store_row(sm.gs + r * kBstLd, dv);
         __syncthreads();
         bst_outer(sm.gs, sm.xs, rows, macc[MV]);
-        bst_colsum(sm.gs, nullptr, rows, sm.vsum[7 * kBstThreads + r]);               // d b_v
+        bst_colsum(sm.gs, nullptr, rows, sm.vsum[7 * 32 + (r & 31)]);               // d b_v
         __syncthreads();
         float dqk[16];
 #pragma unroll
@@ -569,17 +571,17 @@ bst_bwd_kernel(const __grid_constant__ BstParams p, const float* __restrict__ g_
     o[mat_off[M1] + e2] = macc[M1][0]; o[mat_off[M1] + e2 + 1] = macc[M1][1];
     o[mat_off[M2] + e2] = macc[M2][0]; o[mat_off[M2] + e2 + 1] = macc[M2][1];
     if (r < 16) {
-        o[256 + r]  = (float)sm.vsum[5 * kBstThreads + r];    // bq
-        o[528 + r]  = (float)sm.vsum[6 * kBstThreads + r];    // bk
-        o[800 + r]  = (float)sm.vsum[7 * kBstThreads + r];    // bv
-        o[1072 + r] = (float)sm.vsum[4 * kBstThreads + r];    // bo
-        o[1088 + r] = (float)sm.vsum[3 * kBstThreads + r];    // ln1_g
-        o[1376 + r] = (float)sm.vsum[2 * kBstThreads + r];    // b1
-        o[1648 + r] = (float)sm.vsum[1 * kBstThreads + r];    // b2
-        o[1664 + r] = (float)sm.vsum[0 * kBstThreads + r];    // ln2_g
+        o[256 + r]  = (float)sm.vsum[5 * 32 + r];    // bq
+        o[528 + r]  = (float)sm.vsum[6 * 32 + r];    // bk
+        o[800 + r]  = (float)sm.vsum[7 * 32 + r];    // bv
+        o[1072 + r] = (float)sm.vsum[4 * 32 + r];    // bo
+        o[1088 + r] = (float)sm.vsum[3 * 32 + r];    // ln1_g
+        o[1376 + r] = (float)sm.vsum[2 * 32 + r];    // b1
+        o[1648 + r] = (float)sm.vsum[1 * 32 + r];    // b2
+        o[1664 + r] = (float)sm.vsum[0 * 32 + r];    // ln2_g
     } else if (r < 32) {
-        o[1104 + r - 16] = (float)sm.vsum[3 * kBstThreads + r];   // ln1_b
-        o[1680 + r - 16] = (float)sm.vsum[0 * kBstThreads + r];   // ln2_b
+        o[1104 + r - 16] = (float)sm.vsum[3 * 32 + r];   // ln1_b
+        o[1680 + r - 16] = (float)sm.vsum[0 * 32 + r];   // ln2_b
     }
 }
 
