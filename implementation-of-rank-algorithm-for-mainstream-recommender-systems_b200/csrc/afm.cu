@@ -16,8 +16,10 @@ namespace rk {
 
 constexpr int kAfmThreads = 256;
 constexpr int kAfmRows    = 128;
-constexpr int kAfmLd      = 132;   // row stride of feature-major tiles: multiple of 4, = 4 mod 32
 constexpr int kAfmMaxS    = 16;
+// Row stride of the feature-major tiles (AfmParams::ld): the smallest value >= the tile's rows
+// that is a multiple of 4 and = 4 mod 32, so that both the m-contiguous float4 loads and the
+// loads of consecutive features at a fixed m are conflict free.
 
 struct AfmParams {
     FieldSet     fs;
@@ -25,7 +27,7 @@ struct AfmParams {
     const float* b1;   // [A]     attention.0.bias
     const float* w2;   // [A]     attention.2.weight ([1][A])
     const float* b2;   // [1]     attention.2.bias
-    int32_t      D, A, Ap, P, S;
+    int32_t      D, A, Ap, P, S, ld;
     int64_t      B, n_tiles;
 };
 
@@ -41,12 +43,12 @@ struct AfmSmem {
         b1 = q;    q += p.Ap;
         w2 = q;    q += p.Ap;
         e = q;     q += p.S * p.fs.F * p.D;
-        x = q;     q += p.D * kAfmLd;
-        h = q;     q += bwd ? p.Ap * kAfmLd : 0;
-        part = q;  q += (p.Ap / 8) * kAfmLd;
-        score = q; q += kAfmLd;
-        attn = q;  q += kAfmLd;
-        ds = q;    q += kAfmLd;
+        x = q;     q += p.D * p.ld;
+        h = q;     q += bwd ? p.Ap * p.ld : 0;
+        part = q;  q += (p.Ap / 8) * p.ld;
+        score = q; q += p.ld;
+        attn = q;  q += p.ld;
+        ds = q;    q += p.ld;
         gout = q;  q += p.S * p.D;
         pi = (int*)q;   q += p.P;
         pj = (int*)q;   q += p.P;
@@ -54,8 +56,8 @@ struct AfmSmem {
     }
     static size_t bytes(const AfmParams& p, bool bwd) {
         size_t n = (size_t)p.D * p.Ap + (bwd ? (size_t)p.Ap * p.D : 0) + 2 * p.Ap + (size_t)p.S * p.fs.F * p.D +
-                   (size_t)p.D * kAfmLd + (bwd ? (size_t)p.Ap * kAfmLd : 0) + (size_t)(p.Ap / 8) * kAfmLd +
-                   3 * kAfmLd + (size_t)p.S * p.D + 2 * p.P + (size_t)p.fs.F * p.fs.F;
+                   (size_t)p.D * p.ld + (bwd ? (size_t)p.Ap * p.ld : 0) + (size_t)(p.Ap / 8) * p.ld +
+                   3 * p.ld + (size_t)p.S * p.D + 2 * p.P + (size_t)p.fs.F * p.fs.F;
         return n * sizeof(float);
     }
 };
@@ -103,7 +105,7 @@ __device__ __forceinline__ void afm_build_tile(const AfmParams& p, const AfmSmem
             const int s = m / p.P, q = m - s * p.P;
             v = sm.e[(s * F + sm.pi[q]) * D + d] * sm.e[(s * F + sm.pj[q]) * D + d];
         }
-        sm.x[d * kAfmLd + m] = v;
+        sm.x[d * p.ld + m] = v;
     }
     __syncthreads();
 }
@@ -111,7 +113,7 @@ __device__ __forceinline__ void afm_build_tile(const AfmParams& p, const AfmSmem
 // Hidden layer + scores.  KEEP_H also leaves relu(W1 v + b1) in sm.h (feature-major).
 template <bool KEEP_H>
 __device__ __forceinline__ void afm_scores(const AfmParams& p, const AfmSmem& sm, int m_used, int rows) {
-    tile_gemm<8, kAfmThreads>(sm.x, kAfmLd, sm.w1t, p.Ap, p.D, p.Ap, m_used,
+    tile_gemm<8, kAfmThreads>(sm.x, p.ld, sm.w1t, p.Ap, p.D, p.Ap, m_used,
                               [&](int m0, int n0, float (&acc)[4][8]) {
         float part[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
@@ -123,14 +125,14 @@ __device__ __forceinline__ void afm_scores(const AfmParams& p, const AfmSmem& sm
                 part[i] = fmaf(acc[i][j], ww, part[i]);
             }
         }
-        if (KEEP_H) store_tile_kmajor<8>(sm.h, kAfmLd, m0, n0, acc);
-        *reinterpret_cast<float4*>(sm.part + (n0 >> 3) * kAfmLd + m0) = make_float4(part[0], part[1], part[2], part[3]);
+        if (KEEP_H) store_tile_kmajor<8>(sm.h, p.ld, m0, n0, acc);
+        *reinterpret_cast<float4*>(sm.part + (n0 >> 3) * p.ld + m0) = make_float4(part[0], part[1], part[2], part[3]);
     });
     __syncthreads();
     const float b2 = __ldg(p.b2);
     for (int m = threadIdx.x; m < m_used; m += kAfmThreads) {
         float s = b2;
-        for (int t = 0; t < p.Ap / 8; ++t) s += sm.part[t * kAfmLd + m];
+        for (int t = 0; t < p.Ap / 8; ++t) s += sm.part[t * p.ld + m];
         sm.score[m] = s;
         if (m >= rows) sm.attn[m] = 0.f;
     }
@@ -150,7 +152,7 @@ __device__ __forceinline__ void afm_scores(const AfmParams& p, const AfmSmem& sm
     __syncthreads();
 }
 
-__global__ void __launch_bounds__(kAfmThreads)
+__global__ void __launch_bounds__(kAfmThreads, 4)
 afm_fwd_kernel(const __grid_constant__ AfmParams p, float* __restrict__ out, int32_t* err_flag) {
     extern __shared__ __align__(16) float smem_raw[];
     AfmSmem sm(smem_raw, p, false);
@@ -163,21 +165,27 @@ afm_fwd_kernel(const __grid_constant__ AfmParams p, float* __restrict__ out, int
         const int rows = ns * p.P, m_used = (rows + 3) / 4 * 4;
         afm_build_tile(p, sm, b0, ns, m_used, err_flag);
         afm_scores<false>(p, sm, m_used, rows);
-        for (int s = warp; s < ns; s += kAfmThreads / 32) {
+        // weighted sum over the pairs: every warp takes (sample, 4 columns), lanes over the pairs
+        for (int item = warp; item < ns * (D / 4); item += kAfmThreads / 32) {
+            const int s = item / (D / 4), d0 = (item - s * (D / 4)) * 4;
             const int r0 = s * p.P;
-            for (int d = 0; d < D; ++d) {
-                float a = 0.f;
-                for (int q = lane; q < p.P; q += 32) a = fmaf(sm.attn[r0 + q], sm.x[d * kAfmLd + r0 + q], a);
-                a = warp_sum(a);
-                if (lane == 0) out[(b0 + s) * D + d] = a;
+            float a[4] = {0.f, 0.f, 0.f, 0.f};
+            for (int q = lane; q < p.P; q += 32) {
+                const float w = sm.attn[r0 + q];
+#pragma unroll
+                for (int j = 0; j < 4; ++j) a[j] = fmaf(w, sm.x[(d0 + j) * p.ld + r0 + q], a[j]);
             }
+#pragma unroll
+            for (int j = 0; j < 4; ++j) a[j] = warp_sum(a[j]);
+            if (lane == 0)
+                *reinterpret_cast<float4*>(out + (b0 + s) * D + d0) = make_float4(a[0], a[1], a[2], a[3]);
         }
         __syncthreads();
     }
 }
 
 // partial layout per CTA: [dW1 A*D][db1 A][dw2 A][db2 1]
-__global__ void __launch_bounds__(kAfmThreads)
+__global__ void __launch_bounds__(kAfmThreads, 2)
 afm_bwd_kernel(const __grid_constant__ AfmParams p, const float* __restrict__ g_out,
                float* __restrict__ g_rows, float* __restrict__ partials, int32_t* err_flag) {
     extern __shared__ __align__(16) float smem_raw[];
@@ -207,7 +215,7 @@ afm_bwd_kernel(const __grid_constant__ AfmParams p, const float* __restrict__ g_
             float a = 0.f;
             if (m < rows) {
                 const int s = m / p.P;
-                for (int d = 0; d < D; ++d) a = fmaf(sm.gout[s * D + d], sm.x[d * kAfmLd + m], a);
+                for (int d = 0; d < D; ++d) a = fmaf(sm.gout[s * D + d], sm.x[d * p.ld + m], a);
             }
             sm.ds[m] = a;
         }
@@ -222,7 +230,7 @@ afm_bwd_kernel(const __grid_constant__ AfmParams p, const float* __restrict__ g_
         __syncthreads();
         // dw2[n] += sum_m ds[m] h[n][m];  db2 += sum_m ds[m];  then h <- dz = ds * w2[n] * (h > 0)
         if (tid < Ap) {
-            const float* hrow = sm.h + tid * kAfmLd;
+            const float* hrow = sm.h + tid * p.ld;
             float a = 0.f;
             for (int m = 0; m < m_used; m += 4) {
                 const float4 hv = *reinterpret_cast<const float4*>(hrow + m);
@@ -239,19 +247,19 @@ afm_bwd_kernel(const __grid_constant__ AfmParams p, const float* __restrict__ g_
         __syncthreads();
         for (int item = tid; item < Ap * (m_used / 4); item += kAfmThreads) {
             const int n = item / (m_used / 4), m = (item - n * (m_used / 4)) * 4;
-            float4 hv = *reinterpret_cast<float4*>(sm.h + n * kAfmLd + m);
+            float4 hv = *reinterpret_cast<float4*>(sm.h + n * p.ld + m);
             const float4 dv = *reinterpret_cast<const float4*>(sm.ds + m);
             const float ww = sm.w2[n];
             hv.x = hv.x > 0.f ? dv.x * ww : 0.f;
             hv.y = hv.y > 0.f ? dv.y * ww : 0.f;
             hv.z = hv.z > 0.f ? dv.z * ww : 0.f;
             hv.w = hv.w > 0.f ? dv.w * ww : 0.f;
-            *reinterpret_cast<float4*>(sm.h + n * kAfmLd + m) = hv;
+            *reinterpret_cast<float4*>(sm.h + n * p.ld + m) = hv;
         }
         __syncthreads();
         // db1[n] += sum_m dz[n][m]
         if (tid < Ap) {
-            const float* zrow = sm.h + tid * kAfmLd;
+            const float* zrow = sm.h + tid * p.ld;
             float a = 0.f;
             for (int m = 0; m < m_used; m += 4) {
                 const float4 z = *reinterpret_cast<const float4*>(zrow + m);
@@ -259,18 +267,18 @@ afm_bwd_kernel(const __grid_constant__ AfmParams p, const float* __restrict__ g_
             }
             acc_b1 += a;
         }
-        // dW1[n][d] += sum_m dz[n][m] v[d][m]: lanes own consecutive n (stride kAfmLd = 4 mod 32 ->
+        // dW1[n][d] += sum_m dz[n][m] v[d][m]: lanes own consecutive n (stride p.ld = 4 mod 32 ->
         // conflict-free float4 loads along m), the warp's four v rows are broadcast
         if (w_on) {
-            const float* xr = sm.x + (4 * warp) * kAfmLd;
+            const float* xr = sm.x + (4 * warp) * p.ld;
             for (int m = 0; m < m_used; m += 4) {
                 float4 xv[4];
 #pragma unroll
-                for (int j = 0; j < 4; ++j) xv[j] = *reinterpret_cast<const float4*>(xr + j * kAfmLd + m);
+                for (int j = 0; j < 4; ++j) xv[j] = *reinterpret_cast<const float4*>(xr + j * p.ld + m);
 #pragma unroll
                 for (int i = 0; i < 4; ++i) {
                     if (i < NI) {
-                        const float4 z = *reinterpret_cast<const float4*>(sm.h + (lane + 32 * i) * kAfmLd + m);
+                        const float4 z = *reinterpret_cast<const float4*>(sm.h + (lane + 32 * i) * p.ld + m);
 #pragma unroll
                         for (int j = 0; j < 4; ++j) {
                             accW[i][j] = fmaf(z.x, xv[j].x, accW[i][j]);
@@ -284,7 +292,7 @@ afm_bwd_kernel(const __grid_constant__ AfmParams p, const float* __restrict__ g_
         }
         __syncthreads();
         // dv[m][d] = a_m g_out[s][d] + sum_n dz[n][m] W1[n][d]  -> overwrite x (feature-major)
-        tile_gemm<4, kAfmThreads>(sm.h, kAfmLd, sm.w1, D, Ap, D, m_used, [&](int m0, int n0, float (&acc)[4][4]) {
+        tile_gemm<4, kAfmThreads>(sm.h, p.ld, sm.w1, D, Ap, D, m_used, [&](int m0, int n0, float (&acc)[4][4]) {
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
                 const int m = m0 + i;
@@ -293,7 +301,7 @@ afm_bwd_kernel(const __grid_constant__ AfmParams p, const float* __restrict__ g_
 #pragma unroll
                 for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(a, sm.gout[s * D + n0 + j], acc[i][j]);
             }
-            store_tile_kmajor<4>(sm.x, kAfmLd, m0, n0, acc);
+            store_tile_kmajor<4>(sm.x, p.ld, m0, n0, acc);
         });
         __syncthreads();
         // d e_f = sum_{g != f} dv_{pair(f,g)} * e_g
@@ -302,7 +310,7 @@ afm_bwd_kernel(const __grid_constant__ AfmParams p, const float* __restrict__ g_
             float a = 0.f;
             for (int g = 0; g < F; ++g) {
                 if (g == f) continue;
-                a = fmaf(sm.x[d * kAfmLd + s * p.P + sm.pidx[f * F + g]], sm.e[(s * F + g) * D + d], a);
+                a = fmaf(sm.x[d * p.ld + s * p.P + sm.pidx[f * F + g]], sm.e[(s * F + g) * D + d], a);
             }
             g_rows[(b0 + s) * F * D + f * D + d] = a;
         }
@@ -354,6 +362,12 @@ static int afm_fill(const rk_field_t* fields, int F, const float* w1, const floa
     p->P = F * (F - 1) / 2;
     int S = kAfmRows / p->P;
     p->S = S > kAfmMaxS ? kAfmMaxS : S;
+    {
+        const int rows = (p->S * p->P + 3) / 4 * 4;
+        int ld = 4;
+        while (ld < rows) ld += 32;      // 4, 36, 68, 100, 132: multiple of 4 and = 4 mod 32
+        p->ld = ld;
+    }
     p->B = B;
     p->n_tiles = ceil_div(B, p->S);
     return 0;
@@ -368,7 +382,7 @@ int rk_afm_bwd_ctas(int64_t B, int F) {
     int S = rk::kAfmRows / (F * (F - 1) / 2);
     if (S > rk::kAfmMaxS) S = rk::kAfmMaxS;
     int64_t tiles = rk::ceil_div(B, S);
-    int64_t cap = rk::sm_count();
+    int64_t cap = 2 * (int64_t)rk::sm_count();   // two CTAs fit per SM (shared memory and registers)
     return (int)(tiles < cap ? tiles : cap);
 }
 
@@ -383,7 +397,7 @@ int rk_afm_fwd(const rk_field_t* fields, int F, const float* w1, const float* b1
     RK_CHECK_ARG(smem <= 227 * 1024, "afm_fwd: %zu bytes of shared memory", smem);
     RK_CUDA(cudaFuncSetAttribute(afm_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int64_t grid = p.n_tiles;
-    const int64_t cap = (int64_t)sm_count() * 3;
+    const int64_t cap = (int64_t)sm_count() * 4;
     if (grid > cap) grid = cap;
     afm_fwd_kernel<<<(int)grid, kAfmThreads, smem, (cudaStream_t)stream_>>>(p, out, err_flag);
     RK_LAUNCH_CHECK();
