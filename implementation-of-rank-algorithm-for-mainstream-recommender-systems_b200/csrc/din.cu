@@ -635,14 +635,15 @@ struct TcSmem {
     int *row_s, *row_t, *len, *start;
     uint64_t* bar;
     uint32_t* tmem_slot;
-    __device__ explicit TcSmem(uint8_t* base) {
+    // w2_rows: rows of the second weight tile (32 for W2 in forward, 64 for W2^T in backward)
+    __device__ TcSmem(uint8_t* base, int w2_rows) {
         uint8_t* p = base;
         a = p;      p += 128 * 128;
         a_lo = p;   p += 128 * 128;
         w1 = p;     p += 64 * 128;
         w1_lo = p;  p += 64 * 128;
-        w2 = p;     p += 64 * 128;
-        w2_lo = p;  p += 64 * 128;
+        w2 = p;     p += w2_rows * 128;
+        w2_lo = p;  p += w2_rows * 128;
         vec = (float*)p;    p += sizeof(float) * (kH1 + 2 * kH2 + 4);
         q = (float*)p;      p += sizeof(float) * kSamples * 16;
         att = (float*)p;    p += sizeof(float) * kSamples * 16;
@@ -658,8 +659,8 @@ struct TcSmem {
         bar = (uint64_t*)p; p += 8;
         tmem_slot = (uint32_t*)p;
     }
-    static size_t bytes() {
-        return 1024 /* alignment slack */ + 2 * (128 * 128 + 64 * 128 + 64 * 128) +
+    static size_t bytes(int w2_rows) {
+        return 1024 /* alignment slack */ + 2 * (128 * 128 + 64 * 128 + (size_t)w2_rows * 128) +
                sizeof(float) * (kH1 + 2 * kH2 + 4 + 3 * kSamples * 16 + 8 + 2 * kRows + kRows * 17) +
                sizeof(int) * (2 * kRows + 2 * kSamples + 4) + 16;
     }
@@ -671,13 +672,12 @@ din_fwd_tc_kernel(const __grid_constant__ DinParams p, float* __restrict__ conca
                   int32_t* err_flag) {
     extern __shared__ uint8_t smem_raw_tc[];
     uint8_t* base = smem_raw_tc + ((1024u - (smem_u32(smem_raw_tc) & 1023u)) & 1023u);   // swizzle atoms need 1024 B
-    TcSmem sm(base);
+    TcSmem sm(base, 32);
     constexpr int D = 16;
     const int T = p.T;
     const MlpLayout L(D);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int64_t b0 = (int64_t)blockIdx.x * kSamples;
-    const int n_samples = (int)((p.B - b0) < kSamples ? (p.B - b0) : kSamples);
+    const int64_t n_groups = (p.B + kSamples - 1) / kSamples;
 
     // ---- one-time setup: barrier, TMEM, weights (fp32 -> bf16, swizzled, K-major = as registered)
     if (tid == 0) mbar_init(sm.bar, 1);
@@ -702,12 +702,6 @@ din_fwd_tc_kernel(const __grid_constant__ DinParams p, float* __restrict__ conca
         sm.vec[kH1 + kH2 + i] = __ldg(p.mlp + L.w3 + i);
     }
     if (tid == 0) sm.vec[kH1 + 2 * kH2] = __ldg(p.mlp + L.b3);
-    for (int i = tid; i < n_samples * D; i += kTcThreads) {
-        const int s = i / D, e = i - s * D;
-        const int64_t row = checked_row(__ldg(p.tgt_idx + b0 + s), p.tgt_rows, err_flag);
-        sm.q[i] = __ldg(p.tgt_w + row * D + e);
-    }
-    if (tid < kSamples) sm.len[tid] = tid < n_samples ? clip_len(__ldg(p.his_len + b0 + tid), T) : 0;
     fence_async_smem();
     fence_before();
     __syncthreads();
@@ -723,6 +717,18 @@ din_fwd_tc_kernel(const __grid_constant__ DinParams p, float* __restrict__ conca
     const uint64_t w2_desc[2] = {umma_desc(smem_u32(sm.w2)), umma_desc(smem_u32(sm.w2_lo))};
     const uint32_t my_tmem = tmem + ((uint32_t)(warp * 32) << 16);
     uint32_t phase = 0;
+
+  // persistent: the weights, the barrier and the TMEM columns are set up once per CTA
+  for (int64_t group = blockIdx.x; group < n_groups; group += gridDim.x) {
+    const int64_t b0 = group * kSamples;
+    const int n_samples = (int)((p.B - b0) < kSamples ? (p.B - b0) : kSamples);
+    for (int i = tid; i < n_samples * D; i += kTcThreads) {
+        const int s = i / D, e = i - s * D;
+        const int64_t row = checked_row(__ldg(p.tgt_idx + b0 + s), p.tgt_rows, err_flag);
+        sm.q[i] = __ldg(p.tgt_w + row * D + e);
+    }
+    if (tid < kSamples) sm.len[tid] = tid < n_samples ? clip_len(__ldg(p.his_len + b0 + tid), T) : 0;
+    __syncthreads();
 
     int s_begin = 0;
     while (s_begin < n_samples) {
@@ -935,6 +941,8 @@ din_fwd_tc_kernel(const __grid_constant__ DinParams p, float* __restrict__ conca
         ss = warp_sum(ss);
         if (lane == 0 && norm_out) norm_out[b] = sqrtf(ss);
     }
+    __syncthreads();      // q / len / att are rewritten by the next group
+  }
     fence_before();
     __syncthreads();
     if (warp == 0) tmem_dealloc(tmem, kTcTmemCols);
@@ -951,13 +959,12 @@ din_bwd_tc_kernel(const __grid_constant__ DinParams p, const float* __restrict__
                   float* __restrict__ g_hist, int32_t* err_flag) {
     extern __shared__ uint8_t smem_raw_tc[];
     uint8_t* base = smem_raw_tc + ((1024u - (smem_u32(smem_raw_tc) & 1023u)) & 1023u);
-    TcSmem sm(base);
+    TcSmem sm(base, 64);
     constexpr int D = 16;
     const int T = p.T;
     const MlpLayout L(D);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int64_t b0 = (int64_t)blockIdx.x * kSamples;
-    const int n_samples = (int)((p.B - b0) < kSamples ? (p.B - b0) : kSamples);
+    const int64_t n_groups = (p.B + kSamples - 1) / kSamples;
 
     if (tid == 0) mbar_init(sm.bar, 1);
     if (warp == 0) tmem_alloc(sm.tmem_slot, kTcTmemCols);
@@ -976,6 +983,21 @@ din_bwd_tc_kernel(const __grid_constant__ DinParams p, const float* __restrict__
         store_chunk_split(sm.w1, sm.w1_lo, n, c, v);
     }
     for (int i = tid; i < kH2; i += kTcThreads) sm.vec[i] = __ldg(p.mlp + L.w3 + i);
+    fence_async_smem();
+    fence_before();
+    __syncthreads();
+    fence_after();
+    const uint32_t tmem = *sm.tmem_slot;
+    const float* w3 = sm.vec;
+    const uint64_t a_desc[2]  = {umma_desc(smem_u32(sm.a)), umma_desc(smem_u32(sm.a_lo))};
+    const uint64_t w1_desc[2] = {umma_desc(smem_u32(sm.w1)), umma_desc(smem_u32(sm.w1_lo))};
+    const uint64_t w2_desc[2] = {umma_desc(smem_u32(sm.w2)), umma_desc(smem_u32(sm.w2_lo))};
+    const uint32_t my_tmem = tmem + ((uint32_t)(warp * 32) << 16);
+    uint32_t phase = 0;
+
+  for (int64_t group = blockIdx.x; group < n_groups; group += gridDim.x) {   // persistent over sample groups
+    const int64_t b0 = group * kSamples;
+    const int n_samples = (int)((p.B - b0) < kSamples ? (p.B - b0) : kSamples);
     if (tid < kSamples) sm.len[tid] = tid < n_samples ? clip_len(__ldg(p.his_len + b0 + tid), T) : 0;
     for (int i = tid; i < n_samples * D; i += kTcThreads) {
         const int s = i / D, e = i - s * D;
@@ -989,17 +1011,7 @@ din_bwd_tc_kernel(const __grid_constant__ DinParams p, const float* __restrict__
         sm.att[i] = g;          // g_att: upstream gradient of the attention output
         sm.gq[i]  = 0.f;
     }
-    fence_async_smem();
-    fence_before();
     __syncthreads();
-    fence_after();
-    const uint32_t tmem = *sm.tmem_slot;
-    const float* w3 = sm.vec;
-    const uint64_t a_desc[2]  = {umma_desc(smem_u32(sm.a)), umma_desc(smem_u32(sm.a_lo))};
-    const uint64_t w1_desc[2] = {umma_desc(smem_u32(sm.w1)), umma_desc(smem_u32(sm.w1_lo))};
-    const uint64_t w2_desc[2] = {umma_desc(smem_u32(sm.w2)), umma_desc(smem_u32(sm.w2_lo))};
-    const uint32_t my_tmem = tmem + ((uint32_t)(warp * 32) << 16);
-    uint32_t phase = 0;
 
     int s_begin = 0;
     while (s_begin < n_samples) {
@@ -1166,6 +1178,8 @@ din_bwd_tc_kernel(const __grid_constant__ DinParams p, const float* __restrict__
             g_row[b * p.width + c] = g;
         }
     }
+    __syncthreads();      // q / len / att / gq are rewritten by the next group
+  }
     fence_before();
     __syncthreads();
     if (warp == 0) tmem_dealloc(tmem, kTcTmemCols);
@@ -1227,10 +1241,13 @@ int rk_din_fwd(const rk_din_args_t* args, float* concat_all, float* norm, float*
     const int grid = (int)ceil_div(p.B, kSamples);
     if (args->precision == RK_DIN_BF16_TENSOR) {
         RK_CHECK_ARG(p.D == 16, "din_fwd: the tensor-core activation unit is built for D = 16 (got %d)", p.D);
-        const size_t smem_tc = tc::TcSmem::bytes();
+        const size_t smem_tc = tc::TcSmem::bytes(32);
         RK_CUDA(cudaFuncSetAttribute(tc::din_fwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                      (int)smem_tc));
-        tc::din_fwd_tc_kernel<<<grid, tc::kTcThreads, smem_tc, (cudaStream_t)stream_>>>(
+        int per_sm = 1;
+        RK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, tc::din_fwd_tc_kernel, tc::kTcThreads, smem_tc));
+        const int grid_tc = grid < sm_count() * per_sm ? grid : sm_count() * per_sm;   // persistent CTAs
+        tc::din_fwd_tc_kernel<<<grid_tc, tc::kTcThreads, smem_tc, (cudaStream_t)stream_>>>(
             p, concat_all, norm, att_w, relu_masks, err_flag);
         RK_LAUNCH_CHECK();
         return 0;
@@ -1257,10 +1274,13 @@ int rk_din_bwd(const rk_din_args_t* args, const float* concat_all, const float* 
     const int grid = (int)ceil_div(p.B, kSamples);
     if (args->precision == RK_DIN_BF16_TENSOR) {
         RK_CHECK_ARG(p.D == 16, "din_bwd: the tensor-core activation unit is built for D = 16 (got %d)", p.D);
-        const size_t smem_tc = tc::TcSmem::bytes();
+        const size_t smem_tc = tc::TcSmem::bytes(64);
         RK_CUDA(cudaFuncSetAttribute(tc::din_bwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                      (int)smem_tc));
-        tc::din_bwd_tc_kernel<<<grid, tc::kTcThreads, smem_tc, (cudaStream_t)stream_>>>(
+        int per_sm = 1;
+        RK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, tc::din_bwd_tc_kernel, tc::kTcThreads, smem_tc));
+        const int grid_tc = grid < sm_count() * per_sm ? grid : sm_count() * per_sm;   // persistent CTAs
+        tc::din_bwd_tc_kernel<<<grid_tc, tc::kTcThreads, smem_tc, (cudaStream_t)stream_>>>(
             p, concat_all, norm, att_w, relu_masks, g_concat, g_norm, g_row, g_hist, err_flag);
         RK_LAUNCH_CHECK();
         return 0;
