@@ -477,6 +477,8 @@ def run_ours(args, wl):
     eager = Stepper(model, wl, resident[0], False, None)
     if hasattr(model, "ephemeral_frozen"):
         model.ephemeral_frozen = False
+    from rank_b200 import sparse
+    sparse.PLAN_ON_SIDE_STREAM = False      # time the occurrence plan in-stream, not overlapped
     with _lib.CallTimer() as ct:
         for i in range(args.steps):
             eager.load(resident[i % n_pool])

@@ -10,6 +10,7 @@
 from __future__ import annotations
 
 import ctypes as C
+import os
 from dataclasses import dataclass
 
 import torch
@@ -41,6 +42,21 @@ def field_array(weights, indices, offsets):
 
 def _i64_array(values):
     return (C.c_int64 * max(len(values), 1))(*values)
+
+
+_plan_streams: dict = {}
+PLAN_ON_SIDE_STREAM = os.environ.get("RANK_B200_PLAN_STREAM", "1") != "0"
+
+
+def _plan_stream(device):
+    """The per-device side stream the occurrence plans are built on (None: build in-stream)."""
+    if not PLAN_ON_SIDE_STREAM:
+        return None
+    key = device.index if device.index is not None else torch.cuda.current_device()
+    stream = _plan_streams.get(key)
+    if stream is None:
+        stream = _plan_streams[key] = torch.cuda.Stream(device=device)
+    return stream
 
 
 @dataclass
@@ -85,11 +101,33 @@ class OccurrencePlan:
             seq_T = (C.c_int32 * self.F)(*[0 if l is None else self.n[k] // max(int(l.numel()), 1)
                                            for k, l in enumerate(lens)])
             modes = (C.c_int32 * self.F)(*[int(m) for m in live_mode])
-        rc = lib.rk_plan_build(idx_ptrs, _i64_array(self.n), _i64_array(self.rows), self.F,
-                               len_ptrs, seq_T, modes, self.sorted_keys.data_ptr(), self.perm.data_ptr(),
-                               ws.data_ptr(), ws_bytes, _lib.err_flag(dev).data_ptr(),
-                               _lib.stream_ptr())
+        # The order depends on the indices only, so it is built on a side stream while the main
+        # stream runs the forward kernel and the tower; reduce_to_dense() joins.  Every buffer was
+        # allocated above on the main stream and stays referenced until the join, so the caching
+        # allocator cannot hand it out early; inside a CUDA-graph capture the fork/join is captured.
+        main = torch.cuda.current_stream(dev)
+        side = _plan_stream(dev)
+        self._ws = ws
+        self._event = None
+        if side is None:
+            rc = lib.rk_plan_build(idx_ptrs, _i64_array(self.n), _i64_array(self.rows), self.F,
+                                   len_ptrs, seq_T, modes, self.sorted_keys.data_ptr(), self.perm.data_ptr(),
+                                   ws.data_ptr(), ws_bytes, _lib.err_flag(dev).data_ptr(), main.cuda_stream)
+        else:
+            side.wait_stream(main)
+            with torch.cuda.stream(side):
+                rc = lib.rk_plan_build(idx_ptrs, _i64_array(self.n), _i64_array(self.rows), self.F,
+                                       len_ptrs, seq_T, modes, self.sorted_keys.data_ptr(), self.perm.data_ptr(),
+                                       ws.data_ptr(), ws_bytes, _lib.err_flag(dev).data_ptr(), side.cuda_stream)
+                self._event = side.record_event()
         _lib.check(rc, "rk_plan_build")
+
+    def join(self):
+        """Make the current stream wait for the plan (no-op when it was built in-stream)."""
+        if self._event is not None:
+            torch.cuda.current_stream(self.sorted_keys.device).wait_event(self._event)
+            self._event = None
+        self._ws = None
 
     def reduce_to_dense(self, sources: list[GradSource]) -> list[torch.Tensor]:
         """One dense `[rows, dim]` gradient per source, summed over duplicate indices."""
@@ -97,6 +135,7 @@ class OccurrencePlan:
         T = len(sources)
         if not 1 <= T <= _lib.RK_MAX_TABLES:
             raise ValueError(f"{T} gradient tables (max {_lib.RK_MAX_TABLES})")
+        self.join()
         dev = self.sorted_keys.device
         # one zero-filled slab for all dense gradients (a single memset), carved per table
         sizes = [s.rows * s.dim for s in sources]
