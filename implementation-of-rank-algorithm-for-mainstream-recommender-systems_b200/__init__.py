@@ -20,6 +20,7 @@ from .deepcrossing import DeepCrossingModel, residual_unit
 from .din import (DIN, Dice, din_attention, din_collate_fn, get_activation_unit_precision,
                   set_activation_unit_precision)
 from .afm import AFM, create_feature_columns
+from .sharded import RowShardedEmbedding, shard_bst_feedid_table
 from .bst import BSTModel, BSTTransformer, leakyrelu, load_vocabulary
 
 __all__ = [
@@ -28,5 +29,5 @@ __all__ = [
     "GradSource", "OccurrencePlan", "gather_concat",
     "DeepFM", "DCNModel", "cross_layer", "DeepCrossingModel", "residual_unit", "DIN", "Dice", "din_attention", "din_collate_fn", "set_activation_unit_precision",
     "get_activation_unit_precision",
-    "AFM", "create_feature_columns", "BSTModel", "BSTTransformer", "leakyrelu", "load_vocabulary",
+    "AFM", "create_feature_columns", "RowShardedEmbedding", "shard_bst_feedid_table", "BSTModel", "BSTTransformer", "leakyrelu", "load_vocabulary",
 ]

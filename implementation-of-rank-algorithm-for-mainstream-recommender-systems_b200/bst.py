@@ -23,6 +23,7 @@ import torch.nn as nn
 
 from . import _lib
 from .dcn import NUM_DENSE, SIDE_COLUMNS, SIDE_TABLES
+from .sharded import RowShardedEmbedding
 from .sparse import GatherConcat, GradSource, OccurrencePlan
 
 D_MODEL = 16
@@ -234,7 +235,13 @@ class BSTModel(nn.Module):
         blocks = list(self.transformer_blocks)
         if not blocks:      # no transformer: the reference pools the raw sequence embeddings
             raise NotImplementedError("BSTModel needs at least one transformer block on the fused path")
-        x, idx = self.embeddings['feedid'].weight, seq_feedid
+        feed = self.embeddings['feedid']
+        if isinstance(feed, RowShardedEmbedding):
+            # scaled configuration: the table is row-sharded over the ranks; the rows arrive
+            # owner-sorted through the all-to-all and idx becomes the inverse permutation
+            x, idx = feed.exchange(seq_feedid)
+        else:
+            x, idx = feed.weight, seq_feedid
         for i, block in enumerate(blocks):
             last = i == len(blocks) - 1
             x = block.run(x, seq_length, idx=idx, pool=pool if last else None)

@@ -16,7 +16,9 @@ import torch.distributed as dist
 class GradientAllReducer:
     def __init__(self, model: torch.nn.Module, group=None):
         self.group = group
-        self.params = [p for p in model.parameters() if p.requires_grad]
+        # row-sharded tables are owned by one rank each: their gradients are not replicated
+        self.params = [p for p in model.parameters()
+                       if p.requires_grad and not getattr(p, "_rank_local", False)]
         if not self.params:
             raise ValueError("model has no trainable parameters")
         dev, dtype = self.params[0].device, self.params[0].dtype

@@ -185,6 +185,26 @@ int rk_afm_bwd(const rk_field_t* fields, int F, const float* w1, const float* b1
                float* g_b1, float* g_w2, float* g_b2, float* partials, int n_ctas,
                int32_t* err_flag, rk_stream_t stream);
 
+/* ---- row-sharded table (BASELINE config 5 "scaled": BST feedid table of 1e8 rows block-
+ *      partitioned by row over the ranks; the reference itself is single-process) ------------
+ * Bookkeeping around the two all-to-alls (indices out / rows back, mirrored for gradients):
+ *   rk_shard_owner : owner[i] = idx[i] / rows_per_rank (out-of-range indices -> row 0 + err flag)
+ *   rk_shard_route : given the stable owner-sorted order of owner[] from rk_plan_build
+ *                    (sorted_owner, perm), write send_local[i] = owner-local row of the i-th sorted
+ *                    request, inv[p] = sorted slot of original position p, counts[w] = requests
+ *                    for rank w (W <= 64)
+ *   rk_plan_compact: for an all-live single-field plan, rank_keys[i] = number of distinct rows
+ *                    before sorted position i, uniq_rows[r] = the r-th distinct row, *n_uniq =
+ *                    their count; rk_embgrad_segment_reduce run on rank_keys (rows = *n_uniq)
+ *                    then yields the compact [n_uniq, D] gradient of a sparse update. */
+int rk_shard_owner(const int64_t* idx, int64_t n, int64_t rows_total, int64_t rows_per_rank,
+                   int64_t* owner, int32_t* err_flag, rk_stream_t stream);
+int rk_shard_route(const int64_t* idx, const uint32_t* sorted_owner, const uint32_t* perm, int64_t n,
+                   int64_t rows_total, int64_t rows_per_rank, int W, int64_t* send_local, int64_t* inv,
+                   int64_t* counts, rk_stream_t stream);
+int rk_plan_compact(const uint32_t* sorted_keys, int64_t n, int64_t rows, uint32_t* rank_keys,
+                    int64_t* uniq_rows, int64_t* n_uniq, rk_stream_t stream);
+
 /* ---- DeepCrossing residual units (residual_unit + loop, DeepCrossing/deepcrossing.py:25-42,
  *      148-159), fused with the gather + concat ----------------------------------------------
  * units: n_units packed per-call weight blocks of rk_resunit_pack_floats(d, H) floats each,
