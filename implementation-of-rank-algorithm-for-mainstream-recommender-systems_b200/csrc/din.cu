@@ -626,8 +626,38 @@ __device__ __forceinline__ void store_chunk_split(uint8_t* hi_tile, uint8_t* lo_
     store_chunk(lo_tile, r, c, lo);
 }
 
+// 8 consecutive floats (32-byte aligned: every block of the packed weights starts on a multiple of 8)
+__device__ __forceinline__ void ld8(const float* __restrict__ p, float (&v)[8]) {
+    const float4 a = __ldg(reinterpret_cast<const float4*>(p));
+    const float4 b = __ldg(reinterpret_cast<const float4*>(p) + 1);
+    v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+}
+
 constexpr int kTcThreads  = 128;
 constexpr int kTcTmemCols = 128;     // 64 (layer 1) + 32 (layer 2), power of two
+
+// Dynamic group scheduler of the persistent tensor-core kernels: [0] forward, [1] backward.
+// CTAs draw sample groups from `next`; the last CTA to finish re-arms both counters, so every
+// launch (and every CUDA-graph replay) starts from zero without a memset.  One launch of a
+// kernel at a time per device (launches are stream-ordered; one process per GPU).
+__device__ unsigned int g_din_next[2];
+__device__ unsigned int g_din_done[2];
+
+__device__ __forceinline__ int64_t next_group(int which, unsigned int* slot) {
+    if (threadIdx.x == 0) *slot = atomicAdd(&g_din_next[which], 1u);
+    __syncthreads();
+    return (int64_t)*slot;
+}
+__device__ __forceinline__ void scheduler_exit(int which) {
+    if (threadIdx.x == 0) {
+        __threadfence();
+        if (atomicAdd(&g_din_done[which], 1u) == gridDim.x - 1) {
+            g_din_next[which] = 0;
+            g_din_done[which] = 0;
+            __threadfence();
+        }
+    }
+}
 
 struct TcSmem {
     uint8_t *a, *a_lo, *w1, *w1_lo, *w2, *w2_lo;   // swizzled bf16 tiles: [128][64], [64][64], [<=64][64], hi + lo
@@ -685,15 +715,13 @@ din_fwd_tc_kernel(const __grid_constant__ DinParams p, float* __restrict__ conca
     for (int item = tid; item < 64 * 8; item += kTcThreads) {         // W1[n][k]: 64 rows x 8 chunks
         const int n = item >> 3, c = item & 7;
         float v[8];
-#pragma unroll
-        for (int j = 0; j < 8; ++j) v[j] = __ldg(p.mlp + L.w1 + n * 64 + c * 8 + j);
+        ld8(p.mlp + L.w1 + n * 64 + c * 8, v);
         store_chunk_split(sm.w1, sm.w1_lo, n, c, v);
     }
     for (int item = tid; item < 32 * 8; item += kTcThreads) {         // W2[n][k]: 32 rows x 8 chunks
         const int n = item >> 3, c = item & 7;
         float v[8];
-#pragma unroll
-        for (int j = 0; j < 8; ++j) v[j] = __ldg(p.mlp + L.w2 + n * 64 + c * 8 + j);
+        ld8(p.mlp + L.w2 + n * 64 + c * 8, v);
         store_chunk_split(sm.w2, sm.w2_lo, n, c, v);
     }
     for (int i = tid; i < kH1; i += kTcThreads) sm.vec[i] = __ldg(p.mlp + L.b1 + i);
@@ -719,7 +747,10 @@ din_fwd_tc_kernel(const __grid_constant__ DinParams p, float* __restrict__ conca
     uint32_t phase = 0;
 
   // persistent: the weights, the barrier and the TMEM columns are set up once per CTA
-  for (int64_t group = blockIdx.x; group < n_groups; group += gridDim.x) {
+  __shared__ unsigned int group_slot;
+  for (;;) {
+    const int64_t group = next_group(0, &group_slot);
+    if (group >= n_groups) break;
     const int64_t b0 = group * kSamples;
     const int n_samples = (int)((p.B - b0) < kSamples ? (p.B - b0) : kSamples);
     for (int i = tid; i < n_samples * D; i += kTcThreads) {
@@ -943,6 +974,7 @@ din_fwd_tc_kernel(const __grid_constant__ DinParams p, float* __restrict__ conca
     }
     __syncthreads();      // q / len / att are rewritten by the next group
   }
+    scheduler_exit(0);
     fence_before();
     __syncthreads();
     if (warp == 0) tmem_dealloc(tmem, kTcTmemCols);
@@ -971,15 +1003,13 @@ din_bwd_tc_kernel(const __grid_constant__ DinParams p, const float* __restrict__
     for (int item = tid; item < 64 * 4; item += kTcThreads) {          // W2^T[n][k]: 64 rows x 32 k (4 chunks)
         const int n = item >> 2, c = item & 3;
         float v[8];
-#pragma unroll
-        for (int j = 0; j < 8; ++j) v[j] = __ldg(p.mlp + L.w2t + n * 32 + c * 8 + j);
+        ld8(p.mlp + L.w2t + n * 32 + c * 8, v);
         store_chunk_split(sm.w2, sm.w2_lo, n, c, v);
     }
     for (int item = tid; item < 64 * 8; item += kTcThreads) {          // W1^T[c][n]: 64 rows x 64 k
         const int n = item >> 3, c = item & 7;
         float v[8];
-#pragma unroll
-        for (int j = 0; j < 8; ++j) v[j] = __ldg(p.mlp + L.w1t + n * 64 + c * 8 + j);
+        ld8(p.mlp + L.w1t + n * 64 + c * 8, v);
         store_chunk_split(sm.w1, sm.w1_lo, n, c, v);
     }
     for (int i = tid; i < kH2; i += kTcThreads) sm.vec[i] = __ldg(p.mlp + L.w3 + i);
@@ -995,7 +1025,10 @@ din_bwd_tc_kernel(const __grid_constant__ DinParams p, const float* __restrict__
     const uint32_t my_tmem = tmem + ((uint32_t)(warp * 32) << 16);
     uint32_t phase = 0;
 
-  for (int64_t group = blockIdx.x; group < n_groups; group += gridDim.x) {   // persistent over sample groups
+  __shared__ unsigned int group_slot;
+  for (;;) {                                       // persistent: groups drawn from the scheduler
+    const int64_t group = next_group(1, &group_slot);
+    if (group >= n_groups) break;
     const int64_t b0 = group * kSamples;
     const int n_samples = (int)((p.B - b0) < kSamples ? (p.B - b0) : kSamples);
     if (tid < kSamples) sm.len[tid] = tid < n_samples ? clip_len(__ldg(p.his_len + b0 + tid), T) : 0;
@@ -1180,6 +1213,7 @@ din_bwd_tc_kernel(const __grid_constant__ DinParams p, const float* __restrict__
     }
     __syncthreads();      // q / len / att / gq are rewritten by the next group
   }
+    scheduler_exit(1);
     fence_before();
     __syncthreads();
     if (warp == 0) tmem_dealloc(tmem, kTcTmemCols);
@@ -1244,10 +1278,12 @@ int rk_din_fwd(const rk_din_args_t* args, float* concat_all, float* norm, float*
         const size_t smem_tc = tc::TcSmem::bytes(32);
         RK_CUDA(cudaFuncSetAttribute(tc::din_fwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                      (int)smem_tc));
-        // One CTA per group of 8 samples: measured faster than persistent CTAs striding over the
-        // groups (158 vs 101 us forward at B = 8192) because group work varies with the history
-        // lengths and the hardware CTA scheduler balances it; the kernels keep the group loop.
-        const int grid_tc = grid;
+        // Persistent CTAs drawing groups of 8 samples from a device-side counter: static striding was
+        // measured slower than one CTA per group (158 vs 101 us) because group work varies with the
+        // history lengths; dynamic draws keep the balance and pay the per-CTA setup once.
+        int per_sm = 1;
+        RK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, tc::din_fwd_tc_kernel, tc::kTcThreads, smem_tc));
+        const int grid_tc = grid < sm_count() * per_sm ? grid : sm_count() * per_sm;
         tc::din_fwd_tc_kernel<<<grid_tc, tc::kTcThreads, smem_tc, (cudaStream_t)stream_>>>(
             p, concat_all, norm, att_w, relu_masks, err_flag);
         RK_LAUNCH_CHECK();
@@ -1278,10 +1314,9 @@ int rk_din_bwd(const rk_din_args_t* args, const float* concat_all, const float* 
         const size_t smem_tc = tc::TcSmem::bytes(64);
         RK_CUDA(cudaFuncSetAttribute(tc::din_bwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                      (int)smem_tc));
-        // One CTA per group of 8 samples: measured faster than persistent CTAs striding over the
-        // groups (158 vs 101 us forward at B = 8192) because group work varies with the history
-        // lengths and the hardware CTA scheduler balances it; the kernels keep the group loop.
-        const int grid_tc = grid;
+        int per_sm = 1;
+        RK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, tc::din_bwd_tc_kernel, tc::kTcThreads, smem_tc));
+        const int grid_tc = grid < sm_count() * per_sm ? grid : sm_count() * per_sm;   // persistent, dynamic draws
         tc::din_bwd_tc_kernel<<<grid_tc, tc::kTcThreads, smem_tc, (cudaStream_t)stream_>>>(
             p, concat_all, norm, att_w, relu_masks, g_concat, g_norm, g_row, g_hist, err_flag);
         RK_LAUNCH_CHECK();
