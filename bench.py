@@ -456,6 +456,13 @@ def run_ours(args, wl):
     for i in range(args.warmup):
         stepper.load(resident[i % n_pool])
         stepper.run(i)
+    if world > 1:
+        # NCCL builds its channels lazily over the first collectives: settle them (and the host
+        # threads of all ranks) before the timed region, beyond the W model steps above
+        for i in range(10):
+            stepper.load(resident[i % n_pool])
+            stepper.run(100 + i)
+            barrier()
     barrier()
     launches0 = lib.rk_launch_count()
     with ClockSampler(local) as clocks:
