@@ -1281,9 +1281,9 @@ int rk_din_fwd(const rk_din_args_t* args, float* concat_all, float* norm, float*
         // Persistent CTAs drawing groups of 8 samples from a device-side counter: static striding was
         // measured slower than one CTA per group (158 vs 101 us) because group work varies with the
         // history lengths; dynamic draws keep the balance and pay the per-CTA setup once.
-        int per_sm = 1;
-        RK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, tc::din_fwd_tc_kernel, tc::kTcThreads, smem_tc));
-        const int grid_tc = grid < sm_count() * per_sm ? grid : sm_count() * per_sm;
+        // up to 4 CTAs per SM fit the TMEM budget (4 x 128 columns); CTAs that do not become resident
+        // simply find the scheduler empty when they start
+        const int grid_tc = grid < sm_count() * 4 ? grid : sm_count() * 4;
         tc::din_fwd_tc_kernel<<<grid_tc, tc::kTcThreads, smem_tc, (cudaStream_t)stream_>>>(
             p, concat_all, norm, att_w, relu_masks, err_flag);
         RK_LAUNCH_CHECK();
@@ -1314,9 +1314,9 @@ int rk_din_bwd(const rk_din_args_t* args, const float* concat_all, const float* 
         const size_t smem_tc = tc::TcSmem::bytes(64);
         RK_CUDA(cudaFuncSetAttribute(tc::din_bwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                      (int)smem_tc));
-        int per_sm = 1;
-        RK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, tc::din_bwd_tc_kernel, tc::kTcThreads, smem_tc));
-        const int grid_tc = grid < sm_count() * per_sm ? grid : sm_count() * per_sm;   // persistent, dynamic draws
+        // up to 4 CTAs per SM fit the TMEM budget (4 x 128 columns); CTAs that do not become resident
+        // simply find the scheduler empty when they start
+        const int grid_tc = grid < sm_count() * 4 ? grid : sm_count() * 4;
         tc::din_bwd_tc_kernel<<<grid_tc, tc::kTcThreads, smem_tc, (cudaStream_t)stream_>>>(
             p, concat_all, norm, att_w, relu_masks, g_concat, g_norm, g_row, g_hist, err_flag);
         RK_LAUNCH_CHECK();
