@@ -62,6 +62,27 @@ int pack_fields(const rk_field_t* f, int F, FieldSet* out) {
     return 0;
 }
 
+// One warp per output element: lane l adds the partials of CTAs l, l+32, ... in double, then the
+// 32 lane sums are folded by a fixed shuffle tree — the order never depends on scheduling.
+__global__ void __launch_bounds__(256)
+reduce_partials_kernel(const float* __restrict__ partials, int n_cta, int count, float* __restrict__ out) {
+    const int i = (int)((blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5);
+    const int lane = threadIdx.x & 31;
+    if (i >= count) return;
+    double a = 0.0;
+    for (int c = lane; c < n_cta; c += 32) a += (double)partials[(int64_t)c * count + i];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) a += __shfl_xor_sync(kFull, a, o);
+    if (lane == 0) out[i] = (float)a;
+}
+
+int launch_reduce_partials(const float* partials, int n_cta, int count, float* out, cudaStream_t s) {
+    const int64_t threads = (int64_t)count * 32;
+    reduce_partials_kernel<<<(int)ceil_div(threads, 256), 256, 0, s>>>(partials, n_cta, count, out);
+    RK_LAUNCH_CHECK();
+    return 0;
+}
+
 // Measurement aid: keeps the stream busy for `us` microseconds so that the host can enqueue a
 // whole step behind it; the kernels then run back to back and CUDA events see device time only.
 __global__ void spin_kernel(unsigned long long ns) {

@@ -335,16 +335,6 @@ afm_bwd_kernel(const __grid_constant__ AfmParams p, const float* __restrict__ g_
     if (tid == kAfmThreads - 32) out[p.A * D + 2 * p.A] = acc_b2;
 }
 
-// out[i] = sum over CTAs (ascending) of partials[cta][i]
-__global__ void __launch_bounds__(256)
-afm_reduce_partials_kernel(const float* __restrict__ partials, int n_cta, int count, float* __restrict__ out) {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= count) return;
-    float a = 0.f;
-    for (int c = 0; c < n_cta; ++c) a += partials[(int64_t)c * count + i];
-    out[i] = a;
-}
-
 static int afm_fill(const rk_field_t* fields, int F, const float* w1, const float* b1, const float* w2,
                     const float* b2, int A, int64_t B, AfmParams* p) {
     if (int rc = pack_fields(fields, F, &p->fs)) return rc;
@@ -423,9 +413,7 @@ int rk_afm_bwd(const rk_field_t* fields, int F, const float* w1, const float* b1
     afm_bwd_kernel<<<n_ctas, kAfmThreads, smem, s>>>(p, g_out, g_rows, partials, err_flag);
     RK_LAUNCH_CHECK();
     const int count = A * p.D + 2 * A + 1;
-    afm_reduce_partials_kernel<<<(count + 255) / 256, 256, 0, s>>>(partials, n_ctas, count, g_w1);
-    RK_LAUNCH_CHECK();
-    return 0;
+    return launch_reduce_partials(partials, n_ctas, count, g_w1, s);
 }
 
 }  // extern "C"

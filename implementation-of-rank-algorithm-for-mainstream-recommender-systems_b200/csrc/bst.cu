@@ -585,15 +585,6 @@ bst_bwd_kernel(const __grid_constant__ BstParams p, const float* __restrict__ g_
     }
 }
 
-__global__ void __launch_bounds__(256)
-bst_reduce_partials_kernel(const float* __restrict__ partials, int n_cta, int count, float* __restrict__ out) {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= count) return;
-    double a = 0.0;
-    for (int c = 0; c < n_cta; ++c) a += (double)partials[(int64_t)c * count + i];
-    out[i] = (float)a;
-}
-
 static int bst_fill(const rk_bst_block_t* blk, const float* table, const int64_t* idx, int64_t table_rows,
                     const float* x_in, const int64_t* seq_len, int64_t B, int T, int pool_mean, BstParams* p) {
     RK_CHECK_ARG(blk, "bst: block is NULL");
@@ -698,9 +689,7 @@ int rk_bst_block_bwd(const rk_bst_block_t* blk, int nhead, const float* table, c
     }
     if (rc) return rc;
     const int count = rk_bst_grad_floats(T);
-    bst_reduce_partials_kernel<<<(count + 255) / 256, 256, 0, s>>>(partials, n_ctas, count, g_params);
-    RK_LAUNCH_CHECK();
-    return 0;
+    return launch_reduce_partials(partials, n_ctas, count, g_params, s);
 }
 
 }  // extern "C"

@@ -20,6 +20,9 @@ constexpr unsigned kFull = 0xffffffffu;
 void set_error(const char* fmt, ...);
 int  sm_count();
 void note_launch();  // counts kernels launched through the ABI (rk_launch_count)
+// out[i] = sum over c < n_cta (fixed order, double accumulation) of partials[c*count + i]:
+// the deterministic last step of the batch-wide weight-gradient reductions (AFM, BST).
+int  launch_reduce_partials(const float* partials, int n_cta, int count, float* out, cudaStream_t s);
 
 #define RK_CHECK_ARG(cond, ...)              \
     do {                                     \

@@ -107,38 +107,60 @@ segment_chunk_kernel(const __grid_constant__ ReduceParams p, const uint32_t* __r
 
 // Second pass, one warp per chunk: the chunk that holds the head of a row spilling into later
 // chunks adds their lead partials.  The end of the run is found by binary search on the sorted
-// keys; the partials are summed by RL row-lanes in a fixed interleaved order and folded with a
-// fixed shuffle tree, so the result does not depend on scheduling.
-template <int V>
-__device__ __forceinline__ void combine_chunk(const ReduceJob& jb, const uint32_t* __restrict__ keys,
-                                              int64_t c, int lane) {
+// keys; the partials are summed by row-lanes in a fixed interleaved order and folded with a fixed
+// shuffle tree, so the result does not depend on scheduling.  Runs longer than kLongRun chunks
+// (a padding row hit by tens of thousands of positions) are summed by all warps of the CTA, whose
+// per-warp totals are then added in warp order.
+constexpr int kLongRun = 32;
+
+// Is chunk c the head of a row that spills into later chunks?  If so: its key and last chunk.
+__device__ __forceinline__ bool find_run(const ReduceJob& jb, const uint32_t* __restrict__ keys, int64_t c,
+                                         uint32_t* key_out, int64_t* c_last_out) {
     const int64_t n_chunks = (jb.n + kChunk - 1) / kChunk;
     const int64_t pos0     = jb.seg_start + c * kChunk;
     const int     cnt      = (int)((jb.n - c * kChunk) < kChunk ? (jb.n - c * kChunk) : kChunk);
     const int64_t last     = pos0 + cnt - 1;
-    if (c + 1 >= n_chunks) return;
+    if (c + 1 >= n_chunks) return false;
     const uint32_t k = keys[last];
-    if (k == jb.dead_key || keys[last + 1] != k) return;   // nothing spills out of this chunk
+    if (k == jb.dead_key || keys[last + 1] != k) return false;   // nothing spills out of this chunk
     const bool head_here = (keys[pos0] != k) || c == 0 || keys[pos0 - 1] != k;
-    if (!head_here) return;
+    if (!head_here) return false;
     // chunks c+1 .. c_last start with key k (predicate is monotone over the sorted keys)
     int64_t lo = c + 1, hi = n_chunks - 1;
     while (lo < hi) {
         const int64_t mid = (lo + hi + 1) >> 1;
         if (keys[jb.seg_start + mid * kChunk] == k) lo = mid; else hi = mid - 1;
     }
-    const int64_t c_last = lo;
-    const int CL = jb.lanes;                       // column lanes (dim / V)
-    int RL = 1;
-    while (RL * 2 * CL <= 32) RL *= 2;             // row lanes, power of two
+    *key_out = k;
+    *c_last_out = lo;
+    return true;
+}
+
+// Sum of lead[first + slot + i*stride], i >= 0, up to c_last, over this warp's row-lanes; the
+// warp total ends up in the lanes with rl == 0 (one per column lane).
+template <int V>
+__device__ __forceinline__ Vec<V> sum_run(const ReduceJob& jb, int64_t first, int64_t c_last, int lane,
+                                          int slot0, int stride, int RL, bool* owner) {
+    const int CL = jb.lanes;
     const int rl = lane / CL, cl = lane - rl * CL;
     const bool on = rl < RL;
     Vec<V> acc;
     vec_zero(acc);
     if (on) {
-        for (int64_t cc = c + 1 + rl; cc <= c_last; cc += RL) {
+        const float* src = jb.lead + cl * V;
+        int64_t cc = first + slot0 + rl;
+        for (; cc + 3 * (int64_t)stride <= c_last; cc += 4 * (int64_t)stride) {   // four loads in flight
+            Vec<V> p0, p1, p2, p3;
+            p0.load_plain(src + cc * (int64_t)jb.dim);
+            p1.load_plain(src + (cc + stride) * (int64_t)jb.dim);
+            p2.load_plain(src + (cc + 2 * stride) * (int64_t)jb.dim);
+            p3.load_plain(src + (cc + 3 * stride) * (int64_t)jb.dim);
+#pragma unroll
+            for (int e = 0; e < V; ++e) acc.v[e] += (p0.v[e] + p1.v[e]) + (p2.v[e] + p3.v[e]);
+        }
+        for (; cc <= c_last; cc += stride) {
             Vec<V> part;
-            part.load_plain(jb.lead + cc * (int64_t)jb.dim + cl * V);
+            part.load_plain(src + cc * (int64_t)jb.dim);
 #pragma unroll
             for (int e = 0; e < V; ++e) acc.v[e] += part.v[e];
         }
@@ -150,30 +172,88 @@ __device__ __forceinline__ void combine_chunk(const ReduceJob& jb, const uint32_
             if (on && rl < o) acc.v[e] += other;
         }
     }
-    if (on && rl == 0) {
-        float* out = jb.dw + (int64_t)(k - jb.key_base) * jb.dim + cl * V;
+    *owner = on && rl == 0;
+    return acc;
+}
+
+struct LongRun {
+    int64_t  c, c_last;
+    uint32_t key;
+    int32_t  table;      // index into ReduceParams::job, -1 = none
+};
+
+template <int V>
+__device__ __forceinline__ void combine_dispatch(const ReduceJob& jb, bool long_phase, uint32_t k, int64_t c,
+                                                 int64_t c_last, int lane, int warp, float* red) {
+    const int CL = jb.lanes;
+    int RL = 1;
+    while (RL * 2 * CL <= 32) RL *= 2;             // row lanes, power of two
+    const int cl = lane % CL;
+    bool owner;
+    if (!long_phase) {                             // the head's own warp sums the whole run
+        Vec<V> acc = sum_run<V>(jb, c + 1, c_last, lane, 0, RL, RL, &owner);
+        if (owner) {
+            float* out = jb.dw + (int64_t)(k - jb.key_base) * jb.dim + cl * V;
+            Vec<V> own;
+            own.load_plain(out);
+#pragma unroll
+            for (int e = 0; e < V; ++e) own.v[e] += acc.v[e];
+            own.store(out);
+        }
+        return;
+    }
+    // all 8 warps of the CTA: warp w takes the row-lane slots [w*RL, (w+1)*RL) of 8*RL
+    Vec<V> acc = sum_run<V>(jb, c + 1, c_last, lane, warp * RL, 8 * RL, RL, &owner);
+    if (owner) {
+#pragma unroll
+        for (int e = 0; e < V; ++e) red[warp * 128 + cl * V + e] = acc.v[e];
+    }
+    __syncthreads();
+    if (warp == 0 && lane < CL) {
+        float* out = jb.dw + (int64_t)(k - jb.key_base) * jb.dim + lane * V;
         Vec<V> own;
         own.load_plain(out);
+        for (int ww = 0; ww < 8; ++ww) {
 #pragma unroll
-        for (int e = 0; e < V; ++e) own.v[e] += acc.v[e];
+            for (int e = 0; e < V; ++e) own.v[e] += red[ww * 128 + lane * V + e];
+        }
         own.store(out);
     }
+    __syncthreads();
 }
 
 __global__ void __launch_bounds__(256)
 segment_combine_kernel(const __grid_constant__ ReduceParams p, const uint32_t* __restrict__ keys) {
+    __shared__ LongRun jobs[8];
+    __shared__ float red[8 * 128];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int64_t w = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
-    if (w >= p.total_warps) return;
-    int j = 0;
+    if (lane == 0) jobs[warp].table = -1;
+    if (w < p.total_warps) {
+        int j = 0;
 #pragma unroll 1
-    while (j + 1 < p.n_tables && w >= p.job[j + 1].warp_start) ++j;
-    const ReduceJob& jb = p.job[j];
-    const int64_t c = w - jb.warp_start;
-    if (c * kChunk >= jb.n) return;
-    const int lane = threadIdx.x & 31;
-    if (jb.vec == 4)      combine_chunk<4>(jb, keys, c, lane);
-    else if (jb.vec == 2) combine_chunk<2>(jb, keys, c, lane);
-    else                  combine_chunk<1>(jb, keys, c, lane);
+        while (j + 1 < p.n_tables && w >= p.job[j + 1].warp_start) ++j;
+        const ReduceJob& jb = p.job[j];
+        const int64_t c = w - jb.warp_start;
+        uint32_t k;
+        int64_t c_last;
+        if (c * kChunk < jb.n && find_run(jb, keys, c, &k, &c_last)) {
+            if (c_last - c > kLongRun) {
+                if (lane == 0) { jobs[warp].c = c; jobs[warp].c_last = c_last; jobs[warp].key = k; jobs[warp].table = j; }
+            } else if (jb.vec == 4) combine_dispatch<4>(jb, false, k, c, c_last, lane, warp, red);
+            else if (jb.vec == 2)   combine_dispatch<2>(jb, false, k, c, c_last, lane, warp, red);
+            else                    combine_dispatch<1>(jb, false, k, c, c_last, lane, warp, red);
+        }
+    }
+    __syncthreads();
+    for (int q = 0; q < 8; ++q) {                  // long runs found by this CTA's warps, one by one
+        const LongRun r = jobs[q];
+        if (r.table < 0) continue;                 // uniform over the CTA
+        const ReduceJob& jb = p.job[r.table];
+        if (jb.vec == 4)      combine_dispatch<4>(jb, true, r.key, r.c, r.c_last, lane, warp, red);
+        else if (jb.vec == 2) combine_dispatch<2>(jb, true, r.key, r.c, r.c_last, lane, warp, red);
+        else                  combine_dispatch<1>(jb, true, r.key, r.c, r.c_last, lane, warp, red);
+    }
 }
 
 static int vec_of(int dim) { return dim % 4 == 0 ? 4 : (dim % 2 == 0 ? 2 : 1); }
