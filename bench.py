@@ -193,6 +193,29 @@ WORKLOADS = {"deepfm": DeepFMWorkload, "dcn": DCNWorkload, "afm": AFMWorkload, "
 
 
 # ------------------------------------------------------------------------------- helpers
+# fused forward + backward kernels whose ncu dram__bytes (profiles/r01_traffic.json, one
+# `ncu --set full` capture per kernel) are reported as roofline.traffic
+TRAFFIC_KERNELS = {
+    "dcn": ("crossnet_fwd_kernel", "crossnet_bwd_kernel"), "afm": ("afm_fwd_kernel", "afm_bwd_kernel"),
+    "bst": ("bst_fwd_kernel", "bst_bwd_kernel"), "din_tc": ("din_fwd_tc_kernel", "din_bwd_tc_kernel"),
+}
+
+
+def measured_traffic(workload_key):
+    """DRAM bytes per launch (read + write) of the workload's fused fwd+bwd kernels, from the
+    committed ncu capture of this round; None when no capture exists for them."""
+    path = os.path.join(ROOT, "profiles", "r01_traffic.json")
+    names = TRAFFIC_KERNELS.get(workload_key)
+    if not names or not os.path.exists(path):
+        return None, None
+    with open(path) as f:
+        table = json.load(f)
+    if not all(n in table for n in names):
+        return None, None
+    per = {n: table[n]["dram_read_bytes"] + table[n]["dram_write_bytes"] for n in names}
+    return sum(per.values()), per
+
+
 def peaks():
     path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(path):
@@ -209,27 +232,30 @@ class ClockSampler:
              "clocks_event_reasons.sw_power_cap")
 
     def __init__(self, index):
-        self.index, self.proc, self.lines = index, None, []
+        self.index, self.proc, self.lines, self.marks = index, None, [], []
 
     def __enter__(self):
         try:
             self.proc = subprocess.Popen(
                 ["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.QUERY}",
-                 "--format=csv,noheader,nounits", "-lms", "200"],
+                 "--format=csv,noheader,nounits", "-lms", "50"],
                 stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.thread = threading.Thread(target=self._pump, daemon=True)
             self.thread.start()
+            t_end = time.time() + 3.0          # let nvidia-smi finish starting up before any timing
+            while not self.lines and time.time() < t_end and self.proc.poll() is None:
+                time.sleep(0.01)
         except OSError:
             self.proc = None
         return self
 
     def _pump(self):
         for line in self.proc.stdout:
-            self.lines.append(line.strip())
+            self.lines.append((time.time(), line.strip()))
 
     def __exit__(self, *exc):
         if self.proc is not None:
-            time.sleep(0.25)
+            time.sleep(0.06)
             self.proc.terminate()
             try:
                 self.proc.wait(timeout=2)
@@ -237,10 +263,27 @@ class ClockSampler:
                 self.proc.kill()
         return False
 
+    def mark(self):
+        """Call at the start and at the end of the timed region."""
+        self.marks.append(time.time())
+
     def summary(self):
+        """Clocks / throttle reasons of the samples taken during the timed region (the sampler
+        itself is started before the warm-up so that its start-up does not disturb the region;
+        a region shorter than the sampling period takes the samples nearest to it)."""
         sm, smax, reasons = [], [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for line in self.lines:
+        lines = self.lines
+        if len(self.marks) >= 2 and lines:
+            t0, t1 = self.marks[0], self.marks[-1]
+            inside = [l for ts, l in lines if t0 - 0.06 <= ts <= t1 + 0.06]
+            if not inside:
+                nearest = sorted(lines, key=lambda x: min(abs(x[0] - t0), abs(x[0] - t1)))[:3]
+                inside = [l for _, l in nearest]
+            lines = inside
+        else:
+            lines = [l for _, l in lines]
+        for line in lines:
             parts = [p.strip() for p in line.split(",")]
             if len(parts) < 6:
                 continue
@@ -453,22 +496,24 @@ def run_ours(args, wl):
         torch.cuda.synchronize()
         return sum(s.elapsed_time(e) for s, e in evs), float(loss.detach())
 
-    for i in range(args.warmup):
-        stepper.load(resident[i % n_pool])
-        stepper.run(i)
-    if world > 1:
-        # NCCL builds its channels lazily over the first collectives: settle them (and the host
-        # threads of all ranks) before the timed region, beyond the W model steps above
-        for i in range(10):
+    with ClockSampler(local) as clocks:      # started before the warm-up, sampled through the timed region
+        for i in range(args.warmup):
             stepper.load(resident[i % n_pool])
-            stepper.run(100 + i)
-            barrier()
-    barrier()
-    launches0 = lib.rk_launch_count()
-    with ClockSampler(local) as clocks:
+            stepper.run(i)
+        if world > 1:
+            # NCCL builds its channels lazily over the first collectives: settle them (and the host
+            # threads of all ranks) before the timed region, beyond the W model steps above
+            for i in range(10):
+                stepper.load(resident[i % n_pool])
+                stepper.run(100 + i)
+                barrier()
         barrier()
+        launches0 = lib.rk_launch_count()
+        barrier()
+        clocks.mark()
         total_ms, last_loss = timed(args.steps, 10_000, from_host=False)
         barrier()
+        clocks.mark()
     launches = lib.rk_launch_count() - launches0
     if stepper.graph is not None:
         launches = stepper_launches_per_replay(stepper, lib) * args.steps
@@ -502,6 +547,7 @@ def run_ours(args, wl):
 
     if rank == 0:
         pk = peaks()
+        traffic, traffic_by = measured_traffic(args.workload)
         hot_ms = sum(ms for name, (n, ms) in calls.items() if name in wl.hot_calls) / args.steps
         achieved = (B * wl.bytes_per_sample) / (hot_ms * 1e-3) / 1e9 if hot_ms > 0 else 0.0
         line = {
@@ -519,7 +565,11 @@ def run_ours(args, wl):
                     "h2d_bytes_per_step": batch_bytes(host[0]), "d2h_bytes_per_step": 4},
             "gpu_launches": int(launches),
             "roofline": {"bound": wl.bound, "achieved": achieved, "peak": pk["hbm_gbs"], "unit": "GB/s",
-                         "frac": achieved / pk["hbm_gbs"], "traffic": None, "peak_source": pk["source"],
+                         "frac": achieved / pk["hbm_gbs"], "traffic": traffic, "traffic_by_kernel": traffic_by,
+                         "traffic_note": "ncu dram__bytes_read+write of the fused fwd+bwd kernels (one capture, "
+                                         "cold cache); below the algorithmic bytes because tables and outputs "
+                                         "live in the 126 MB L2",
+                         "peak_source": pk["source"],
                          "what": "hot path (all ABI calls of a step: " + ", ".join(wl.hot_calls) + ")",
                          "algorithmic_bytes_per_sample": wl.bytes_per_sample, "hot_ms_per_step": hot_ms},
             "hotpath_calls": {k: {"calls_per_step": n / args.steps, "ms_per_step": ms / args.steps}
