@@ -30,8 +30,8 @@ struct FieldKeys {              // how to turn occurrence o of one field into it
     int32_t        bits;        // bits of rows (+ sentinel)
 };
 
-__device__ __forceinline__ uint32_t local_key(const FieldKeys& f, int64_t o, int32_t* err_flag) {
-    int64_t row = checked_row(f.idx[o], f.rows, err_flag);
+__device__ __forceinline__ uint32_t key_of(const FieldKeys& f, int64_t o, int64_t raw_index, int32_t* err_flag) {
+    int64_t row = checked_row(raw_index, f.rows, err_flag);
     if (f.mode != RK_LIVE_ALL) {
         // padded history positions carry no gradient: park them on the field's sentinel row
         const int64_t b = o / f.T, t = o - b * f.T;
@@ -40,6 +40,9 @@ __device__ __forceinline__ uint32_t local_key(const FieldKeys& f, int64_t o, int
         if (dead) row = f.rows;
     }
     return (uint32_t)row;
+}
+__device__ __forceinline__ uint32_t local_key(const FieldKeys& f, int64_t o, int32_t* err_flag) {
+    return key_of(f, o, f.idx[o], err_flag);
 }
 
 // --------------------------------------------------------------------------- small fields
@@ -68,8 +71,19 @@ small_field_sort_kernel(const __grid_constant__ SmallBatch batch, uint32_t* __re
     const FieldKeys& f = batch.f[blockIdx.x];
     const int tid = threadIdx.x, w = tid >> 5, lane = tid & 31;
     const int n = (int)f.n;
-    for (int i = tid; i < kSmallN; i += kSmallThreads)
-        if (i < n) buf0[i] = (local_key(f, i, err_flag) << kSmallOccBits) | (uint32_t)i;
+    {   // all of a thread's index loads in flight at once (the column is cold in HBM)
+        int64_t raw[kSmallRounds];
+#pragma unroll
+        for (int r = 0; r < kSmallRounds; ++r) {
+            const int i = tid + r * kSmallThreads;
+            raw[r] = i < n ? __ldg(f.idx + i) : 0;
+        }
+#pragma unroll
+        for (int r = 0; r < kSmallRounds; ++r) {
+            const int i = tid + r * kSmallThreads;
+            if (i < n) buf0[i] = (key_of(f, i, raw[r], err_flag) << kSmallOccBits) | (uint32_t)i;
+        }
+    }
 
     const int passes = (f.bits + 8) / 9;
     const int dbits  = (f.bits + passes - 1) / passes;

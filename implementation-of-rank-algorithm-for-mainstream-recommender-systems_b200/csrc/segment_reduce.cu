@@ -53,8 +53,9 @@ __device__ __forceinline__ void reduce_chunk(const ReduceJob& jb, const uint32_t
     vec_zero(acc);
     float* lead_out = jb.lead + c * (int64_t)jb.dim + col;
 
-#pragma unroll 1
-    for (int j0 = 0; j0 < cnt; j0 += 8) {
+#pragma unroll
+    for (int j0 = 0; j0 < kChunk; j0 += 8) {
+        if (j0 >= cnt) break;
         uint32_t kk[8];
         Vec<V>   vv[8];
 #pragma unroll
@@ -125,8 +126,14 @@ __device__ __forceinline__ bool find_run(const ReduceJob& jb, const uint32_t* __
     if (k == jb.dead_key || keys[last + 1] != k) return false;   // nothing spills out of this chunk
     const bool head_here = (keys[pos0] != k) || c == 0 || keys[pos0 - 1] != k;
     if (!head_here) return false;
-    // chunks c+1 .. c_last start with key k (predicate is monotone over the sorted keys)
-    int64_t lo = c + 1, hi = n_chunks - 1;
+    // chunks c+1 .. c_last start with key k (predicate is monotone over the sorted keys): gallop
+    // from c+1 (most runs end within a chunk or two), then bisect the last doubling step
+    int64_t lo = c + 1, step = 1;
+    while (lo + step <= n_chunks - 1 && keys[jb.seg_start + (lo + step) * kChunk] == k) {
+        lo += step;
+        step <<= 1;
+    }
+    int64_t hi = lo + step - 1 < n_chunks - 1 ? lo + step - 1 : n_chunks - 1;
     while (lo < hi) {
         const int64_t mid = (lo + hi + 1) >> 1;
         if (keys[jb.seg_start + mid * kChunk] == k) lo = mid; else hi = mid - 1;
