@@ -696,21 +696,152 @@ struct TcSmem {
     }
 };
 
+// ---- forward -------------------------------------------------------------------------------
+constexpr int kTcGroup = kSamples;   // samples per scheduler draw (16 was measured slower: 93 vs 82 us)
+
+struct TcFwdSmem {
+    uint8_t *a, *a_lo, *w1, *w1_lo, *w2, *w2_lo;   // swizzled split-bf16 tiles; a_lo doubles as pooling scratch
+    float *kstage;                                 // [128][16] history rows landed by cp.async.bulk
+    float *vec, *q, *att, *score, *wt;
+    int *len;
+    int64_t *ix_his, *ix_tgt, *ix_len, *ix_cat;    // the group's raw indices, landed by cp.async
+    int16_t* colmap;                               // concat column -> categorical field; -1 dense/none, -2 target/attention
+    uint64_t *bar_mma;
+    uint32_t* tmem_slot;
+    __device__ TcFwdSmem(uint8_t* base, int T, int F) {
+        uint8_t* p = base;
+        a = p;       p += 128 * 128;
+        a_lo = p;    p += 128 * 128;
+        w1 = p;      p += 64 * 128;
+        w1_lo = p;   p += 64 * 128;
+        w2 = p;      p += 32 * 128;
+        w2_lo = p;   p += 32 * 128;
+        kstage = (float*)p;  p += sizeof(float) * kRows * 16;
+        vec = (float*)p;     p += sizeof(float) * (kH1 + 2 * kH2 + 4);
+        q = (float*)p;       p += sizeof(float) * kTcGroup * 16;
+        att = (float*)p;     p += sizeof(float) * kTcGroup * 16;
+        score = (float*)p;   p += sizeof(float) * kRows;
+        wt = (float*)p;      p += sizeof(float) * kRows;
+        len = (int*)p;       p += sizeof(int) * kTcGroup;
+        bar_mma = (uint64_t*)p;   p += 8;
+        tmem_slot = (uint32_t*)p; p += 8;
+        ix_his = (int64_t*)p;     p += sizeof(int64_t) * kTcGroup * T;
+        ix_tgt = (int64_t*)p;     p += sizeof(int64_t) * kTcGroup;
+        ix_len = (int64_t*)p;     p += sizeof(int64_t) * kTcGroup;
+        ix_cat = (int64_t*)p;     p += sizeof(int64_t) * kTcGroup * F;
+        colmap = (int16_t*)p;
+    }
+    static size_t bytes(int width, int T, int F) {
+        return 1024 /* alignment slack */ + 2 * (128 * 128 + 64 * 128 + 32 * 128) + sizeof(float) * kRows * 16 +
+               sizeof(float) * (kH1 + 2 * kH2 + 4 + 2 * kTcGroup * 16 + 2 * kRows) + sizeof(int) * kTcGroup + 32 +
+               sizeof(int64_t) * kTcGroup * (size_t)(T + 2 + F) + sizeof(int16_t) * (size_t)width;
+    }
+};
+
+// A tile = whole samples [s_begin, s_end) of the group, n_rows <= 128 live (b,t) rows; this
+// thread's row is (my_s, my_t) when `on`.
+struct TcTile {
+    int s_end, n_rows, my_s, my_t;
+    bool on;
+};
+__device__ __forceinline__ TcTile plan_tile_tc(const int* len, int n_samples, int s_begin, int tid) {
+    TcTile t;
+    int rows = 0, s = s_begin;
+    t.my_s = s_begin; t.my_t = 0; t.on = false;
+    while (s < n_samples && rows + len[s] <= kRows) {
+        if (tid >= rows && tid < rows + len[s]) { t.my_s = s; t.my_t = tid - rows; t.on = true; }
+        rows += len[s];
+        ++s;
+    }
+    t.s_end = s;
+    t.n_rows = rows;
+    return t;
+}
+__device__ __forceinline__ int tile_row0(const int* len, int s_begin, int s) {
+    int r0 = 0;
+    for (int i = s_begin; i < s; ++i) r0 += len[i];
+    return r0;
+}
+
+// Asynchronous staging of the tile's history rows: a thread that owns a live row issues four 16-byte
+// cp.async (LDGSTS) copies of it into its own slot of kstage and commits the group; it later waits
+// for its own group only (each thread reads back just the row it copied, so no barrier is needed).
+// No registers are tied up while the rows are in flight: this is issued for tile i+1 while the
+// tensor core works on tile i.  (One 64-byte cp.async.bulk per row was measured slower — 96 vs
+// 82 us for the whole kernel — the TMA unit is built for few large copies, not 200k small ones.)
+__device__ __forceinline__ void issue_rows(const DinParams& p, const TcFwdSmem& sm, const TcTile& t, int tid,
+                                           int32_t* err_flag) {
+    if (t.on) {
+        const int64_t row = checked_row(sm.ix_his[t.my_s * p.T + t.my_t], p.his_rows, err_flag);
+        const float* src = p.his_w + row * 16;
+        const uint32_t dst = smem_u32(sm.kstage + tid * 16);
+#pragma unroll
+        for (int c = 0; c < 4; ++c)
+            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst + 16 * c), "l"(src + 4 * c) : "memory");
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+}
+__device__ __forceinline__ void wait_rows() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
+
+// Every index the group needs — history ids, target id, length, categorical ids — in one round of
+// 8-byte cp.async copies: issued one group ahead (during the last tile of the previous group), so
+// that a group starts with its indices in shared memory and pays one memory latency (the rows)
+// instead of an index -> row chain per feature.
+__device__ __forceinline__ void cp_async8(const void* dst_smem, const void* src) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(smem_u32(dst_smem)), "l"(src) : "memory");
+}
+__device__ __forceinline__ void issue_idx(const DinParams& p, const TcFwdSmem& sm, int64_t group, int tid) {
+    const int64_t b0 = group * kTcGroup;
+    const int n = (int)((p.B - b0) < kTcGroup ? (p.B - b0) : kTcGroup);
+    for (int i = tid; i < n * p.T; i += kTcThreads) cp_async8(sm.ix_his + i, p.his_idx + b0 * p.T + i);
+    if (tid < n) {
+        cp_async8(sm.ix_tgt + tid, p.tgt_idx + b0 + tid);
+        cp_async8(sm.ix_len + tid, p.his_len + b0 + tid);
+    }
+    for (int i = tid; i < p.cat.F * kTcGroup; i += kTcThreads) {
+        const int f = i / kTcGroup, s_ = i - f * kTcGroup;
+        if (s_ < n) cp_async8(sm.ix_cat + i, p.cat.idx[f] + b0 + s_);
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+}
+
+#ifdef RK_DIN_PROFILE
+__device__ unsigned long long g_din_prof[16];
+#define PROF_DECL __shared__ unsigned long long prof_acc[16]; long long prof_t0 = clock64(); const long long prof_start = prof_t0; \
+    if (threadIdx.x < 16) prof_acc[threadIdx.x] = 0;
+#define PROF(i) do { if (threadIdx.x == 0) { const long long t_ = clock64(); prof_acc[i] += t_ - prof_t0; prof_t0 = t_; } } while (0)
+#define PROF_COUNT(i) do { if (threadIdx.x == 0) prof_acc[i] += 1; } while (0)
+#define PROF_END do { if (threadIdx.x == 0) { prof_acc[11] = clock64() - prof_start; for (int i_ = 0; i_ < 16; ++i_) atomicAdd(&g_din_prof[i_], prof_acc[i_]); } } while (0)
+#else
+#define PROF_DECL
+#define PROF(i)
+#define PROF_COUNT(i)
+#define PROF_END
+#endif
+
 __global__ void __launch_bounds__(kTcThreads)
 din_fwd_tc_kernel(const __grid_constant__ DinParams p, float* __restrict__ concat_all,
                   float* __restrict__ norm_out, float* __restrict__ att_w, uint32_t* __restrict__ masks,
                   int32_t* err_flag) {
     extern __shared__ uint8_t smem_raw_tc[];
     uint8_t* base = smem_raw_tc + ((1024u - (smem_u32(smem_raw_tc) & 1023u)) & 1023u);   // swizzle atoms need 1024 B
-    TcSmem sm(base, 32);
+    TcFwdSmem sm(base, p.T, p.cat.F);
+    PROF_DECL
     constexpr int D = 16;
     const int T = p.T;
     const MlpLayout L(D);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int64_t n_groups = (p.B + kSamples - 1) / kSamples;
+    const int64_t n_groups = (p.B + kTcGroup - 1) / kTcGroup;
 
-    // ---- one-time setup: barrier, TMEM, weights (fp32 -> bf16, swizzled, K-major = as registered)
-    if (tid == 0) mbar_init(sm.bar, 1);
+    // The first group is static (blockIdx.x <= n_groups - 1: the grid never exceeds the group count);
+    // later ones are drawn from the device counter.  Its indices start flying before the set-up.
+    int64_t group = blockIdx.x;
+    issue_idx(p, sm, group, tid);
+
+    // ---- one-time setup: barriers, TMEM, weights (fp32 -> split bf16, swizzled, K-major = as registered)
+    if (tid == 0) {
+        mbar_init(sm.bar_mma, 1);
+    }
     if (warp == 0) tmem_alloc(sm.tmem_slot, kTcTmemCols);
     for (int item = tid; item < 64 * 8; item += kTcThreads) {         // W1[n][k]: 64 rows x 8 chunks
         const int n = item >> 3, c = item & 7;
@@ -730,6 +861,13 @@ din_fwd_tc_kernel(const __grid_constant__ DinParams p, float* __restrict__ conca
         sm.vec[kH1 + kH2 + i] = __ldg(p.mlp + L.w3 + i);
     }
     if (tid == 0) sm.vec[kH1 + 2 * kH2] = __ldg(p.mlp + L.b3);
+    for (int c = tid; c < p.width; c += kTcThreads) {
+        int m = -1;
+        for (int f = 0; f < p.cat.F; ++f)
+            if (c >= p.cat.off[f] && c < p.cat.off[f] + p.cat.dim[f]) m = f;
+        if ((c >= p.att_off && c < p.att_off + D) || (c >= p.tgt_off && c < p.tgt_off + D)) m = -2;
+        sm.colmap[c] = (int16_t)m;
+    }
     fence_async_smem();
     fence_before();
     __syncthreads();
@@ -744,237 +882,286 @@ din_fwd_tc_kernel(const __grid_constant__ DinParams p, float* __restrict__ conca
     const uint64_t w1_desc[2] = {umma_desc(smem_u32(sm.w1)), umma_desc(smem_u32(sm.w1_lo))};
     const uint64_t w2_desc[2] = {umma_desc(smem_u32(sm.w2)), umma_desc(smem_u32(sm.w2_lo))};
     const uint32_t my_tmem = tmem + ((uint32_t)(warp * 32) << 16);
-    uint32_t phase = 0;
+    float* pool = reinterpret_cast<float*>(sm.a_lo);     // [128][17], free once the second MMA has read a_lo
+    uint32_t ph_mma = 0;
 
-  // persistent: the weights, the barrier and the TMEM columns are set up once per CTA
-  __shared__ unsigned int group_slot;
-  for (;;) {
-    const int64_t group = next_group(0, &group_slot);
-    if (group >= n_groups) break;
-    const int64_t b0 = group * kSamples;
-    const int n_samples = (int)((p.B - b0) < kSamples ? (p.B - b0) : kSamples);
-    for (int i = tid; i < n_samples * D; i += kTcThreads) {
-        const int s = i / D, e = i - s * D;
-        const int64_t row = checked_row(__ldg(p.tgt_idx + b0 + s), p.tgt_rows, err_flag);
-        sm.q[i] = __ldg(p.tgt_w + row * D + e);
-    }
-    if (tid < kSamples) sm.len[tid] = tid < n_samples ? clip_len(__ldg(p.his_len + b0 + tid), T) : 0;
-    __syncthreads();
-
-    int s_begin = 0;
-    while (s_begin < n_samples) {
-        int s_end;
-        int n_rows = 0;
-        {
-            int s = s_begin;
-            while (s < n_samples && n_rows + sm.len[s] <= kRows) { n_rows += sm.len[s]; ++s; }
-            s_end = s;
-        }
-        if (tid < kSamples + 1) {
-            int acc = 0;
-            for (int s = s_begin; s < s_begin + tid && s < s_end; ++s) acc += sm.len[s];
-            sm.start[tid] = acc;
+    PROF(0);
+    __shared__ unsigned int group_slot;
+    while (group < n_groups) {                   // persistent: groups of 8 samples
+        // the next draw is issued now and published at the first barrier of a tile: its latency is
+        // never exposed, and the last tile of this group prefetches the indices of the next one
+        unsigned int next_draw = 0;
+        if (tid == 0) next_draw = gridDim.x + atomicAdd(&g_din_next[0], 1u);
+        const int64_t b0 = group * kTcGroup;
+        const int n_samples = (int)((p.B - b0) < kTcGroup ? (p.B - b0) : kTcGroup);
+        wait_rows();                             // this group's indices (issue_idx) have landed ...
+        __syncthreads();                         // ... for every thread
+        if (tid < kTcGroup) sm.len[tid] = tid < n_samples ? clip_len(sm.ix_len[tid], T) : 0;
+        if (tid < n_samples * 4) {               // target rows: 4 x 16 bytes per sample, same commit group as the tile rows
+            const int s = tid >> 2, c = tid & 3;
+            const int64_t row = checked_row(sm.ix_tgt[s], p.tgt_rows, err_flag);
+            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;"
+                         ::"r"(smem_u32(sm.q + s * D + 4 * c)), "l"(p.tgt_w + row * D + 4 * c) : "memory");
         }
         __syncthreads();
-        {
-            int s = s_begin;
-            while (s + 1 < s_end && tid >= sm.start[s + 1 - s_begin]) ++s;
-            sm.row_s[tid] = s;
-            sm.row_t[tid] = tid - sm.start[s - s_begin];
+        PROF(1); PROF_COUNT(13);
+
+        int s_begin = 0;
+        TcTile cur = plan_tile_tc(sm.len, n_samples, 0, tid);
+        issue_rows(p, sm, cur, tid, err_flag);               // first tile of the group: exposed latency
+
+        // ---- while those rows fly: every column of the concat rows except the attention output.
+        // Warp w owns samples w and w + 4; all index loads, then all row loads are issued back to
+        // back (registers), so the group pays two memory latencies instead of two per column.
+        constexpr int kSlots = kTcGroup / 4;
+        float ss_part[kSlots];
+#pragma unroll
+        for (int slot = 0; slot < kSlots; ++slot) ss_part[slot] = 0.f;
+        for (int c0 = 0; c0 < p.width; c0 += 128) {
+            const float* src[kSlots][4];
+#pragma unroll
+            for (int slot = 0; slot < kSlots; ++slot)
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const int s = warp + 4 * slot, c = c0 + lane + 32 * j;
+                    src[slot][j] = nullptr;
+                    if (s < n_samples && c < p.width) {
+                        const int64_t b = b0 + s;
+                        const int f = sm.colmap[c];
+                        if (f >= 0) {
+                            const int64_t row = checked_row(sm.ix_cat[f * kTcGroup + s], p.cat.rows[f], err_flag);
+                            src[slot][j] = p.cat.weight[f] + row * p.cat.dim[f] + (c - p.cat.off[f]);
+                        } else if (c < p.n_dense) {
+                            src[slot][j] = p.dense_col[c] + b * p.dense_stride;
+                        }
+                    }
+                }
+            float v[kSlots][4];
+#pragma unroll
+            for (int slot = 0; slot < kSlots; ++slot)
+#pragma unroll
+                for (int j = 0; j < 4; ++j) v[slot][j] = src[slot][j] ? __ldg(src[slot][j]) : 0.f;
+#pragma unroll
+            for (int slot = 0; slot < kSlots; ++slot)
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const int s = warp + 4 * slot, c = c0 + lane + 32 * j;
+                    if (s < n_samples && c < p.width && sm.colmap[c] != -2) {
+                        const float x = v[slot][j];
+                        concat_all[(b0 + s) * p.width + c] = x;
+                        if (c >= p.l2_from) ss_part[slot] = fmaf(x, x, ss_part[slot]);
+                    }
+                }
         }
-        const bool on = tid < n_rows;
-        const int  my_s = sm.row_s[tid], my_t = sm.row_t[tid];
-        float k[16];
+        while (s_begin < n_samples) {
+            // ---- the tile's history rows have landed in shared memory
+            wait_rows();
+            if (s_begin == 0) __syncthreads();   // the target rows were copied by other threads
+            PROF(2); PROF_COUNT(12);
+            float k[16];
 #pragma unroll
-        for (int e = 0; e < 16; ++e) k[e] = 0.f;
-        if (n_rows > 0) {
-            // ---- build this thread's row of A1 = [q, k, q-k, q*k]
-            float qv[16];
-#pragma unroll
-            for (int e = 0; e < 16; ++e) qv[e] = 0.f;
-            if (on) {
-                const int64_t row = checked_row(__ldg(p.his_idx + (b0 + my_s) * T + my_t), p.his_rows, err_flag);
-                const float4* src = reinterpret_cast<const float4*>(p.his_w + row * D);
+            for (int e = 0; e < 16; ++e) k[e] = 0.f;
+            if (cur.on) {
 #pragma unroll
                 for (int c = 0; c < 4; ++c) {
-                    const float4 v = __ldg(src + c);
+                    const float4 v = *reinterpret_cast<const float4*>(sm.kstage + tid * 16 + 4 * c);
                     k[4 * c] = v.x; k[4 * c + 1] = v.y; k[4 * c + 2] = v.z; k[4 * c + 3] = v.w;
                 }
-#pragma unroll
-                for (int e = 0; e < 16; ++e) qv[e] = sm.q[my_s * D + e];
             }
-#pragma unroll
-            for (int half = 0; half < 2; ++half) {
-                float a[8], b[8], c[8], d[8];
-#pragma unroll
-                for (int j = 0; j < 8; ++j) {
-                    a[j] = qv[8 * half + j];
-                    b[j] = k[8 * half + j];
-                    c[j] = a[j] - b[j];
-                    d[j] = a[j] * b[j];
+            const bool has_next = cur.s_end < n_samples;
+            TcTile nxt = cur;
+            // issued while the tensor core works: the rows of the next tile or, on the last tile of
+            // the group, the indices of the next group (kstage / ix_* were consumed before the barrier)
+            auto shadow_work = [&]() {
+                if (has_next) {
+                    nxt = plan_tile_tc(sm.len, n_samples, cur.s_end, tid);
+                    issue_rows(p, sm, nxt, tid, err_flag);
+                } else if ((int64_t)group_slot < n_groups) {
+                    issue_idx(p, sm, (int64_t)group_slot, tid);
                 }
-                store_chunk_split(sm.a, sm.a_lo, tid, 0 + half, a);
-                store_chunk_split(sm.a, sm.a_lo, tid, 2 + half, b);
-                store_chunk_split(sm.a, sm.a_lo, tid, 4 + half, c);
-                store_chunk_split(sm.a, sm.a_lo, tid, 6 + half, d);
-            }
-            fence_async_smem();
-            fence_before();
-            __syncthreads();
-            // ---- layer 1 on the tensor core
-            if (tid == 0) {
-                fence_after();
+            };
+            if (cur.n_rows > 0) {
+                // ---- this thread's row of A1 = [q, k, q-k, q*k]
+                float qv[16];
 #pragma unroll
-                for (int term = 0; term < 3; ++term)   // hi.hi + lo.hi + hi.lo
+                for (int e = 0; e < 16; ++e) qv[e] = cur.on ? sm.q[cur.my_s * D + e] : 0.f;
 #pragma unroll
-                    for (int kk = 0; kk < 4; ++kk)     // K = 64 = 4 x 16; +32 B per step inside the swizzle atom
-                        umma_bf16(tmem, a_desc[term == 1] + 2 * kk, w1_desc[term == 2] + 2 * kk, umma_idesc(64),
-                                  (term | kk) > 0);
-                umma_commit(sm.bar);
-            }
-            mbar_wait(sm.bar, phase);
-            phase ^= 1;
-            fence_after();
-            uint32_t m1a = 0, m1b = 0;
+                for (int half = 0; half < 2; ++half) {
+                    float a[8], b[8], c[8], d[8];
 #pragma unroll
-            for (int half = 0; half < 2; ++half) {
-                float v[32];
-                tmem_ld32(my_tmem + 32 * half, v);
-                uint32_t bits = 0;
-#pragma unroll
-                for (int j = 0; j < 32; ++j) {
-                    v[j] = fmaxf(v[j] + b1[32 * half + j], 0.f);
-                    bits |= (v[j] > 0.f ? 1u : 0u) << j;
-                }
-                if (half == 0) m1a = bits; else m1b = bits;
-#pragma unroll
-                for (int c = 0; c < 4; ++c) {
-                    float h8[8];
-#pragma unroll
-                    for (int j = 0; j < 8; ++j) h8[j] = v[8 * c + j];
-                    store_chunk_split(sm.a, sm.a_lo, tid, 4 * half + c, h8);   // A2 = relu(layer 1), in place
-                }
-            }
-            fence_async_smem();
-            fence_before();
-            __syncthreads();
-            // ---- layer 2 on the tensor core
-            if (tid == 0) {
-                fence_after();
-#pragma unroll
-                for (int term = 0; term < 3; ++term)
-#pragma unroll
-                    for (int kk = 0; kk < 4; ++kk)
-                        umma_bf16(tmem + 64, a_desc[term == 1] + 2 * kk, w2_desc[term == 2] + 2 * kk, umma_idesc(32),
-                                  (term | kk) > 0);
-                umma_commit(sm.bar);
-            }
-            mbar_wait(sm.bar, phase);
-            phase ^= 1;
-            fence_after();
-            {
-                float v[32];
-                tmem_ld32(my_tmem + 64, v);
-                float sc = b3;
-                uint32_t m2 = 0;
-#pragma unroll
-                for (int j = 0; j < 32; ++j) {
-                    const float h = fmaxf(v[j] + b2[j], 0.f);
-                    m2 |= (h > 0.f ? 1u : 0u) << j;
-                    sc = fmaf(h, w3[j], sc);
-                }
-                sm.score[tid] = sc;
-                if (on && masks) {
-                    uint32_t* mk = masks + ((b0 + my_s) * T + my_t) * 3;
-                    mk[0] = m1a; mk[1] = m1b; mk[2] = m2;
-                }
-            }
-            fence_before();
-            __syncthreads();
-        }
-        // ---- attention weights per sample (warp per sample), then weighted pooling through smem
-        for (int s = s_begin + warp; s < s_end; s += kTcThreads / 32) {
-            const int len = sm.len[s], r0 = sm.start[s - s_begin];
-            float* wrow = att_w + (b0 + s) * T;
-            if (len == 0) {
-                const float u = p.use_softmax ? 1.0f / (float)T : 0.f;
-                for (int t = lane; t < T; t += 32) wrow[t] = u;
-                continue;
-            }
-            float inv_sum = 1.f, mx = 0.f;
-            if (p.use_softmax) {
-                mx = -INFINITY;
-                for (int t = lane; t < len; t += 32) mx = fmaxf(mx, sm.score[r0 + t] * inv_sqrt_d);
-                mx = warp_max(mx);
-                float sum = 0.f;
-                for (int t = lane; t < len; t += 32) sum += expf(sm.score[r0 + t] * inv_sqrt_d - mx);
-                inv_sum = 1.0f / warp_sum(sum);
-            }
-            for (int t = lane; t < T; t += 32) {
-                float w = 0.f;
-                if (t < len) {
-                    w = p.use_softmax ? expf(sm.score[r0 + t] * inv_sqrt_d - mx) * inv_sum : sm.score[r0 + t];
-                    sm.wt[r0 + t] = w;
-                }
-                wrow[t] = w;
-            }
-        }
-        __syncthreads();
-        {
-            const float w = on ? sm.wt[tid] : 0.f;
-#pragma unroll
-            for (int e = 0; e < 16; ++e) sm.pool[tid * 17 + e] = w * k[e];
-        }
-        __syncthreads();
-        for (int item = tid; item < (s_end - s_begin) * 16; item += kTcThreads) {
-            const int s = s_begin + (item >> 4), e = item & 15;
-            const int len = sm.len[s], r0 = sm.start[s - s_begin];
-            float a = 0.f;
-            if (len > 0) {
-                for (int t = 0; t < len; ++t) a += sm.pool[(r0 + t) * 17 + e];
-            } else if (p.use_softmax) {      // uniform 1/T over ALL positions (they hold the padding score)
-                const float u = 1.0f / (float)T;
-                for (int t = 0; t < T; ++t) {
-                    const int64_t row = checked_row(__ldg(p.his_idx + (b0 + s) * T + t), p.his_rows, err_flag);
-                    a = fmaf(u, __ldg(p.his_w + row * D + e), a);
-                }
-            }
-            sm.att[s * 16 + e] = a;
-        }
-        __syncthreads();
-        s_begin = s_end;
-    }
-
-    // ---- assemble the concat row and the L2 norm: one warp per sample
-    for (int s = warp; s < n_samples; s += kTcThreads / 32) {
-        const int64_t b = b0 + s;
-        float* out = concat_all + b * p.width;
-        float ss = 0.f;
-        for (int c = lane; c < p.width; c += 32) {
-            float v;
-            if (c < p.n_dense) {
-                v = __ldg(p.dense_col[c] + b * p.dense_stride);
-            } else if (c >= p.att_off && c < p.att_off + D) {
-                v = sm.att[s * 16 + c - p.att_off];
-            } else if (c >= p.tgt_off && c < p.tgt_off + D) {
-                v = sm.q[s * D + c - p.tgt_off];
-            } else {
-                v = 0.f;
-                for (int f = 0; f < p.cat.F; ++f)
-                    if (c >= p.cat.off[f] && c < p.cat.off[f] + p.cat.dim[f]) {
-                        const int64_t row = checked_row(__ldg(p.cat.idx[f] + b), p.cat.rows[f], err_flag);
-                        v = __ldg(p.cat.weight[f] + row * p.cat.dim[f] + c - p.cat.off[f]);
+                    for (int j = 0; j < 8; ++j) {
+                        a[j] = qv[8 * half + j];
+                        b[j] = k[8 * half + j];
+                        c[j] = a[j] - b[j];
+                        d[j] = a[j] * b[j];
                     }
+                    store_chunk_split(sm.a, sm.a_lo, tid, 0 + half, a);
+                    store_chunk_split(sm.a, sm.a_lo, tid, 2 + half, b);
+                    store_chunk_split(sm.a, sm.a_lo, tid, 4 + half, c);
+                    store_chunk_split(sm.a, sm.a_lo, tid, 6 + half, d);
+                }
+                if (tid == 0) group_slot = next_draw;
+                fence_async_smem();
+                fence_before();
+                __syncthreads();
+                if (tid == 0) {                          // layer 1 on the tensor core
+                    PROF(3);
+                    fence_after();
+#pragma unroll
+                    for (int term = 0; term < 3; ++term)   // hi.hi + lo.hi + hi.lo
+#pragma unroll
+                        for (int kk = 0; kk < 4; ++kk)     // K = 64 = 4 x 16; +32 B per step inside the swizzle atom
+                            umma_bf16(tmem, a_desc[term == 1] + 2 * kk, w1_desc[term == 2] + 2 * kk, umma_idesc(64),
+                                      (term | kk) > 0);
+                    umma_commit(sm.bar_mma);
+                }
+                shadow_work();
+                mbar_wait(sm.bar_mma, ph_mma);
+                ph_mma ^= 1;
+                fence_after();
+                uint32_t m1a = 0, m1b = 0;
+                PROF(4);
+#pragma unroll
+                for (int half = 0; half < 2; ++half) {
+                    float v[32];
+                    tmem_ld32(my_tmem + 32 * half, v);
+                    uint32_t bits = 0;
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) {
+                        v[j] = fmaxf(v[j] + b1[32 * half + j], 0.f);
+                        bits |= (v[j] > 0.f ? 1u : 0u) << j;
+                    }
+                    if (half == 0) m1a = bits; else m1b = bits;
+#pragma unroll
+                    for (int c = 0; c < 4; ++c) {
+                        float h8[8];
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) h8[j] = v[8 * c + j];
+                        store_chunk_split(sm.a, sm.a_lo, tid, 4 * half + c, h8);   // A2 = relu(layer 1), in place
+                    }
+                }
+                fence_async_smem();
+                fence_before();
+                __syncthreads();
+                if (tid == 0) {                          // layer 2 on the tensor core
+                    PROF(5);
+                    fence_after();
+#pragma unroll
+                    for (int term = 0; term < 3; ++term)
+#pragma unroll
+                        for (int kk = 0; kk < 4; ++kk)
+                            umma_bf16(tmem + 64, a_desc[term == 1] + 2 * kk, w2_desc[term == 2] + 2 * kk,
+                                      umma_idesc(32), (term | kk) > 0);
+                    umma_commit(sm.bar_mma);
+                }
+                mbar_wait(sm.bar_mma, ph_mma);
+                ph_mma ^= 1;
+                fence_after();
+                {
+                    PROF(6);
+                    float v[32];
+                    tmem_ld32(my_tmem + 64, v);
+                    float sc = b3;
+                    uint32_t m2 = 0;
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) {
+                        const float h = fmaxf(v[j] + b2[j], 0.f);
+                        m2 |= (h > 0.f ? 1u : 0u) << j;
+                        sc = fmaf(h, w3[j], sc);
+                    }
+                    sm.score[tid] = sc;
+                    if (cur.on && masks) {
+                        uint32_t* mk = masks + ((b0 + cur.my_s) * T + cur.my_t) * 3;
+                        mk[0] = m1a; mk[1] = m1b; mk[2] = m2;
+                    }
+                }
+                fence_before();
+                __syncthreads();
+            } else {                                     // a tile of empty histories: nothing for the tensor core
+                if (tid == 0) group_slot = next_draw;
+                __syncthreads();
+                shadow_work();
             }
-            out[c] = v;
-            if (c >= p.l2_from) ss = fmaf(v, v, ss);
+            PROF(7);
+            // ---- attention weights per sample (warp per sample), then weighted pooling through smem
+            for (int s = s_begin + warp; s < cur.s_end; s += kTcThreads / 32) {
+                const int len = sm.len[s], r0 = tile_row0(sm.len, s_begin, s);
+                float* wrow = att_w + (b0 + s) * T;
+                if (len == 0) {
+                    const float u = p.use_softmax ? 1.0f / (float)T : 0.f;
+                    for (int t = lane; t < T; t += 32) wrow[t] = u;
+                    continue;
+                }
+                float inv_sum = 1.f, mx = 0.f;
+                if (p.use_softmax) {
+                    mx = -INFINITY;
+                    for (int t = lane; t < len; t += 32) mx = fmaxf(mx, sm.score[r0 + t] * inv_sqrt_d);
+                    mx = warp_max(mx);
+                    float sum = 0.f;
+                    for (int t = lane; t < len; t += 32) sum += expf(sm.score[r0 + t] * inv_sqrt_d - mx);
+                    inv_sum = 1.0f / warp_sum(sum);
+                }
+                for (int t = lane; t < T; t += 32) {
+                    float w = 0.f;
+                    if (t < len) {
+                        w = p.use_softmax ? expf(sm.score[r0 + t] * inv_sqrt_d - mx) * inv_sum : sm.score[r0 + t];
+                        sm.wt[r0 + t] = w;
+                    }
+                    wrow[t] = w;
+                }
+            }
+            __syncthreads();
+            PROF(8);
+            {
+                const float w = cur.on ? sm.wt[tid] : 0.f;
+#pragma unroll
+                for (int e = 0; e < 16; ++e) pool[tid * 17 + e] = w * k[e];
+            }
+            __syncthreads();
+            for (int item = tid; item < (cur.s_end - s_begin) * 16; item += kTcThreads) {
+                const int s = s_begin + (item >> 4), e = item & 15;
+                const int len = sm.len[s], r0 = tile_row0(sm.len, s_begin, s);
+                float a = 0.f;
+                if (len > 0) {
+                    for (int t = 0; t < len; ++t) a += pool[(r0 + t) * 17 + e];
+                } else if (p.use_softmax) {      // uniform 1/T over ALL positions (they hold the padding score)
+                    const float u = 1.0f / (float)T;
+                    for (int t = 0; t < T; ++t) {
+                        const int64_t row = checked_row(__ldg(p.his_idx + (b0 + s) * T + t), p.his_rows, err_flag);
+                        a = fmaf(u, __ldg(p.his_w + row * D + e), a);
+                    }
+                }
+                sm.att[s * 16 + e] = a;
+            }
+            __syncthreads();
+            s_begin = cur.s_end;
+            cur = nxt;
+            PROF(9);
         }
-        ss = warp_sum(ss);
-        if (lane == 0 && norm_out) norm_out[b] = sqrtf(ss);
+
+        // ---- the attention output columns and the L2 norm of the finished rows
+#pragma unroll
+        for (int slot = 0; slot < kSlots; ++slot) {
+            const int s = warp + 4 * slot;
+            if (s >= n_samples) continue;
+            const int64_t b = b0 + s;
+            float ss = ss_part[slot];
+            {                                    // lanes 0..15: attention output, 16..31: target row
+                const int e = lane & 15;
+                const int c = (lane < D ? p.att_off : p.tgt_off) + e;
+                const float x = lane < D ? sm.att[s * 16 + e] : sm.q[s * D + e];
+                concat_all[b * p.width + c] = x;
+                if (c >= p.l2_from) ss = fmaf(x, x, ss);
+            }
+            ss = warp_sum(ss);
+            if (lane == 0 && norm_out) norm_out[b] = sqrtf(ss);
+        }
+        __syncthreads();      // q / len / att are rewritten by the next group
+        group = (int64_t)group_slot;     // rewritten only after the next group's first barrier
+        PROF(10);
     }
-    __syncthreads();      // q / len / att are rewritten by the next group
-  }
     scheduler_exit(0);
+    PROF_END;
     fence_before();
     __syncthreads();
     if (warp == 0) tmem_dealloc(tmem, kTcTmemCols);
@@ -1275,16 +1462,20 @@ int rk_din_fwd(const rk_din_args_t* args, float* concat_all, float* norm, float*
     const int grid = (int)ceil_div(p.B, kSamples);
     if (args->precision == RK_DIN_BF16_TENSOR) {
         RK_CHECK_ARG(p.D == 16, "din_fwd: the tensor-core activation unit is built for D = 16 (got %d)", p.D);
-        const size_t smem_tc = tc::TcSmem::bytes(32);
-        RK_CUDA(cudaFuncSetAttribute(tc::din_fwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                     (int)smem_tc));
-        // Persistent CTAs drawing groups of 8 samples from a device-side counter: static striding was
+        const size_t smem_tc = tc::TcFwdSmem::bytes(p.width, p.T, p.cat.F);
+        static const int per_sm = [] {
+            const char* e = getenv("RANK_B200_DIN_TC_CTAS_PER_SM");
+            const int v = e ? atoi(e) : 0;
+            return v >= 1 && v <= 4 ? v : 3;
+        }();
+        auto kernel = tc::din_fwd_tc_kernel;
+        RK_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_tc));
+        // Persistent CTAs drawing groups of samples from a device-side counter: static striding was
         // measured slower than one CTA per group (158 vs 101 us) because group work varies with the
         // history lengths; dynamic draws keep the balance and pay the per-CTA setup once.
-        // up to 4 CTAs per SM fit the TMEM budget (4 x 128 columns); CTAs that do not become resident
-        // simply find the scheduler empty when they start
-        const int grid_tc = grid < sm_count() * 4 ? grid : sm_count() * 4;
-        tc::din_fwd_tc_kernel<<<grid_tc, tc::kTcThreads, smem_tc, (cudaStream_t)stream_>>>(
+        const int n_groups = (int)ceil_div(p.B, tc::kTcGroup);
+        const int grid_tc = n_groups < sm_count() * per_sm ? n_groups : sm_count() * per_sm;
+        kernel<<<grid_tc, tc::kTcThreads, smem_tc, (cudaStream_t)stream_>>>(
             p, concat_all, norm, att_w, relu_masks, err_flag);
         RK_LAUNCH_CHECK();
         return 0;
@@ -1331,3 +1522,15 @@ int rk_din_bwd(const rk_din_args_t* args, const float* concat_all, const float* 
 }
 
 }  // extern "C"
+
+#ifdef RK_DIN_PROFILE
+extern "C" int rk_debug_din_profile(unsigned long long* out16, int reset) {
+    RK_CUDA(cudaDeviceSynchronize());
+    RK_CUDA(cudaMemcpyFromSymbol(out16, rk::tc::g_din_prof, sizeof(unsigned long long) * 16));
+    if (reset) {
+        unsigned long long z[16] = {0};
+        RK_CUDA(cudaMemcpyToSymbol(rk::tc::g_din_prof, z, sizeof(z)));
+    }
+    return 0;
+}
+#endif
