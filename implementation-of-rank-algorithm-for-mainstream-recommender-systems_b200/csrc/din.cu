@@ -659,43 +659,6 @@ __device__ __forceinline__ void scheduler_exit(int which) {
     }
 }
 
-struct TcSmem {
-    uint8_t *a, *a_lo, *w1, *w1_lo, *w2, *w2_lo;   // swizzled bf16 tiles: [128][64], [64][64], [<=64][64], hi + lo
-    float *vec, *q, *att, *gq, *dot, *score, *wt, *pool;
-    int *row_s, *row_t, *len, *start;
-    uint64_t* bar;
-    uint32_t* tmem_slot;
-    // w2_rows: rows of the second weight tile (32 for W2 in forward, 64 for W2^T in backward)
-    __device__ TcSmem(uint8_t* base, int w2_rows) {
-        uint8_t* p = base;
-        a = p;      p += 128 * 128;
-        a_lo = p;   p += 128 * 128;
-        w1 = p;     p += 64 * 128;
-        w1_lo = p;  p += 64 * 128;
-        w2 = p;     p += w2_rows * 128;
-        w2_lo = p;  p += w2_rows * 128;
-        vec = (float*)p;    p += sizeof(float) * (kH1 + 2 * kH2 + 4);
-        q = (float*)p;      p += sizeof(float) * kSamples * 16;
-        att = (float*)p;    p += sizeof(float) * kSamples * 16;
-        gq = (float*)p;     p += sizeof(float) * kSamples * 16;
-        dot = (float*)p;    p += sizeof(float) * 8;
-        score = (float*)p;  p += sizeof(float) * kRows;
-        wt = (float*)p;     p += sizeof(float) * kRows;
-        pool = (float*)p;   p += sizeof(float) * kRows * 17;
-        row_s = (int*)p;    p += sizeof(int) * kRows;
-        row_t = (int*)p;    p += sizeof(int) * kRows;
-        len = (int*)p;      p += sizeof(int) * kSamples;
-        start = (int*)p;    p += sizeof(int) * (kSamples + 4);
-        bar = (uint64_t*)p; p += 8;
-        tmem_slot = (uint32_t*)p;
-    }
-    static size_t bytes(int w2_rows) {
-        return 1024 /* alignment slack */ + 2 * (128 * 128 + 64 * 128 + (size_t)w2_rows * 128) +
-               sizeof(float) * (kH1 + 2 * kH2 + 4 + 3 * kSamples * 16 + 8 + 2 * kRows + kRows * 17) +
-               sizeof(int) * (2 * kRows + 2 * kSamples + 4) + 16;
-    }
-};
-
 // ---- forward -------------------------------------------------------------------------------
 constexpr int kTcGroup = kSamples;   // samples per scheduler draw (16 was measured slower: 93 vs 82 us)
 
@@ -953,6 +916,29 @@ din_fwd_tc_kernel(const __grid_constant__ DinParams p, float* __restrict__ conca
                     }
                 }
         }
+        // Softmax over an empty history: every position holds the padding score, so the weights are
+        // uniform 1/T over ALL T positions.  One warp per such sample, lanes = (16-byte chunk, t mod 8).
+        if (p.use_softmax) {
+            const float u = 1.0f / (float)T;
+            for (int s = warp; s < n_samples; s += kTcThreads / 32) {
+                if (sm.len[s] != 0) continue;
+                const int c4 = lane & 3;
+                float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll 4
+                for (int t = lane >> 2; t < T; t += 8) {
+                    const int64_t row = checked_row(sm.ix_his[s * T + t], p.his_rows, err_flag);
+                    const float4 v = __ldg(reinterpret_cast<const float4*>(p.his_w + row * D) + c4);
+                    acc.x = fmaf(u, v.x, acc.x); acc.y = fmaf(u, v.y, acc.y);
+                    acc.z = fmaf(u, v.z, acc.z); acc.w = fmaf(u, v.w, acc.w);
+                }
+#pragma unroll
+                for (int o = 4; o < 32; o <<= 1) {
+                    acc.x += __shfl_xor_sync(kFull, acc.x, o); acc.y += __shfl_xor_sync(kFull, acc.y, o);
+                    acc.z += __shfl_xor_sync(kFull, acc.z, o); acc.w += __shfl_xor_sync(kFull, acc.w, o);
+                }
+                if (lane < 4) *reinterpret_cast<float4*>(sm.att + s * 16 + 4 * c4) = acc;
+            }
+        }
         while (s_begin < n_samples) {
             // ---- the tile's history rows have landed in shared memory
             wait_rows();
@@ -1122,16 +1108,8 @@ din_fwd_tc_kernel(const __grid_constant__ DinParams p, float* __restrict__ conca
                 const int s = s_begin + (item >> 4), e = item & 15;
                 const int len = sm.len[s], r0 = tile_row0(sm.len, s_begin, s);
                 float a = 0.f;
-                if (len > 0) {
-                    for (int t = 0; t < len; ++t) a += pool[(r0 + t) * 17 + e];
-                } else if (p.use_softmax) {      // uniform 1/T over ALL positions (they hold the padding score)
-                    const float u = 1.0f / (float)T;
-                    for (int t = 0; t < T; ++t) {
-                        const int64_t row = checked_row(__ldg(p.his_idx + (b0 + s) * T + t), p.his_rows, err_flag);
-                        a = fmaf(u, __ldg(p.his_w + row * D + e), a);
-                    }
-                }
-                sm.att[s * 16 + e] = a;
+                for (int t = 0; t < len; ++t) a += pool[(r0 + t) * 17 + e];
+                if (len > 0 || !p.use_softmax) sm.att[s * 16 + e] = a;     // (softmax, no history): set at group start
             }
             __syncthreads();
             s_begin = cur.s_end;
@@ -1167,6 +1145,96 @@ din_fwd_tc_kernel(const __grid_constant__ DinParams p, float* __restrict__ conca
     if (warp == 0) tmem_dealloc(tmem, kTcTmemCols);
 }
 
+// ---- backward ------------------------------------------------------------------------------
+struct TcBwdSmem {
+    uint8_t *a, *a_lo, *w1, *w1_lo, *w2, *w2_lo;   // w1 = W1^T, w2 = W2^T (64 rows each); a_lo doubles as pooling scratch
+    float *kstage;                                 // [128][16] history rows landed by cp.async
+    float *vec, *q, *att, *gq, *gt, *dot, *score, *wt;
+    float *ca, *gc;                                // the group's concat_all / g_concat rows [8][width]
+    float *attw;                                   // the group's attention weights [8][T]
+    uint32_t* mask;                                // the group's ReLU masks [8][T][3]
+    float *nrm, *gnrm;                             // [8]
+    int64_t *ix_his, *ix_len;
+    int* len;
+    uint64_t* bar;
+    uint32_t* tmem_slot;
+    static __host__ __device__ size_t pad16(size_t n) { return (n + 15) & ~(size_t)15; }
+    __device__ TcBwdSmem(uint8_t* base, int T, int width) {
+        uint8_t* p = base;
+        a = p;       p += 128 * 128;
+        a_lo = p;    p += 128 * 128;
+        w1 = p;      p += 64 * 128;
+        w1_lo = p;   p += 64 * 128;
+        w2 = p;      p += 64 * 128;
+        w2_lo = p;   p += 64 * 128;
+        kstage = (float*)p;   p += sizeof(float) * kRows * 16;
+        ca = (float*)p;       p += pad16(sizeof(float) * kSamples * width);
+        gc = (float*)p;       p += pad16(sizeof(float) * kSamples * width);
+        attw = (float*)p;     p += pad16(sizeof(float) * kSamples * T);
+        mask = (uint32_t*)p;  p += pad16(sizeof(uint32_t) * kSamples * T * 3);
+        ix_his = (int64_t*)p; p += pad16(sizeof(int64_t) * kSamples * T);
+        ix_len = (int64_t*)p; p += sizeof(int64_t) * kSamples;
+        nrm = (float*)p;      p += sizeof(float) * kSamples;
+        gnrm = (float*)p;     p += sizeof(float) * kSamples;
+        vec = (float*)p;      p += sizeof(float) * kH2;
+        q = (float*)p;        p += sizeof(float) * kSamples * 16;
+        att = (float*)p;      p += sizeof(float) * kSamples * 16;
+        gq = (float*)p;       p += sizeof(float) * kSamples * 16;
+        gt = (float*)p;       p += sizeof(float) * kSamples * 16;
+        dot = (float*)p;      p += sizeof(float) * 8;
+        score = (float*)p;    p += sizeof(float) * kRows;
+        wt = (float*)p;       p += sizeof(float) * kRows;
+        len = (int*)p;        p += sizeof(int) * kSamples;
+        bar = (uint64_t*)p;   p += 8;
+        tmem_slot = (uint32_t*)p;
+    }
+    static size_t bytes(int T, int width) {
+        return 1024 /* alignment slack */ + 2 * (128 * 128 + 2 * 64 * 128) + sizeof(float) * kRows * 16 +
+               2 * pad16(sizeof(float) * kSamples * width) + pad16(sizeof(float) * kSamples * T) +
+               pad16(sizeof(uint32_t) * kSamples * T * 3) + pad16(sizeof(int64_t) * kSamples * T) +
+               sizeof(int64_t) * kSamples + sizeof(float) * (2 * kSamples + kH2 + 4 * kSamples * 16 + 8 + 2 * kRows) +
+               sizeof(int) * kSamples + 16;
+    }
+};
+
+// n 4-byte words, global -> shared, asynchronously: 16-byte copies when the block allows it.
+__device__ __forceinline__ void copy_words_async(void* dst_smem, const void* src, int n, int tid) {
+    const uint32_t dst = smem_u32(dst_smem);
+    const char* s = reinterpret_cast<const char*>(src);
+    if ((n & 3) == 0 && (reinterpret_cast<uintptr_t>(src) & 15) == 0) {
+        for (int i = tid; i < (n >> 2); i += kTcThreads)
+            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst + 16 * i), "l"(s + 16 * (size_t)i) : "memory");
+    } else {
+        for (int i = tid; i < n; i += kTcThreads)
+            asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(dst + 4 * i), "l"(s + 4 * (size_t)i) : "memory");
+    }
+}
+
+// Everything the backward of a group reads that does not depend on an index: issued one group ahead.
+__device__ __forceinline__ void issue_group_bwd(const DinParams& p, const TcBwdSmem& sm, int64_t group, int tid,
+                                                const float* concat_all, const float* norm, const float* att_w,
+                                                const uint32_t* masks, const float* g_concat, const float* g_norm) {
+    const int64_t b0 = group * kSamples;
+    const int n = (int)((p.B - b0) < kSamples ? (p.B - b0) : kSamples);
+    copy_words_async(sm.ix_his, p.his_idx + b0 * p.T, 2 * n * p.T, tid);
+    copy_words_async(sm.attw, att_w + b0 * p.T, n * p.T, tid);
+    copy_words_async(sm.mask, masks + b0 * p.T * 3, 3 * n * p.T, tid);
+    copy_words_async(sm.ca, concat_all + b0 * p.width, n * p.width, tid);
+    if (g_concat) copy_words_async(sm.gc, g_concat + b0 * p.width, n * p.width, tid);
+    else for (int i = tid; i < n * p.width; i += kTcThreads) sm.gc[i] = 0.f;
+    if (tid < n) {
+        cp_async8(sm.ix_len + tid, p.his_len + b0 + tid);
+        if (g_norm) {
+            asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(smem_u32(sm.nrm + tid)), "l"(norm + b0 + tid) : "memory");
+            asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(smem_u32(sm.gnrm + tid)), "l"(g_norm + b0 + tid) : "memory");
+        } else {
+            sm.nrm[tid] = 0.f;
+            sm.gnrm[tid] = 0.f;
+        }
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+}
+
 // Tensor-core backward (D = 16): g_score -> (x W2) -> relu' -> (x W1) -> g_cross on tcgen05 with
 // split-bf16 operands; B operands are the transposed weights of the pack (W2^T [64][32] and
 // W1^T [64][64], both K-major for these products).  Same outputs as din_bwd_kernel.
@@ -1178,12 +1246,16 @@ din_bwd_tc_kernel(const __grid_constant__ DinParams p, const float* __restrict__
                   float* __restrict__ g_hist, int32_t* err_flag) {
     extern __shared__ uint8_t smem_raw_tc[];
     uint8_t* base = smem_raw_tc + ((1024u - (smem_u32(smem_raw_tc) & 1023u)) & 1023u);
-    TcSmem sm(base, 64);
+    TcBwdSmem sm(base, p.T, p.width);
     constexpr int D = 16;
-    const int T = p.T;
+    const int T = p.T, W = p.width;
     const MlpLayout L(D);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int64_t n_groups = (p.B + kSamples - 1) / kSamples;
+
+    // first group static (the grid never exceeds the group count); its inputs fly during the set-up
+    int64_t group = blockIdx.x;
+    issue_group_bwd(p, sm, group, tid, concat_all, norm, att_w, masks, g_concat, g_norm);
 
     if (tid == 0) mbar_init(sm.bar, 1);
     if (warp == 0) tmem_alloc(sm.tmem_slot, kTcTmemCols);
@@ -1210,196 +1282,219 @@ din_bwd_tc_kernel(const __grid_constant__ DinParams p, const float* __restrict__
     const uint64_t w1_desc[2] = {umma_desc(smem_u32(sm.w1)), umma_desc(smem_u32(sm.w1_lo))};
     const uint64_t w2_desc[2] = {umma_desc(smem_u32(sm.w2)), umma_desc(smem_u32(sm.w2_lo))};
     const uint32_t my_tmem = tmem + ((uint32_t)(warp * 32) << 16);
+    float* pool = reinterpret_cast<float*>(sm.a_lo);     // [128][17], free once the second MMA has read a_lo
     uint32_t phase = 0;
 
-  __shared__ unsigned int group_slot;
-  for (;;) {                                       // persistent: groups drawn from the scheduler
-    const int64_t group = next_group(1, &group_slot);
-    if (group >= n_groups) break;
-    const int64_t b0 = group * kSamples;
-    const int n_samples = (int)((p.B - b0) < kSamples ? (p.B - b0) : kSamples);
-    if (tid < kSamples) sm.len[tid] = tid < n_samples ? clip_len(__ldg(p.his_len + b0 + tid), T) : 0;
-    for (int i = tid; i < n_samples * D; i += kTcThreads) {
-        const int s = i / D, e = i - s * D;
-        const int64_t b = b0 + s;
-        sm.q[i] = concat_all[b * p.width + p.tgt_off + e];
-        float g = g_concat ? g_concat[b * p.width + p.att_off + e] : 0.f;
-        if (g_norm) {
-            const float nv = norm[b];
-            if (nv > 0.f) g = fmaf(g_norm[b] / nv, concat_all[b * p.width + p.att_off + e], g);
+    __shared__ unsigned int group_slot;
+    while (group < n_groups) {                       // persistent: groups of 8 samples
+        unsigned int next_draw = 0;                  // drawn now, published at a tile barrier, used by the last tile
+        if (tid == 0) next_draw = gridDim.x + atomicAdd(&g_din_next[1], 1u);
+        const int64_t b0 = group * kSamples;
+        const int n_samples = (int)((p.B - b0) < kSamples ? (p.B - b0) : kSamples);
+        wait_rows();                                 // the group's inputs (issue_group_bwd) have landed ...
+        __syncthreads();                             // ... for every thread
+        if (tid < kSamples) sm.len[tid] = tid < n_samples ? clip_len(sm.ix_len[tid], T) : 0;
+        for (int i = tid; i < n_samples * D; i += kTcThreads) {
+            const int s = i / D, e = i - s * D;
+            sm.q[i] = sm.ca[s * W + p.tgt_off + e];
+            const float nv = sm.nrm[s];
+            const float scale = nv > 0.f ? sm.gnrm[s] / nv : 0.f;
+            sm.att[i] = fmaf(scale, sm.ca[s * W + p.att_off + e], sm.gc[s * W + p.att_off + e]);   // g_att
+            sm.gq[i]  = 0.f;
         }
-        sm.att[i] = g;          // g_att: upstream gradient of the attention output
-        sm.gq[i]  = 0.f;
-    }
-    __syncthreads();
-
-    int s_begin = 0;
-    while (s_begin < n_samples) {
-        int s_end, n_rows = 0;
-        {
-            int s = s_begin;
-            while (s < n_samples && n_rows + sm.len[s] <= kRows) { n_rows += sm.len[s]; ++s; }
-            s_end = s;
-        }
-        if (tid < kSamples + 1) {
-            int acc = 0;
-            for (int s = s_begin; s < s_begin + tid && s < s_end; ++s) acc += sm.len[s];
-            sm.start[tid] = acc;
+        // g_row of every column but the target's (those wait for g_q): smem -> coalesced stores
+        for (int i = tid; i < n_samples * W; i += kTcThreads) {
+            const int s = i / W, c = i - s * W;
+            const float nv = sm.nrm[s];
+            const float scale = nv > 0.f ? sm.gnrm[s] / nv : 0.f;
+            float g = sm.gc[i];
+            if (c >= p.l2_from) g = fmaf(scale, sm.ca[i], g);
+            if (c >= p.tgt_off && c < p.tgt_off + D) sm.gt[s * D + c - p.tgt_off] = g;
+            else g_row[b0 * W + i] = g;
         }
         __syncthreads();
-        int my_s = s_begin;
-        while (my_s + 1 < s_end && tid >= sm.start[my_s + 1 - s_begin]) ++my_s;
-        const int  my_t = tid - sm.start[my_s - s_begin];
-        const bool on = tid < n_rows;
-        if (n_rows > 0) {
-            float k[16], gatt[16];
-            float w = 0.f, gw = 0.f;
-            uint32_t m1a = 0, m1b = 0, m2 = 0;
-#pragma unroll
-            for (int e = 0; e < 16; ++e) { k[e] = 0.f; gatt[e] = 0.f; }
-            if (on) {
-                const int64_t row = checked_row(__ldg(p.his_idx + (b0 + my_s) * T + my_t), p.his_rows, err_flag);
-                const float4* src = reinterpret_cast<const float4*>(p.his_w + row * D);
-#pragma unroll
-                for (int c = 0; c < 4; ++c) {
-                    const float4 v = __ldg(src + c);
-                    k[4 * c] = v.x; k[4 * c + 1] = v.y; k[4 * c + 2] = v.z; k[4 * c + 3] = v.w;
-                }
-#pragma unroll
-                for (int e = 0; e < 16; ++e) { gatt[e] = sm.att[my_s * D + e]; gw = fmaf(gatt[e], k[e], gw); }
-                w = att_w[(b0 + my_s) * T + my_t];
-                const uint32_t* mk = masks + ((b0 + my_s) * T + my_t) * 3;
-                m1a = mk[0]; m1b = mk[1]; m2 = mk[2];
-            }
-            if (p.use_softmax) {          // g_s = w (g_w - sum_u w_u g_w_u) / sqrt(D)
-                sm.wt[tid] = w;
-                sm.score[tid] = gw;
-                __syncthreads();
-                for (int s = s_begin + warp; s < s_end; s += kTcThreads / 32) {
-                    const int len = sm.len[s], r0 = sm.start[s - s_begin];
-                    float dsum = 0.f;
-                    for (int t = lane; t < len; t += 32) dsum = fmaf(sm.wt[r0 + t], sm.score[r0 + t], dsum);
-                    dsum = warp_sum(dsum);
-                    if (lane == 0) sm.dot[s] = dsum;
-                }
-                __syncthreads();
-                gw = w * (gw - sm.dot[my_s]) * 0.25f;
-            }
-            if (!on) gw = 0.f;
-            // ---- A = g_z2 [128 x 32]
-#pragma unroll
-            for (int c = 0; c < 4; ++c) {
-                float v[8];
-#pragma unroll
-                for (int j = 0; j < 8; ++j) v[j] = ((m2 >> (8 * c + j)) & 1u) ? gw * w3[8 * c + j] : 0.f;
-                store_chunk_split(sm.a, sm.a_lo, tid, c, v);
-            }
-            fence_async_smem();
-            fence_before();
-            __syncthreads();
-            if (tid == 0) {
-                fence_after();
-#pragma unroll
-                for (int term = 0; term < 3; ++term)
-#pragma unroll
-                    for (int kk = 0; kk < 2; ++kk)     // K = 32
-                        umma_bf16(tmem, a_desc[term == 1] + 2 * kk, w2_desc[term == 2] + 2 * kk, umma_idesc(64),
-                                  (term | kk) > 0);
-                umma_commit(sm.bar);
-            }
-            mbar_wait(sm.bar, phase);
-            phase ^= 1;
-            fence_after();
-            // ---- g_z1 = (g_z2 x W2) * relu1'  -> A [128 x 64]
-#pragma unroll
-            for (int half = 0; half < 2; ++half) {
-                float v[32];
-                tmem_ld32(my_tmem + 32 * half, v);
-                const uint32_t bits = half == 0 ? m1a : m1b;
-#pragma unroll
-                for (int c = 0; c < 4; ++c) {
-                    float h8[8];
-#pragma unroll
-                    for (int j = 0; j < 8; ++j) h8[j] = ((bits >> (8 * c + j)) & 1u) ? v[8 * c + j] : 0.f;
-                    store_chunk_split(sm.a, sm.a_lo, tid, 4 * half + c, h8);
-                }
-            }
-            fence_async_smem();
-            fence_before();
-            __syncthreads();
-            if (tid == 0) {
-                fence_after();
-#pragma unroll
-                for (int term = 0; term < 3; ++term)
-#pragma unroll
-                    for (int kk = 0; kk < 4; ++kk)     // K = 64
-                        umma_bf16(tmem + 64, a_desc[term == 1] + 2 * kk, w1_desc[term == 2] + 2 * kk, umma_idesc(64),
-                                  (term | kk) > 0);
-                umma_commit(sm.bar);
-            }
-            mbar_wait(sm.bar, phase);
-            phase ^= 1;
-            fence_after();
-            // ---- g_cross = [gc_q | gc_k | gc_d | gc_p] -> g_k row, and this row's share of g_q
-            float gk[16], gqr[16];
-            {
-                float v[32];
-                tmem_ld32(my_tmem + 64, v);
-#pragma unroll
-                for (int e = 0; e < 16; ++e) { gqr[e] = v[e]; gk[e] = fmaf(w, gatt[e], v[16 + e]); }
-                tmem_ld32(my_tmem + 96, v);
-#pragma unroll
-                for (int e = 0; e < 16; ++e) {
-                    const float qe = sm.q[my_s * D + e];
-                    gqr[e] += v[e] + v[16 + e] * k[e];
-                    gk[e]  += v[16 + e] * qe - v[e];
-                }
-            }
-            if (on) {
-                float4* dst = reinterpret_cast<float4*>(g_hist + ((b0 + my_s) * T + my_t) * D);
-#pragma unroll
-                for (int c = 0; c < 4; ++c) dst[c] = make_float4(gk[4 * c], gk[4 * c + 1], gk[4 * c + 2], gk[4 * c + 3]);
-            }
-#pragma unroll
-            for (int e = 0; e < 16; ++e) sm.pool[tid * 17 + e] = on ? gqr[e] : 0.f;
-            fence_before();
-            __syncthreads();
-            for (int item = tid; item < (s_end - s_begin) * 16; item += kTcThreads) {
-                const int s = s_begin + (item >> 4), e = item & 15;
-                const int len = sm.len[s], r0 = sm.start[s - s_begin];
-                float a = 0.f;
-                for (int t = 0; t < len; ++t) a += sm.pool[(r0 + t) * 17 + e];
-                sm.gq[s * 16 + e] = a;
-            }
-        }
-        if (p.use_softmax) {      // no history: uniform weights, gradient g_att / T on every position
-            for (int s = s_begin; s < s_end; ++s) {
-                if (sm.len[s] != 0) continue;
-                const float u = 1.0f / (float)T;
-                for (int i = tid; i < T * D; i += kTcThreads)
-                    g_hist[(b0 + s) * T * D + i] = u * sm.att[s * D + (i % D)];
-            }
-        }
-        __syncthreads();
-        s_begin = s_end;
-    }
 
-    for (int s = warp; s < n_samples; s += kTcThreads / 32) {
-        const int64_t b = b0 + s;
-        float scale = 0.f;
-        if (g_norm) {
-            const float nv = norm[b];
-            scale = nv > 0.f ? g_norm[b] / nv : 0.f;
+        int s_begin = 0;
+        TcTile cur = plan_tile_tc(sm.len, n_samples, 0, tid);
+        {                                            // first tile of the group: exposed latency
+            if (cur.on) {
+                const int64_t row = checked_row(sm.ix_his[cur.my_s * T + cur.my_t], p.his_rows, err_flag);
+                const uint32_t dst = smem_u32(sm.kstage + tid * 16);
+#pragma unroll
+                for (int c = 0; c < 4; ++c)
+                    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst + 16 * c), "l"(p.his_w + row * 16 + 4 * c) : "memory");
+            }
+            asm volatile("cp.async.commit_group;" ::: "memory");
         }
-        for (int c = lane; c < p.width; c += 32) {
-            float g = g_concat ? g_concat[b * p.width + c] : 0.f;
-            if (c >= p.l2_from) g = fmaf(scale, concat_all[b * p.width + c], g);
-            if (c >= p.tgt_off && c < p.tgt_off + D) g += sm.gq[s * D + c - p.tgt_off];
-            g_row[b * p.width + c] = g;
+        while (s_begin < n_samples) {
+            wait_rows();
+            const bool on = cur.on;
+            const int my_s = cur.my_s, my_t = cur.my_t;
+            const bool has_next = cur.s_end < n_samples;
+            TcTile nxt = cur;
+            // issued while the tensor core works: the rows of the next tile or, on the last tile of the
+            // group, the inputs of the next group (everything staged was consumed before the barrier)
+            auto shadow_work = [&]() {
+                if (has_next) {
+                    nxt = plan_tile_tc(sm.len, n_samples, cur.s_end, tid);
+                    if (nxt.on) {
+                        const int64_t row = checked_row(sm.ix_his[nxt.my_s * T + nxt.my_t], p.his_rows, err_flag);
+                        const uint32_t dst = smem_u32(sm.kstage + tid * 16);
+#pragma unroll
+                        for (int c = 0; c < 4; ++c)
+                            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst + 16 * c), "l"(p.his_w + row * 16 + 4 * c) : "memory");
+                    }
+                    asm volatile("cp.async.commit_group;" ::: "memory");
+                } else if ((int64_t)group_slot < n_groups) {
+                    issue_group_bwd(p, sm, (int64_t)group_slot, tid, concat_all, norm, att_w, masks, g_concat, g_norm);
+                }
+            };
+            if (cur.n_rows > 0) {
+                float k[16], gatt[16];
+                float w = 0.f, gw = 0.f;
+                uint32_t m1a = 0, m1b = 0, m2 = 0;
+#pragma unroll
+                for (int e = 0; e < 16; ++e) { k[e] = 0.f; gatt[e] = 0.f; }
+                if (on) {
+#pragma unroll
+                    for (int c = 0; c < 4; ++c) {
+                        const float4 v = *reinterpret_cast<const float4*>(sm.kstage + tid * 16 + 4 * c);
+                        k[4 * c] = v.x; k[4 * c + 1] = v.y; k[4 * c + 2] = v.z; k[4 * c + 3] = v.w;
+                    }
+#pragma unroll
+                    for (int e = 0; e < 16; ++e) { gatt[e] = sm.att[my_s * D + e]; gw = fmaf(gatt[e], k[e], gw); }
+                    w = sm.attw[my_s * T + my_t];
+                    const uint32_t* mk = sm.mask + (my_s * T + my_t) * 3;
+                    m1a = mk[0]; m1b = mk[1]; m2 = mk[2];
+                }
+                if (p.use_softmax) {          // g_s = w (g_w - sum_u w_u g_w_u) / sqrt(D)
+                    sm.wt[tid] = w;
+                    sm.score[tid] = gw;
+                    __syncthreads();
+                    for (int s = s_begin + warp; s < cur.s_end; s += kTcThreads / 32) {
+                        const int len = sm.len[s], r0 = tile_row0(sm.len, s_begin, s);
+                        float dsum = 0.f;
+                        for (int t = lane; t < len; t += 32) dsum = fmaf(sm.wt[r0 + t], sm.score[r0 + t], dsum);
+                        dsum = warp_sum(dsum);
+                        if (lane == 0) sm.dot[s] = dsum;
+                    }
+                    __syncthreads();
+                    gw = w * (gw - sm.dot[my_s]) * 0.25f;
+                }
+                if (!on) gw = 0.f;
+                // ---- A = g_z2 [128 x 32]
+#pragma unroll
+                for (int c = 0; c < 4; ++c) {
+                    float v[8];
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) v[j] = ((m2 >> (8 * c + j)) & 1u) ? gw * w3[8 * c + j] : 0.f;
+                    store_chunk_split(sm.a, sm.a_lo, tid, c, v);
+                }
+                if (tid == 0) group_slot = next_draw;
+                fence_async_smem();
+                fence_before();
+                __syncthreads();
+                if (tid == 0) {
+                    fence_after();
+#pragma unroll
+                    for (int term = 0; term < 3; ++term)
+#pragma unroll
+                        for (int kk = 0; kk < 2; ++kk)     // K = 32
+                            umma_bf16(tmem, a_desc[term == 1] + 2 * kk, w2_desc[term == 2] + 2 * kk, umma_idesc(64),
+                                      (term | kk) > 0);
+                    umma_commit(sm.bar);
+                }
+                shadow_work();
+                mbar_wait(sm.bar, phase);
+                phase ^= 1;
+                fence_after();
+                // ---- g_z1 = (g_z2 x W2) * relu1'  -> A [128 x 64]
+#pragma unroll
+                for (int half = 0; half < 2; ++half) {
+                    float v[32];
+                    tmem_ld32(my_tmem + 32 * half, v);
+                    const uint32_t bits = half == 0 ? m1a : m1b;
+#pragma unroll
+                    for (int c = 0; c < 4; ++c) {
+                        float h8[8];
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) h8[j] = ((bits >> (8 * c + j)) & 1u) ? v[8 * c + j] : 0.f;
+                        store_chunk_split(sm.a, sm.a_lo, tid, 4 * half + c, h8);
+                    }
+                }
+                fence_async_smem();
+                fence_before();
+                __syncthreads();
+                if (tid == 0) {
+                    fence_after();
+#pragma unroll
+                    for (int term = 0; term < 3; ++term)
+#pragma unroll
+                        for (int kk = 0; kk < 4; ++kk)     // K = 64
+                            umma_bf16(tmem + 64, a_desc[term == 1] + 2 * kk, w1_desc[term == 2] + 2 * kk, umma_idesc(64),
+                                      (term | kk) > 0);
+                    umma_commit(sm.bar);
+                }
+                mbar_wait(sm.bar, phase);
+                phase ^= 1;
+                fence_after();
+                // ---- g_cross = [gc_q | gc_k | gc_d | gc_p] -> g_k row, and this row's share of g_q
+                float gk[16], gqr[16];
+                {
+                    float v[32];
+                    tmem_ld32(my_tmem + 64, v);
+#pragma unroll
+                    for (int e = 0; e < 16; ++e) { gqr[e] = v[e]; gk[e] = fmaf(w, gatt[e], v[16 + e]); }
+                    tmem_ld32(my_tmem + 96, v);
+#pragma unroll
+                    for (int e = 0; e < 16; ++e) {
+                        const float qe = sm.q[my_s * D + e];
+                        gqr[e] += v[e] + v[16 + e] * k[e];
+                        gk[e]  += v[16 + e] * qe - v[e];
+                    }
+                }
+                if (on) {
+                    float4* dst = reinterpret_cast<float4*>(g_hist + ((b0 + my_s) * T + my_t) * D);
+#pragma unroll
+                    for (int c = 0; c < 4; ++c) dst[c] = make_float4(gk[4 * c], gk[4 * c + 1], gk[4 * c + 2], gk[4 * c + 3]);
+                }
+#pragma unroll
+                for (int e = 0; e < 16; ++e) pool[tid * 17 + e] = on ? gqr[e] : 0.f;
+                fence_before();
+                __syncthreads();
+                for (int item = tid; item < (cur.s_end - s_begin) * 16; item += kTcThreads) {
+                    const int s = s_begin + (item >> 4), e = item & 15;
+                    const int len = sm.len[s], r0 = tile_row0(sm.len, s_begin, s);
+                    float a = 0.f;
+                    for (int t = 0; t < len; ++t) a += pool[(r0 + t) * 17 + e];
+                    sm.gq[s * 16 + e] = a;
+                }
+            } else {                                     // a tile of empty histories: nothing for the tensor core
+                if (tid == 0) group_slot = next_draw;
+                __syncthreads();
+                shadow_work();
+            }
+            if (p.use_softmax) {      // no history: uniform weights, gradient g_att / T on every position
+                for (int s = s_begin; s < cur.s_end; ++s) {
+                    if (sm.len[s] != 0) continue;
+                    const float u = 1.0f / (float)T;
+                    for (int i = tid; i < T * D; i += kTcThreads)
+                        g_hist[(b0 + s) * T * D + i] = u * sm.att[s * D + (i % D)];
+                }
+            }
+            __syncthreads();
+            s_begin = cur.s_end;
+            cur = nxt;
         }
+
+        // the target's columns of g_row: upstream + L2-norm share (gt) + the attention unit's g_q
+        for (int i = tid; i < n_samples * D; i += kTcThreads) {
+            const int s = i / D, e = i - s * D;
+            g_row[(b0 + s) * W + p.tgt_off + e] = sm.gt[i] + sm.gq[i];
+        }
+        __syncthreads();      // q / len / att / gq / gt are rewritten by the next group
+        group = (int64_t)group_slot;     // rewritten only after the next group's first barrier
     }
-    __syncthreads();      // q / len / att / gq are rewritten by the next group
-  }
     scheduler_exit(1);
     fence_before();
     __syncthreads();
@@ -1502,12 +1597,17 @@ int rk_din_bwd(const rk_din_args_t* args, const float* concat_all, const float* 
     const int grid = (int)ceil_div(p.B, kSamples);
     if (args->precision == RK_DIN_BF16_TENSOR) {
         RK_CHECK_ARG(p.D == 16, "din_bwd: the tensor-core activation unit is built for D = 16 (got %d)", p.D);
-        const size_t smem_tc = tc::TcSmem::bytes(64);
+        const size_t smem_tc = tc::TcBwdSmem::bytes(p.T, p.width);
+        RK_CHECK_ARG(smem_tc <= 227 * 1024, "din_bwd: %zu bytes of shared memory (width %d)", smem_tc, p.width);
         RK_CUDA(cudaFuncSetAttribute(tc::din_bwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                      (int)smem_tc));
-        // up to 4 CTAs per SM fit the TMEM budget (4 x 128 columns); CTAs that do not become resident
-        // simply find the scheduler empty when they start
-        const int grid_tc = grid < sm_count() * 4 ? grid : sm_count() * 4;
+        // persistent CTAs, two per SM by shared memory; the grid never exceeds the group count
+        static const int per_sm = [] {
+            const char* e = getenv("RANK_B200_DIN_TC_BWD_CTAS_PER_SM");
+            const int v = e ? atoi(e) : 0;
+            return v >= 1 && v <= 4 ? v : 2;
+        }();
+        const int grid_tc = grid < sm_count() * per_sm ? grid : sm_count() * per_sm;
         tc::din_bwd_tc_kernel<<<grid_tc, tc::kTcThreads, smem_tc, (cudaStream_t)stream_>>>(
             p, concat_all, norm, att_w, relu_masks, g_concat, g_norm, g_row, g_hist, err_flag);
         RK_LAUNCH_CHECK();
