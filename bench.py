@@ -75,6 +75,26 @@ class DeepFMWorkload(Workload):
         return F.binary_cross_entropy(prob.squeeze(), batch["label"])
 
 
+class FwFMWorkload(Workload):
+    # FwFM/fwfm.py defaults: batch 1024, embedding_dim 8, six fields.  Algorithmic bytes per sample:
+    # fwd 48 idx + 192 rows + 24 first-order + 192 emb + 4 y = 460; bwd 48 idx + 192 emb + 8 (y, g_y)
+    # + 3 x (192 + 24) gradient rows (written per occurrence, read sorted, written unique) = 896.
+    name, batch, bytes_per_sample, flops_per_sample = "fwfm_d8", 1024, 1356, 1000
+    hot_calls = ("rk_fwfm_fwd", "rk_plan_build", "rk_fwfm_bwd", "rk_embgrad_segment_reduce")
+
+    def model(self, ns, oracle, vocab_dir):
+        from rank_b200 import synthetic
+        cls = ns.OracleFwFM if oracle else ns.FwFM
+        return cls(synthetic.fwfm_field_dims(), 8)
+
+    def make_batch(self, B, seed):
+        from rank_b200 import synthetic
+        return synthetic.fwfm_batch(B, seed)
+
+    def loss(self, model, batch):
+        return F.binary_cross_entropy(model(batch["x"]), batch["label"])
+
+
 class DCNWorkload(Workload):
     name, batch, bytes_per_sample, flops_per_sample = "dcn_l3_dnn512-256-128", 8192, 1704, 2300
     hot_calls = ("rk_crossnet_fwd", "rk_plan_build", "rk_crossnet_bwd", "rk_embgrad_segment_reduce")
@@ -186,7 +206,7 @@ class DeepCrossingWorkload(Workload):
         return F.binary_cross_entropy_with_logits(logit.squeeze(), batch["label"])
 
 
-WORKLOADS = {"deepfm": DeepFMWorkload, "dcn": DCNWorkload, "afm": AFMWorkload, "din": DINWorkload,
+WORKLOADS = {"deepfm": DeepFMWorkload, "fwfm": FwFMWorkload, "dcn": DCNWorkload, "afm": AFMWorkload, "din": DINWorkload,
              "din_softmax": DINSoftmaxWorkload, "din_tc": DINTensorCoreWorkload,
              "din_softmax_tc": DINSoftmaxTensorCoreWorkload, "bst": BSTWorkload,
              "deepcrossing": DeepCrossingWorkload}

@@ -15,6 +15,7 @@ from ._lib import RankB200Error, check_index_errors, library_path
 from .vocab import VOCAB_FILE, WECHAT_VOCAB_LINES, table_heights, write_vocab_dir
 from .sparse import GatherConcat, GradSource, OccurrencePlan, gather_concat
 from .deepfm import DeepFM
+from .fwfm import FwFM
 from .dcn import DCNModel, cross_layer
 from .deepcrossing import DeepCrossingModel, residual_unit
 from .din import (DIN, Dice, din_attention, din_collate_fn, get_activation_unit_precision,
@@ -27,7 +28,7 @@ __all__ = [
     "RankB200Error", "check_index_errors", "library_path",
     "VOCAB_FILE", "WECHAT_VOCAB_LINES", "table_heights", "write_vocab_dir",
     "GradSource", "OccurrencePlan", "gather_concat",
-    "DeepFM", "DCNModel", "cross_layer", "DeepCrossingModel", "residual_unit", "DIN", "Dice", "din_attention", "din_collate_fn", "set_activation_unit_precision",
+    "DeepFM", "FwFM", "DCNModel", "cross_layer", "DeepCrossingModel", "residual_unit", "DIN", "Dice", "din_attention", "din_collate_fn", "set_activation_unit_precision",
     "get_activation_unit_precision",
     "AFM", "create_feature_columns", "RowShardedEmbedding", "shard_bst_feedid_table", "BSTModel", "BSTTransformer", "leakyrelu", "load_vocabulary",
 ]

@@ -68,6 +68,9 @@ PROTOTYPES = {
     "rk_gather_concat_fwd": (_I, [_P, _I, _P, _I, _L, _P, _I, _P, _P]),
     "rk_deepfm_fwd": (_I, [_P, _P, _I, _L, _P, _P, _P, _P, _P]),
     "rk_deepfm_bwd": (_I, [_P, _P, _P, _I, _I, _L, _P, _P]),
+    "rk_fwfm_fwd": (_I, [_P, _P, _P, _P, _I, _L, _P, _P, _P, _P]),
+    "rk_fwfm_bwd_ctas": (_I, []),
+    "rk_fwfm_bwd": (_I, [_P, _P, _P, _P, _I, _I, _L, _P, _P, _P, _P, _P]),
     "rk_crossnet_fwd": (_I, [_P, _I, _P, _I, _P, _P, _I, _L, _P, _P, _P, _P]),
     "rk_crossnet_bwd": (_I, [_P, _P, _P, _I, _I, _L, _P, _P, _P, _P]),
     "rk_cross_layer_fwd": (_I, [_P, _P, _P, _P, _I, _L, _P, _P]),
@@ -126,7 +129,7 @@ class CallTimer:
     (bench.py's live per-call device times).  Use as a context manager; `summary()` after a
     synchronize gives {entry point: (calls, total ms)}."""
 
-    NO_KERNEL = ("rk_resunit_pack_floats", "rk_din_mlp_floats","rk_afm_bwd_ctas", "rk_bst_grad_floats", "rk_bst_bwd_ctas", "rk_version", "rk_last_error", "rk_device_sm_count", "rk_launch_count", "rk_debug_spin",
+    NO_KERNEL = ("rk_resunit_pack_floats", "rk_din_mlp_floats", "rk_afm_bwd_ctas", "rk_fwfm_bwd_ctas", "rk_bst_grad_floats", "rk_bst_bwd_ctas", "rk_version", "rk_last_error", "rk_device_sm_count", "rk_launch_count", "rk_debug_spin",
                  "rk_plan_workspace_bytes", "rk_reduce_workspace_bytes")
 
     def __init__(self):

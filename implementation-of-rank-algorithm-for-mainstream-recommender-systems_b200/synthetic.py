@@ -62,6 +62,19 @@ def deepfm_batch(B, seed=SEED, lines=None, uniform=False):
     return dict(category=cat, label=labels(gen, B))
 
 
+def fwfm_field_dims(lines=None):
+    """`field_dims` as FwFM's main() builds them: the vocabulary lengths, no extra row (FwFM/fwfm.py:235-242)."""
+    lines = WECHAT_VOCAB_LINES if lines is None else lines
+    return [lines[c] for c in DEEPFM_COLUMNS]
+
+
+def fwfm_batch(B, seed=SEED, lines=None, uniform=False):
+    gen = torch.Generator().manual_seed(seed)
+    dims = fwfm_field_dims(lines)
+    x = {c: zipf_indices(gen, rows, (B,), uniform=uniform) for c, rows in zip(DEEPFM_COLUMNS, dims)}
+    return dict(x=x, label=labels(gen, B))
+
+
 def side_batch(B, seed=SEED, lines=None, uniform=False):
     """dense [B,16] + the six side-information columns (DCN, DeepCrossing)."""
     gen = torch.Generator().manual_seed(seed)

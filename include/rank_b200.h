@@ -107,6 +107,24 @@ int rk_deepfm_fwd(const rk_field_t* second, const float* const* first_weight, in
 int rk_deepfm_bwd(const float* deep_input, const float* g_deep, const float* g_second, int F,
                   int D, int64_t B, float* g_rows, rk_stream_t stream);
 
+/* ---- FwFM (FwFM/fwfm.py:87-139; "next" row of the scope table) -----------------------------
+ * second[f]: the F embedding tables (dim D each); first_weight[f]: the `linear` tables [rows,1],
+ * same idx; field_weight[P], P = F(F-1)/2 in the reference's pair order (i outer, j inner,
+ * fwfm.py:126-135); bias[1].  emb[B, F*D] = cat_f e_f (kept for the backward);
+ * y[B] = sigmoid(sum_f w_f + sum_p r_p <e_i, e_j> + bias)  (fwfm.py:137-139). */
+int rk_fwfm_fwd(const rk_field_t* second, const float* const* first_weight,
+                const float* field_weight, const float* bias, int F, int64_t B, float* emb,
+                float* y, int32_t* err_flag, rk_stream_t stream);
+/* Rows of `partials` the backward may use (one per CTA). */
+int rk_fwfm_bwd_ctas(void);
+/* g_z[B] = g_y * y * (1-y) (the per-occurrence gradient of every first-order table);
+ * g_rows[B, F*D]: per-occurrence gradients of the embedding rows;
+ * g_pair[P+1] = [d field_weight (P), d bias]; partials: scratch [rk_fwfm_bwd_ctas()][P+1].
+ * Sums over the batch have a fixed order (no float atomics). */
+int rk_fwfm_bwd(const float* emb, const float* y, const float* g_y, const float* field_weight,
+                int F, int D, int64_t B, float* g_rows, float* g_z, float* partials,
+                float* g_pair, rk_stream_t stream);
+
 /* ---- DCN CrossNet (cross_layer + loop, DCN/dcn.py:25-50,169-173) -------------------------
  * fwd: x0 = [dense | gathered rows] -> concat_all[B,d]; x_{l+1} = x0*(x_l.w_l) + b_l + x_l
  * -> cross_vec[B,d].  w, b: [L, d]. */

@@ -78,6 +78,18 @@ def deepfm_fm_part(first_tables, second_tables, idx_columns):
     return deep_input, fm_first, fm_second
 
 
+def fwfm_logit(first_tables, second_tables, idx_columns, field_weight, bias):
+    """FwFM/fwfm.py:118-137.  z[B,1] = sum_f w_f + sum_{i<j} r_p <e_i, e_j> + bias, the pairs p
+    enumerated i outer / j inner as the reference's double loop (:126-135)."""
+    linear_sum = sum(gather_rows(t, i) for t, i in zip(first_tables, idx_columns))      # :122-123
+    embs = torch.stack([gather_rows(t, i) for t, i in zip(second_tables, idx_columns)], dim=1)   # [B,F,D]
+    F = embs.shape[1]
+    left, right = torch.triu_indices(F, F, offset=1)          # row-major upper triangle = loop order
+    dots = (embs[:, left, :] * embs[:, right, :]).sum(dim=2)                            # [B,P]  :131
+    quadratic = (dots * field_weight).sum(dim=1, keepdim=True)                          # :133
+    return linear_sum + quadratic + bias                                                # :137
+
+
 # --------------------------------------------------------------------------- DCN / DeepCrossing
 def concat_features(dense, tables, idx_columns):
     """[dense | e_0 | e_1 ...]: DCN/dcn.py:163-169, DeepCrossing/deepcrossing.py:148-155."""

@@ -73,6 +73,27 @@ class OracleDeepFM(nn.Module):          # DeepFM/deepfm.py:73-151
         return torch.sigmoid(total), total, first, second, deep_logit
 
 
+class OracleFwFM(nn.Module):            # FwFM/fwfm.py:87-139
+    COLUMNS = ("userid", "feedid", "device", "authorid", "bgm_song_id", "bgm_singer_id")
+
+    def __init__(self, field_dims, embed_dim):
+        super().__init__()
+        self.field_dims, self.num_fields, self.embed_dim = field_dims, len(field_dims), embed_dim
+        self.linear = nn.ModuleList([nn.Embedding(v, 1) for v in field_dims])
+        self.embedding = nn.ModuleList([nn.Embedding(v, embed_dim) for v in field_dims])
+        for table in self.embedding:
+            nn.init.xavier_uniform_(table.weight)
+        self.num_pairs = self.num_fields * (self.num_fields - 1) // 2
+        self.field_weight = nn.Parameter(torch.randn(self.num_pairs), requires_grad=True)
+        self.bias = nn.Parameter(torch.zeros(1))
+
+    def forward(self, x):
+        idx = [x[c] for c in self.COLUMNS[:self.num_fields]]
+        z = X.fwfm_logit([t.weight for t in self.linear], [t.weight for t in self.embedding], idx,
+                         self.field_weight, self.bias)
+        return torch.sigmoid(z).squeeze(1)
+
+
 def _side_embeddings(vocab_sizes, extra=()):
     return nn.ModuleDict({c: nn.Embedding(vocab_sizes[c], d) for c, d in _SIDE + tuple(extra)})
 

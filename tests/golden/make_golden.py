@@ -74,6 +74,14 @@ def record(model, fwd, seed, extra):
     return fx
 
 
+def save(fx, name):
+    """`python make_golden.py fwfm` rewrites only the files whose name starts with `fwfm` (the others
+    are still computed, so the generator stream is the same as in a full run)."""
+    only = sys.argv[1:]
+    if not only or any(name.startswith(o) for o in only):
+        torch.save(fx, os.path.join(HERE, name))
+
+
 def main():
     tmp = tempfile.mkdtemp(prefix="rk_golden_vocab_")
     vocab_dir = write_vocab(tmp, SMALL_LINES) + "/"
@@ -94,7 +102,7 @@ def main():
             model="DeepFM", vocab_lines=SMALL_LINES,
             ctor=dict(embedding_dim=D, hidden_units=[32, 16], dropout_rate=0.0, batch_norm=True),
             inputs=dict(category=cat)))
-        torch.save(fx, os.path.join(HERE, f"deepfm_d{D}.pt"))
+        save(fx, f"deepfm_d{D}.pt")
 
     # ---- DCN
     ref = load_reference("DCN/dcn.py", "ref_dcn")
@@ -103,7 +111,7 @@ def main():
     fx = record(m, lambda: m(dense, cat), 11, dict(
         model="DCNModel", vocab_lines=SMALL_LINES, ctor=dict(hidden_units=[32, 16], num_cross_layer=3),
         inputs=dict(dense=dense, category=cat)))
-    torch.save(fx, os.path.join(HERE, "dcn_l3.pt"))
+    save(fx, "dcn_l3.pt")
 
     # ---- DeepCrossing
     ref = load_reference("DeepCrossing/deepcrossing.py", "ref_dc")
@@ -112,7 +120,7 @@ def main():
         model="DeepCrossingModel", vocab_lines=SMALL_LINES,
         ctor=dict(residual_internal_dim=24, residual_network_num=2),
         inputs=dict(dense=dense, category=cat)))
-    torch.save(fx, os.path.join(HERE, "deepcrossing_n2.pt"))
+    save(fx, "deepcrossing_n2.pt")
 
     # ---- AFM (10 fields: the 7 shipped + 3 synthetic ones, as BASELINE config 3)
     ref = load_reference("AFM/afm.py", "ref_afm")
@@ -126,7 +134,7 @@ def main():
     fx = record(m, lambda: m(dense, cat10), 17, dict(
         model="AFM", ctor=dict(embedding_dim=8, attention_factor=12),
         feature_columns=fc, inputs=dict(dense=dense, category=cat10)))
-    torch.save(fx, os.path.join(HERE, "afm_f10.pt"))
+    save(fx, "afm_f10.pt")
 
     # ---- DIN (both attention modes; lengths include 0 and T)
     ref = load_reference("DIN/din.py", "ref_din")
@@ -147,7 +155,7 @@ def main():
             ctor=dict(hidden_units=[32, 16], activation="dice", dropout_rate=0.0, batch_norm=True,
                       use_softmax=soft, l2_lambda=0.2, mini_batch_aware_regularization=True),
             inputs=dict(dense=dense_dict, category=cat, sequence=sequence, target=target)))
-        torch.save(fx, os.path.join(HERE, f"din_softmax{int(soft)}.pt"))
+        save(fx, f"din_softmax{int(soft)}.pt")
 
     # the reference's own smoke input for din_attention (DIN/din_attention.py:54-68)
     ref_att = load_reference("DIN/din_attention.py", "ref_din_attention")
@@ -179,7 +187,20 @@ def main():
             ctor=dict(hidden_units=[32, 16], dropout_rate=0.0, batch_norm=True, nhead=nhead,
                       num_transformer_blocks=blocks, max_seq_length=Tb, pooling_method=pool),
             inputs=dict(dense=dense, category=cat, seq_feedid=bseq, seq_length=blen)))
-        torch.save(fx, os.path.join(HERE, f"bst_h{nhead}_b{blocks}_{pool}.pt"))
+        save(fx, f"bst_h{nhead}_b{blocks}_{pool}.pt")
+    # ---- FwFM: field_dims are vocabulary lengths, forward returns one tensor
+    ref = load_reference("FwFM/fwfm.py", "ref_fwfm")
+    six = ["userid", "feedid", "device", "authorid", "bgm_song_id", "bgm_singer_id"]
+    dims = [SMALL_LINES[c] for c in six]
+    for D in (8, 5):
+        torch.manual_seed(21)
+        m = ref.FwFM(dims, D)
+        with torch.no_grad():
+            m.bias.fill_(0.25)          # the reference initialises it to 0: make it visible in y
+        x = {c: rand_idx(gen, SMALL_LINES[c], (B,)) for c in six}
+        fx = record(m, lambda: (m(x),), 29, dict(
+            model="FwFM", ctor=dict(field_dims=dims, embed_dim=D), inputs=dict(x=x)))
+        save(fx, f"fwfm_d{D}.pt")
     print("golden fixtures written to", HERE)
 
 

@@ -2,7 +2,7 @@
 import torch
 
 ORACLE = {"DeepFM": "OracleDeepFM", "DCNModel": "OracleDCN", "DeepCrossingModel": "OracleDeepCrossing",
-          "AFM": "OracleAFM", "DIN": "OracleDIN", "BSTModel": "OracleBST"}
+          "AFM": "OracleAFM", "FwFM": "OracleFwFM", "DIN": "OracleDIN", "BSTModel": "OracleBST"}
 
 
 def build(fx, namespace, vocab_dir, oracle):
@@ -10,6 +10,8 @@ def build(fx, namespace, vocab_dir, oracle):
     cls = getattr(namespace, name)
     if fx["model"] == "AFM":
         return cls(fx["feature_columns"], **fx["ctor"])
+    if fx["model"] == "FwFM":
+        return cls(**fx["ctor"])
     return cls(vocab_dir, **fx["ctor"])
 
 
@@ -19,6 +21,8 @@ def call(model, fx, inputs):
         return model(inputs["category"])
     if k in ("DCNModel", "DeepCrossingModel", "AFM"):
         return model(inputs["dense"], inputs["category"])
+    if k == "FwFM":
+        return (model(inputs["x"]),)
     if k == "DIN":
         return model(inputs["dense"], inputs["category"], inputs["sequence"], inputs["target"])
     if k == "BSTModel":

@@ -17,7 +17,7 @@ from oracle import models as oracle_models
 pytestmark = pytest.mark.gpu
 DEV = "cuda"
 FP32_TOL = 1e-5
-IMPLEMENTED = {n for n in ("DeepFM", "DCNModel", "DeepCrossingModel", "AFM", "DIN", "BSTModel")
+IMPLEMENTED = {n for n in ("DeepFM", "FwFM", "DCNModel", "DeepCrossingModel", "AFM", "DIN", "BSTModel")
                if hasattr(rank_b200, n)}
 FIXTURES = [p for p in golden_files() if "smoke" not in p]
 
@@ -274,3 +274,62 @@ def test_din_tensor_core_activation_unit(wechat_vocab_dir, B, T, soft):
     compare(o_outs, o_grads, r_outs, r_grads, BF16_TOL, g64)
     # and it is a different kernel: fp32-exact agreement would mean the switch did nothing
     assert rel_err(o_outs[1], r_outs[1]) > 1e-7
+
+
+# ---------------------------------------------------------------------------------- FwFM
+def _fwfm_pair(D, dims=None):
+    dims = synthetic.fwfm_field_dims() if dims is None else dims
+    torch.manual_seed(0)
+    ours = rank_b200.FwFM(dims, D)
+    ref = oracle_models.OracleFwFM(dims, D)
+    ref.load_state_dict(ours.state_dict(), strict=True)
+    with torch.no_grad():                       # bias starts at 0 in the reference: exercise it
+        ours.bias.fill_(-0.5)
+        ref.bias.fill_(-0.5)
+    return ours.to(DEV), ref
+
+
+@pytest.mark.parametrize("B,D", [(1024, 8), (8192, 16), (333, 6), (1, 5), (4097, 32)])
+def test_fwfm_vs_oracle_wechat_sizes(B, D):
+    ours, ref = _fwfm_pair(D)
+    batch = synthetic.fwfm_batch(B)
+    fx = {"model": "FwFM", "seed": 3}
+    inputs = {"x": batch["x"]}
+    gen = torch.Generator().manual_seed(5)
+    cots = [torch.randn(B, generator=gen) / B]
+    r_outs, r_grads = golden_cases.replay(ref, fx, inputs, cots)
+    o_outs, o_grads = golden_cases.replay(ours, fx, to_device(inputs, DEV), to_device(cots, DEV))
+    rank_b200.check_index_errors()
+    _, grads64 = golden_cases.replay(copy.deepcopy(ref).double(), fx, inputs, _to_double(cots))
+    assert o_outs[0].shape == r_outs[0].shape == (B,)
+    compare(o_outs, o_grads, r_outs, r_grads, FP32_TOL, grads64)
+
+
+def test_fwfm_training_loss_and_repeatability():
+    """BCELoss on y as the reference's train() (FwFM/fwfm.py:152-156); two runs give identical bits
+    (no float atomics anywhere on the path)."""
+    ours, ref = _fwfm_pair(8)
+    batch = synthetic.fwfm_batch(2048)
+    x, label = to_device(batch["x"], DEV), batch["label"].to(DEV)
+    runs = []
+    for _ in range(2):
+        ours.zero_grad()
+        loss = torch.nn.functional.binary_cross_entropy(ours(x), label)
+        loss.backward()
+        runs.append((loss.detach().clone(), {k: p.grad.clone() for k, p in ours.named_parameters()}))
+    assert torch.equal(runs[0][0], runs[1][0])
+    for k in runs[0][1]:
+        assert torch.equal(runs[0][1][k], runs[1][1][k]), k
+    ref_loss = torch.nn.functional.binary_cross_entropy(ref(batch["x"]), batch["label"])
+    assert rel_err(runs[0][0], ref_loss) <= FP32_TOL
+
+
+def test_fwfm_index_out_of_range_is_reported():
+    ours, _ = _fwfm_pair(8)
+    batch = synthetic.fwfm_batch(64)
+    x = to_device(batch["x"], DEV)
+    x["device"] = x["device"].clone()
+    x["device"][7] = 10 ** 6
+    ours(x)
+    with pytest.raises(IndexError):
+        rank_b200.check_index_errors()
