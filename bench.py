@@ -134,6 +134,18 @@ class AFMWorkload(Workload):
         return F.binary_cross_entropy(prob.squeeze(), batch["label"])
 
 
+class AFMTensorCoreWorkload(AFMWorkload):
+    # attention MLP on tcgen05 (split-bf16 operands, fp32 TMEM accumulation)
+    name, dtype = "afm_f10_d32_a128_tcgen05", "bf16x3 tensor-core MLP, f32 elsewhere"
+    hot_calls = ("rk_afm_tc_fwd", "rk_afm_tc_bwd", "rk_plan_build", "rk_afm_bwd", "rk_embgrad_segment_reduce")
+
+    def model(self, ns, oracle, vocab_dir):
+        m = super().model(ns, oracle, vocab_dir)
+        if not oracle:
+            m.attention_precision = "bf16"
+        return m
+
+
 class DINWorkload(Workload):
     name, batch, bytes_per_sample, flops_per_sample = "din_t50_raw", 8192, 18648, 1_240_000
     hot_calls = ("rk_din_fwd", "rk_plan_build", "rk_din_bwd", "rk_embgrad_segment_reduce")
@@ -206,7 +218,7 @@ class DeepCrossingWorkload(Workload):
         return F.binary_cross_entropy_with_logits(logit.squeeze(), batch["label"])
 
 
-WORKLOADS = {"deepfm": DeepFMWorkload, "fwfm": FwFMWorkload, "dcn": DCNWorkload, "afm": AFMWorkload, "din": DINWorkload,
+WORKLOADS = {"deepfm": DeepFMWorkload, "fwfm": FwFMWorkload, "dcn": DCNWorkload, "afm": AFMWorkload, "afm_tc": AFMTensorCoreWorkload, "din": DINWorkload,
              "din_softmax": DINSoftmaxWorkload, "din_tc": DINTensorCoreWorkload,
              "din_softmax_tc": DINSoftmaxTensorCoreWorkload, "bst": BSTWorkload,
              "deepcrossing": DeepCrossingWorkload}

@@ -77,6 +77,7 @@ PROTOTYPES = {
     "rk_cross_layer_bwd": (_I, [_P, _P, _P, _I, _L, _P, _P, _P, _P]),
     "rk_afm_bwd_ctas": (_I, [_L, _I]),
     "rk_afm_fwd": (_I, [_P, _I, _P, _P, _P, _P, _I, _L, _P, _P, _P]),
+    "rk_afm_tc_fwd": (_I, [_P, _I, _P, _P, _P, _P, _I, _L, _P, _P, _P]),
     "rk_afm_bwd": (_I, [_P, _I, _P, _P, _P, _P, _I, _L, _P, _P, _P, _P, _P, _P, _P, _I, _P, _P]),
     "rk_shard_owner": (_I, [_P, _L, _L, _L, _P, _P, _P]),
     "rk_shard_route": (_I, [_P, _P, _P, _L, _L, _L, _I, _P, _P, _P, _P]),

@@ -24,8 +24,9 @@ class _AfmPooling(torch.autograd.Function):
     """(w1, b1, w2, b2, idx_0.., table_0..) -> pooled[B, D]."""
 
     @staticmethod
-    def forward(ctx, F, w1, b1, w2, b2, *args):
+    def forward(ctx, cfg, w1, b1, w2, b2, *args):
         lib = _lib.load()
+        F, precision = cfg
         idx, tables = args[:F], args[F:2 * F]
         D = int(tables[0].shape[1])
         fields, keep = field_array(tables, idx, [f * D for f in range(F)])
@@ -39,14 +40,16 @@ class _AfmPooling(torch.autograd.Function):
         B = int(idx[0].shape[0])
         dev = w1.device
         out = torch.empty(B, D, dtype=torch.float32, device=dev)
-        rc = lib.rk_afm_fwd(fields, F, w1.data_ptr(), b1.data_ptr(), w2.data_ptr(), b2.data_ptr(), A, B,
-                            out.data_ptr(), _lib.err_flag(dev).data_ptr(), _lib.stream_ptr())
+        fwd = lib.rk_afm_tc_fwd if precision == "bf16" else lib.rk_afm_fwd
+        rc = fwd(fields, F, w1.data_ptr(), b1.data_ptr(), w2.data_ptr(), b2.data_ptr(), A, B,
+                 out.data_ptr(), _lib.err_flag(dev).data_ptr(), _lib.stream_ptr())
         _lib.check(rc, "rk_afm_fwd")
         if _lib.CHECK_EVERY_CALL:
             _lib.check_index_errors(dev)
         ctx.set_materialize_grads(False)
         if any(ctx.needs_input_grad):
             ctx.meta = (F, D, A, B, [int(t.shape[0]) for t in tables])
+            ctx.precision = precision
             ctx.fields, ctx.keep = fields, keep
             if any(ctx.needs_input_grad[5 + F:]):
                 ctx.plan = OccurrencePlan([keep[2 * f + 1] for f in range(F)], ctx.meta[4])
@@ -98,12 +101,15 @@ class AFM(nn.Module):
         self.attention = nn.Sequential(
             nn.Linear(embedding_dim, attention_factor), nn.ReLU(), nn.Linear(attention_factor, 1))
         self.p = nn.Linear(embedding_dim, 1)
+        # "fp32": SIMT kernels (csrc/afm.cu), the reference's arithmetic; "bf16": the attention MLP on
+        # tcgen05 with split-bf16 operands and fp32 accumulation (csrc/afm_tc.cu).  Not a parameter.
+        self.attention_precision = "fp32"
 
     def forward(self, dense_input, category_input):
         dense_logit = self.dense_layer(dense_input)
         cols = self.category_features
         pooled = _AfmPooling.apply(
-            len(cols), self.attention[0].weight, self.attention[0].bias, self.attention[2].weight,
+            (len(cols), self.attention_precision), self.attention[0].weight, self.attention[0].bias, self.attention[2].weight,
             self.attention[2].bias, *[category_input[c] for c in cols],
             *[self.embeddings[c].weight for c in cols])
         total_logit = dense_logit + self.p(pooled)

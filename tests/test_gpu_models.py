@@ -276,6 +276,23 @@ def test_din_tensor_core_activation_unit(wechat_vocab_dir, B, T, soft):
     assert rel_err(o_outs[1], r_outs[1]) > 1e-7
 
 
+@pytest.mark.parametrize("B,F,D,A", [(2048, 10, 32, 128), (1000, 7, 16, 64), (513, 3, 8, 20), (300, 16, 4, 128),
+                                     (129, 10, 32, 100), (1, 2, 32, 128)])
+def test_afm_tensor_core_attention(B, F, D, A):
+    """AFM's attention MLP on tcgen05 (split-bf16 operands, fp32 TMEM accumulation)."""
+    fc = synthetic.afm_feature_columns(F, extra_vocab=5000)
+    torch.manual_seed(0)
+    ours = rank_b200.AFM(fc, D, A)
+    ref = oracle_models.OracleAFM(fc, D, A)
+    ref.load_state_dict(ours.state_dict(), strict=True)
+    ours.to(DEV)
+    ours.attention_precision = "bf16"
+    o_outs, o_grads, r_outs, r_grads, _, g64 = _run_both(ours, ref, "AFM", synthetic.afm_batch(B, fc))
+    print("afm tc: logit err %.3e" % rel_err(o_outs[1], r_outs[1]),
+          {k: "%.2e" % rel_err(o_grads[k], r_grads[k]) for k in r_grads if k.startswith("attention")})
+    compare(o_outs, o_grads, r_outs, r_grads, BF16_TOL, g64)
+
+
 # ---------------------------------------------------------------------------------- FwFM
 def _fwfm_pair(D, dims=None):
     dims = synthetic.fwfm_field_dims() if dims is None else dims
