@@ -68,10 +68,12 @@ class _AfmPooling(torch.autograd.Function):
         g_out = _lib.require_cuda(g_out, "g_pooled", torch.float32)
         g_rows = torch.empty(B, F * D, dtype=torch.float32, device=dev)
         g_att = torch.empty(A * D + 2 * A + 1, dtype=torch.float32, device=dev)   # w1 | b1 | w2 | b2
-        n_ctas = lib.rk_afm_bwd_ctas(B, F)
+        tc = ctx.precision == "bf16"
+        n_ctas = (lib.rk_afm_tc_bwd_ctas if tc else lib.rk_afm_bwd_ctas)(B, F)
         partials = torch.empty(n_ctas * g_att.numel(), dtype=torch.float32, device=dev)
         base = g_att.data_ptr()
-        rc = lib.rk_afm_bwd(ctx.fields, F, w1.data_ptr(), b1.data_ptr(), w2.data_ptr(), b2.data_ptr(), A, B,
+        bwd = lib.rk_afm_tc_bwd if tc else lib.rk_afm_bwd
+        rc = bwd(ctx.fields, F, w1.data_ptr(), b1.data_ptr(), w2.data_ptr(), b2.data_ptr(), A, B,
                             g_out.data_ptr(), g_rows.data_ptr(), base, base + 4 * A * D,
                             base + 4 * (A * D + A), base + 4 * (A * D + 2 * A), partials.data_ptr(), n_ctas,
                             _lib.err_flag(dev).data_ptr(), _lib.stream_ptr())

@@ -220,6 +220,364 @@ afm_fwd_tc_kernel(const __grid_constant__ AfmTcParams p, float* __restrict__ out
     if (warp == 0) tmem_dealloc(tmem, 128);
 }
 
+
+// ---- backward ------------------------------------------------------------------------------
+// Per row r = (sample, pair):  pre = v W1^T + b1,  mask = [pre > 0],  s = w2 . relu(pre) + b2,
+// a = softmax_pairs(s),  g_a = <g_out, v>,  g_s = a (g_a - sum_q a_q g_a_q).
+// Everything that touches the hidden layer is written in terms of the 0/1 mask (exact in bf16):
+//   g_v[r]  = a g_out + g_s[r] * (mask[r,:] . B2),        B2[d][a] = w2[a] W1[a][d]   (split hi | lo along N)
+//   U[a][n] = sum_r mask[r][a] * X[r][n],                  X[r] = g_s[r] * [v_hi | v_lo | 1_hi, 1_lo]
+// and the registered-weight gradients follow from U alone (exact identities, no division):
+//   dW1[a][d] = w2[a] U[a][d],  db1[a] = w2[a] u0[a],  dw2[a] = sum_d W1[a][d] U[a][d] + b1[a] u0[a]
+// (u0 = the "1" columns of U; U[a][d] = U_hi + U_lo).  mask is stored once (K-major for g_v) and read
+// a second time as the MN-major (transposed) A operand of the U product, whose accumulator stays
+// in TMEM for the whole life of the CTA.  db2 = sum_r g_s (mathematically 0) is summed on the side.
+struct AfmTcBwdSmem {
+    uint8_t *b3, *a1, *b1t, *a2, *b2t;   // b3 panel 0 and a1 are adjacent: a1 doubles as b3's second panel
+    float   *e[2], *gout[2];
+    float   *bias, *w2, *score, *attn, *ga, *gs, *dot, *red;
+    int     *pi, *pj, *pidx;
+    uint64_t* bar;
+    uint32_t* tmem_slot;
+    __device__ AfmTcBwdSmem(uint8_t* base, const AfmTcParams& p) {
+        uint8_t* q = base;
+        b3 = q;   q += 128 * 128;
+        a1 = q;   q += 128 * 128;
+        b1t = q;  q += 128 * 128;
+        a2 = q;   q += 2 * 128 * 128;
+        b2t = q;  q += 2 * 64 * 128;
+        const size_t eb = sizeof(float) * p.S * p.fs.F * p.estride;
+        e[0] = (float*)q;  q += eb;
+        e[1] = (float*)q;  q += eb;
+        gout[0] = (float*)q;  q += sizeof(float) * p.S * 32;
+        gout[1] = (float*)q;  q += sizeof(float) * p.S * 32;
+        bias = (float*)q;  q += sizeof(float) * 128;
+        w2 = (float*)q;    q += sizeof(float) * 128;
+        score = (float*)q; q += sizeof(float) * kAfmTcRows;
+        attn = (float*)q;  q += sizeof(float) * kAfmTcRows;
+        ga = (float*)q;    q += sizeof(float) * kAfmTcRows;
+        gs = (float*)q;    q += sizeof(float) * kAfmTcRows;
+        dot = (float*)q;   q += sizeof(float) * kAfmTcMaxS;
+        red = (float*)q;   q += sizeof(float) * kAfmTcThreads;
+        pi = (int*)q;      q += sizeof(int) * 128;
+        pj = (int*)q;      q += sizeof(int) * 128;
+        pidx = (int*)q;    q += sizeof(int) * 256;
+        bar = (uint64_t*)q; q += 8;
+        tmem_slot = (uint32_t*)q;
+    }
+    static size_t bytes(const AfmTcParams& p) {
+        return 1024 + 3 * 128 * 128 + 2 * 128 * 128 + 2 * 64 * 128 + 2 * sizeof(float) * p.S * p.fs.F * p.estride +
+               2 * sizeof(float) * p.S * 32 + sizeof(float) * (2 * 128 + 4 * kAfmTcRows + kAfmTcMaxS + kAfmTcThreads) +
+               sizeof(int) * 512 + 16;
+    }
+};
+
+__device__ __forceinline__ void afm_issue_gout(const AfmTcParams& p, float* dst, const float* g_out, int64_t tile, int tid) {
+    const int c4 = p.D >> 2;
+    const int64_t b0 = tile * p.S;
+    const int n_s = (int)((p.B - b0) < p.S ? (p.B - b0) : p.S);
+    for (int item = tid; item < n_s * c4; item += kAfmTcThreads) {
+        const int s = item / c4, c = item - s * c4;
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;"
+                     ::"r"(smem_u32(dst + s * 32 + 4 * c)), "l"(g_out + (b0 + s) * p.D + 4 * c) : "memory");
+    }
+}
+
+template <int KP>
+__global__ void __launch_bounds__(kAfmTcThreads)
+afm_bwd_tc_kernel(const __grid_constant__ AfmTcParams p, const float* __restrict__ g_out, float* __restrict__ g_rows,
+                  float* __restrict__ partials, int32_t* err_flag) {
+    extern __shared__ uint8_t afm_tc_raw[];
+    uint8_t* base = afm_tc_raw + ((1024u - (smem_u32(afm_tc_raw) & 1023u)) & 1023u);
+    AfmTcBwdSmem sm(base, p);
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int F = p.fs.F, D = p.D, P = p.P, A = p.A, Ap = p.Ap;
+    constexpr int LO = KP / 8;                       // 16-byte units from the hi half to the lo half of a line
+    constexpr int N2 = 2 * KP;                       // g_v product: [hi | lo] along N
+    constexpr int N3 = 2 * KP + 16;                  // U product:   [v_hi | v_lo | 1_hi, 1_lo, 0 ...]
+    constexpr uint32_t kUOff = 128;                  // TMEM columns: [0,128) pre / g_v, [128, 128 + N3) U
+
+    int64_t tile = blockIdx.x;
+    if (tile < p.n_tiles) {
+        afm_issue_gout(p, sm.gout[0], g_out, tile, tid);
+        afm_issue_rows(p, sm.e[0], tile, tid, err_flag);
+    }
+    if (tid == 0) mbar_init(sm.bar, 1);
+    if (warp == 0) tmem_alloc(sm.tmem_slot, 256);
+    for (int n = tid; n < 128; n += kAfmTcThreads) {             // W1[n][:] -> B1 line n; bias, w2
+        float x[KP];
+#pragma unroll
+        for (int d = 0; d < KP; ++d) x[d] = (n < A && d < D) ? __ldg(p.w1 + n * D + d) : 0.f;
+        store_line_split<KP>(sm.b1t, n, x);
+        sm.bias[n] = n < A ? __ldg(p.b1 + n) : 0.f;
+        sm.w2[n]   = n < A ? __ldg(p.w2 + n) : 0.f;
+    }
+    // B2 lines n < KP: hi of w2[a] W1[a][n]; n >= KP: lo.  K = a, 64 per panel.
+    for (int item = tid; item < N2 * 16; item += kAfmTcThreads) {
+        const int n = item >> 4, c16 = item & 15, q = c16 >> 3, c = c16 & 7;
+        const int d = n < KP ? n : n - KP;
+        float x[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const int a = 64 * q + 8 * c + j;
+            float w = (a < A && d < D) ? __ldg(p.w2 + a) * __ldg(p.w1 + a * D + d) : 0.f;
+            if (n >= KP) w -= __bfloat162float(__float2bfloat16_rn(w));
+            x[j] = w;
+        }
+        store_chunk(sm.b2t + q * (64 * 128), n, c, x);
+    }
+    for (int i = tid; i < 2 * 128 * 128 / 16; i += kAfmTcThreads)       // mask columns >= Ap stay zero
+        reinterpret_cast<uint4*>(sm.a2)[i] = make_uint4(0u, 0u, 0u, 0u);
+    if (tid == 0) {
+        int q = 0;
+        for (int i = 0; i < F; ++i)
+            for (int j = i + 1; j < F; ++j) {
+                sm.pi[q] = i; sm.pj[q] = j;
+                sm.pidx[i * F + j] = q; sm.pidx[j * F + i] = q;
+                ++q;
+            }
+    }
+    fence_async_smem();
+    fence_before();
+    __syncthreads();
+    fence_after();
+    const uint32_t tmem = *sm.tmem_slot;
+    const uint32_t my_tmem = tmem + ((uint32_t)(warp * 32) << 16);
+    const uint64_t a1_desc = umma_desc(smem_u32(sm.a1)), b1_desc = umma_desc(smem_u32(sm.b1t));
+    const float b2 = __ldg(p.b2);
+    float* stage = reinterpret_cast<float*>(sm.b3);  // [128][32] floats, chunk-swizzled; b3 is free after the U product
+    uint32_t phase = 0;
+    int buf = 0;
+    bool first_tile = true;
+    float gb2_acc = 0.f;
+
+    for (; tile < p.n_tiles; tile += gridDim.x, buf ^= 1) {
+        const int64_t b0 = tile * p.S;
+        const int n_s = (int)((p.B - b0) < p.S ? (p.B - b0) : p.S);
+        const int n_rows = n_s * P;
+        asm volatile("cp.async.wait_group 0;" ::: "memory");
+        __syncthreads();
+        const bool on = tid < n_rows;
+        const int s = on ? tid / P : 0, pr = on ? tid - s * P : 0;
+        const float* esm = sm.e[buf];
+        float v[KP];
+        float ga = 0.f;
+#pragma unroll
+        for (int d = 0; d < KP; ++d) v[d] = 0.f;
+        if (on) {
+            const float* ei = esm + (s * F + sm.pi[pr]) * p.estride;
+            const float* ej = esm + (s * F + sm.pj[pr]) * p.estride;
+            const float* go = sm.gout[buf] + s * 32;
+#pragma unroll
+            for (int c = 0; c < KP / 4; ++c)
+                if (4 * c < D) {
+                    const float4 x = *reinterpret_cast<const float4*>(ei + 4 * c);
+                    const float4 y = *reinterpret_cast<const float4*>(ej + 4 * c);
+                    const float4 g = *reinterpret_cast<const float4*>(go + 4 * c);
+                    v[4 * c] = x.x * y.x; v[4 * c + 1] = x.y * y.y; v[4 * c + 2] = x.z * y.z; v[4 * c + 3] = x.w * y.w;
+                    ga = fmaf(g.x, v[4 * c], ga); ga = fmaf(g.y, v[4 * c + 1], ga);
+                    ga = fmaf(g.z, v[4 * c + 2], ga); ga = fmaf(g.w, v[4 * c + 3], ga);
+                }
+        }
+        sm.ga[tid] = ga;
+        store_line_split<KP>(sm.a1, tid, v);
+        fence_async_smem();
+        fence_before();
+        __syncthreads();
+        if (tid == 0) {                                  // pre = V W1^T
+            fence_after();
+#pragma unroll
+            for (int term = 0; term < 3; ++term)
+#pragma unroll
+                for (int kk = 0; kk < KP / 16; ++kk)
+                    umma_bf16(tmem, a1_desc + (term == 1 ? LO : 0) + 2 * kk, b1_desc + (term == 2 ? LO : 0) + 2 * kk,
+                              umma_idesc(Ap), (term | kk) > 0);
+            umma_commit(sm.bar);
+        }
+        if (tile + gridDim.x < p.n_tiles) {              // while the tensor core works: the next tile's inputs
+            afm_issue_gout(p, sm.gout[buf ^ 1], g_out, tile + gridDim.x, tid);
+            afm_issue_rows(p, sm.e[buf ^ 1], tile + gridDim.x, tid, err_flag);
+        }
+        mbar_wait(sm.bar, phase);
+        phase ^= 1;
+        fence_after();
+        // ---- score and the 0/1 mask line (bf16 1.0 = 0x3F80)
+        float sc = b2;
+        for (int ch = 0; ch < Ap / 32; ++ch) {
+            float h[32];
+            tmem_ld32(my_tmem + 32 * ch, h);
+            uint32_t bits = 0;
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+                const float x = h[j] + sm.bias[32 * ch + j];
+                bits |= (x > 0.f ? 1u : 0u) << j;
+                sc = fmaf(fmaxf(x, 0.f), sm.w2[32 * ch + j], sc);
+            }
+            uint8_t* panel = sm.a2 + (ch >> 1) * (128 * 128);
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+                uint4 w;
+                const uint32_t b8 = bits >> (8 * c);
+                w.x = ((b8 & 1u) ? 0x3F80u : 0u) | ((b8 & 2u) ? 0x3F800000u : 0u);
+                w.y = ((b8 & 4u) ? 0x3F80u : 0u) | ((b8 & 8u) ? 0x3F800000u : 0u);
+                w.z = ((b8 & 16u) ? 0x3F80u : 0u) | ((b8 & 32u) ? 0x3F800000u : 0u);
+                w.w = ((b8 & 64u) ? 0x3F80u : 0u) | ((b8 & 128u) ? 0x3F800000u : 0u);
+                const int cc = (ch & 1) * 4 + c;
+                *reinterpret_cast<uint4*>(panel + tid * 128 + ((cc ^ (tid & 7)) << 4)) = w;
+            }
+        }
+        sm.score[tid] = sc;
+        fence_before();
+        __syncthreads();
+        // ---- softmax over the sample's pairs and g_s: one warp per sample
+        for (int ss = warp; ss < n_s; ss += kAfmTcThreads / 32) {
+            const int r0 = ss * P;
+            float mx = -INFINITY;
+            for (int q = lane; q < P; q += 32) mx = fmaxf(mx, sm.score[r0 + q]);
+            mx = warp_max(mx);
+            float sum = 0.f;
+            for (int q = lane; q < P; q += 32) sum += expf(sm.score[r0 + q] - mx);
+            const float inv = 1.0f / warp_sum(sum);
+            float dsum = 0.f;
+            for (int q = lane; q < P; q += 32) {
+                const float a = expf(sm.score[r0 + q] - mx) * inv;
+                sm.attn[r0 + q] = a;
+                dsum = fmaf(a, sm.ga[r0 + q], dsum);
+            }
+            dsum = warp_sum(dsum);
+            for (int q = lane; q < P; q += 32) sm.gs[r0 + q] = sm.attn[r0 + q] * (sm.ga[r0 + q] - dsum);
+        }
+        __syncthreads();
+        // ---- X line: g_s * [v_hi | v_lo] in b3, [g_s hi, lo, 0...] in the second panel (the old A1 tile)
+        const float gs = on ? sm.gs[tid] : 0.f;
+        const float at = on ? sm.attn[tid] : 0.f;
+        gb2_acc += gs;
+        {
+            float x[KP];
+#pragma unroll
+            for (int d = 0; d < KP; ++d) x[d] = gs * v[d];
+            store_line_split<KP>(sm.b3, tid, x);
+            float one[8] = {gs, gs - __bfloat162float(__float2bfloat16_rn(gs)), 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+            one[0] = __bfloat162float(__float2bfloat16_rn(gs));
+            const float zero[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+            if (KP == 32) {                              // n = 64..79: chunks 0, 1 of the second panel
+                store_chunk(sm.a1, tid, 0, one);
+                store_chunk(sm.a1, tid, 1, zero);
+            } else {                                     // n = 32..47: chunks 4, 5 of the first panel
+                store_chunk(sm.b3, tid, 4, one);
+                store_chunk(sm.b3, tid, 5, zero);
+            }
+        }
+        fence_async_smem();
+        fence_before();
+        __syncthreads();
+        if (tid == 0) {
+            fence_after();
+            // g_v part: mask (K-major, K = a) x B2 -> columns [0, N2)
+            for (int kk = 0; kk < Ap / 16; ++kk)
+                umma_bf16(tmem, umma_desc(smem_u32(sm.a2 + (kk >> 2) * (128 * 128))) + 2 * (kk & 3),
+                          umma_desc(smem_u32(sm.b2t + (kk >> 2) * (64 * 128))) + 2 * (kk & 3), umma_idesc(N2), kk > 0);
+            // U += mask^T X: both operands MN-major, K = the 128 rows of the tile (16 rows = 2048 B per step)
+#pragma unroll
+            for (int kk = 0; kk < 8; ++kk)
+                umma_bf16(tmem + kUOff, umma_desc_mn(smem_u32(sm.a2 + kk * 2048), 128 * 128),
+                          umma_desc_mn(smem_u32(sm.b3 + kk * 2048), 128 * 128),
+                          umma_idesc(N3) | kUmmaAMn | kUmmaBMn, (!first_tile || kk > 0) ? 1u : 0u);
+            umma_commit(sm.bar);
+        }
+        first_tile = false;
+        mbar_wait(sm.bar, phase);
+        phase ^= 1;
+        fence_after();
+        // ---- g_v = a g_out + g_s (mask . B2): staged for the per-field sums
+        {
+            float gv[KP];
+            const float* go = sm.gout[buf] + s * 32;
+            if (KP == 32) {
+                float t0[32], t1[32];
+                tmem_ld32(my_tmem, t0);
+                tmem_ld32(my_tmem + 32, t1);
+#pragma unroll
+                for (int d = 0; d < KP; ++d) gv[d] = fmaf(gs, t0[d] + t1[d], at * (d < D ? go[d] : 0.f));
+            } else {
+                float t0[32];
+                tmem_ld32(my_tmem, t0);
+#pragma unroll
+                for (int d = 0; d < KP; ++d) gv[d] = fmaf(gs, t0[d] + t0[(KP + d) & 31], at * (d < D ? go[d] : 0.f));
+            }
+#pragma unroll
+            for (int c = 0; c < KP / 4; ++c)
+                *reinterpret_cast<float4*>(stage + tid * 32 + 4 * ((c ^ tid) & 7)) =
+                    on ? make_float4(gv[4 * c], gv[4 * c + 1], gv[4 * c + 2], gv[4 * c + 3]) : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+        fence_before();
+        __syncthreads();
+        // g_e[s][f][d] = sum_{g != f} g_v[pair(f,g)][d] * e[s][g][d]
+        for (int item = tid; item < n_s * F * D; item += kAfmTcThreads) {
+            const int d = item % D, sf = item / D, f = sf % F, ss = sf / F;
+            float acc = 0.f;
+            for (int g = 0; g < F; ++g) {
+                if (g == f) continue;
+                const int r = ss * P + sm.pidx[f * F + g];
+                acc = fmaf(stage[r * 32 + 4 * (((d >> 2) ^ r) & 7) + (d & 3)], esm[(ss * F + g) * p.estride + d], acc);
+            }
+            g_rows[(b0 + ss) * F * D + f * D + d] = acc;
+        }
+        __syncthreads();                             // stage (b3), a1, score... are rewritten by the next tile
+    }
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+
+    // ---- this CTA's share of the attention-weight gradients, from U (lane = a)
+    float* outp = partials + (int64_t)blockIdx.x * (A * D + 2 * A + 1);
+    {
+        float u[KP];
+        float u0 = 0.f;
+#pragma unroll
+        for (int d = 0; d < KP; ++d) u[d] = 0.f;
+        if (!first_tile) {
+            fence_after();
+            if (KP == 32) {
+                float t0[32], t1[32], t2[32];
+                tmem_ld32(my_tmem + kUOff, t0);
+                tmem_ld32(my_tmem + kUOff + 32, t1);
+                tmem_ld32(my_tmem + kUOff + 64, t2);
+#pragma unroll
+                for (int d = 0; d < KP; ++d) u[d] = t0[d] + t1[d];
+                u0 = t2[0] + t2[1];
+            } else {
+                float t0[32], t1[32];
+                tmem_ld32(my_tmem + kUOff, t0);
+                tmem_ld32(my_tmem + kUOff + 32, t1);
+#pragma unroll
+                for (int d = 0; d < KP; ++d) u[d] = t0[d] + t0[(KP + d) & 31];
+                u0 = t1[0] + t1[1];
+            }
+        }
+        if (tid < A) {
+            const float w2a = sm.w2[tid];
+            float gw2 = sm.bias[tid] * u0;
+#pragma unroll
+            for (int d = 0; d < KP; ++d)
+                if (d < D) {
+                    outp[tid * D + d] = w2a * u[d];
+                    gw2 = fmaf(__ldg(p.w1 + tid * D + d), u[d], gw2);
+                }
+            outp[A * D + tid]     = w2a * u0;
+            outp[A * D + A + tid] = gw2;
+        }
+    }
+    sm.red[tid] = gb2_acc;
+    __syncthreads();
+    if (tid == 0) {
+        float t = 0.f;
+        for (int i = 0; i < kAfmTcThreads; ++i) t += sm.red[i];
+        outp[A * D + 2 * A] = t;
+    }
+    fence_before();
+    __syncthreads();
+    if (warp == 0) tmem_dealloc(tmem, 256);
+}
+
 }  // namespace tc
 
 static int afm_tc_fill(const rk_field_t* fields, int F, const float* w1, const float* b1, const float* w2,
@@ -266,6 +624,39 @@ int rk_afm_tc_fwd(const rk_field_t* fields, int F, const float* w1, const float*
     kernel<<<(int)grid, tc::kAfmTcThreads, smem, (cudaStream_t)stream_>>>(p, out, err_flag);
     RK_LAUNCH_CHECK();
     return 0;
+}
+
+int rk_afm_tc_bwd_ctas(int64_t B, int F) {
+    if (F < 2 || F > 16 || B <= 0) return 1;
+    int S = rk::tc::kAfmTcRows / (F * (F - 1) / 2);
+    if (S > rk::tc::kAfmTcMaxS) S = rk::tc::kAfmTcMaxS;
+    const int64_t tiles = rk::ceil_div(B, S);
+    const int64_t cap = 2 * (int64_t)rk::sm_count();   // two CTAs per SM: 2 x 256 TMEM columns, ~107 KB of shared memory each
+    return (int)(tiles < cap ? tiles : cap);
+}
+
+int rk_afm_tc_bwd(const rk_field_t* fields, int F, const float* w1, const float* b1, const float* w2,
+                  const float* b2, int A, int64_t B, const float* g_out, float* g_rows, float* g_w1,
+                  float* g_b1, float* g_w2, float* g_b2, float* partials, int n_ctas, int32_t* err_flag,
+                  rk_stream_t stream_) {
+    using namespace rk;
+    tc::AfmTcParams p;
+    if (int rc = afm_tc_fill(fields, F, w1, b1, w2, b2, A, B, &p)) return rc;
+    RK_CHECK_ARG(g_out && g_rows && g_w1 && g_b1 && g_w2 && g_b2 && partials, "afm_tc_bwd: NULL pointer");
+    RK_CHECK_ARG(n_ctas == rk_afm_tc_bwd_ctas(B, F), "afm_tc_bwd: n_ctas %d != rk_afm_tc_bwd_ctas", n_ctas);
+    RK_CHECK_ARG(g_b1 == g_w1 + (size_t)A * p.D && g_w2 == g_b1 + A && g_b2 == g_w2 + A,
+                 "afm_tc_bwd: g_w1|g_b1|g_w2|g_b2 must be one contiguous buffer in that order");
+    RK_CHECK_ARG(((uintptr_t)g_out % 16) == 0, "afm_tc_bwd: g_out must be 16-byte aligned");
+    if (B == 0) return 0;
+    const size_t smem = tc::AfmTcBwdSmem::bytes(p);
+    RK_CHECK_ARG(smem <= 227 * 1024, "afm_tc_bwd: %zu bytes of shared memory", smem);
+    auto kernel = p.Kp == 16 ? tc::afm_bwd_tc_kernel<16> : tc::afm_bwd_tc_kernel<32>;
+    RK_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    cudaStream_t s = (cudaStream_t)stream_;
+    kernel<<<n_ctas, tc::kAfmTcThreads, smem, s>>>(p, g_out, g_rows, partials, err_flag);
+    RK_LAUNCH_CHECK();
+    const int count = A * p.D + 2 * A + 1;
+    return launch_reduce_partials(partials, n_ctas, count, g_w1, s);
 }
 
 }  // extern "C"

@@ -206,6 +206,15 @@ int rk_afm_bwd(const rk_field_t* fields, int F, const float* w1, const float* b1
  * hi.hi + lo.hi + hi.lo, fp32 accumulation in TMEM); same arguments and outputs as rk_afm_fwd. */
 int rk_afm_tc_fwd(const rk_field_t* fields, int F, const float* w1, const float* b1, const float* w2,
                   const float* b2, int A, int64_t B, float* out, int32_t* err_flag, rk_stream_t stream);
+/* The backward on the tensor cores: same arguments and outputs as rk_afm_bwd, with
+ * n_ctas = rk_afm_tc_bwd_ctas(B, F).  The hidden layer only enters through its 0/1 ReLU mask
+ * (exact in bf16), the other operands are split-bf16; the weight-gradient accumulator lives in
+ * TMEM for the life of a CTA and the per-CTA partials are added in a fixed order. */
+int rk_afm_tc_bwd_ctas(int64_t B, int F);
+int rk_afm_tc_bwd(const rk_field_t* fields, int F, const float* w1, const float* b1, const float* w2,
+                  const float* b2, int A, int64_t B, const float* g_out, float* g_rows, float* g_w1,
+                  float* g_b1, float* g_w2, float* g_b2, float* partials, int n_ctas,
+                  int32_t* err_flag, rk_stream_t stream);
 
 /* ---- row-sharded table (BASELINE config 5 "scaled": BST feedid table of 1e8 rows block-
  *      partitioned by row over the ranks; the reference itself is single-process) ------------
