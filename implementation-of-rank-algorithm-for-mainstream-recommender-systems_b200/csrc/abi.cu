@@ -3,6 +3,7 @@
 #include <string.h>
 #include <atomic>
 #include "common.cuh"
+#include "prof.cuh"
 
 namespace rk {
 
@@ -115,3 +116,16 @@ int rk_debug_spin(int us, rk_stream_t stream) {
 }
 
 }  // extern "C"
+
+#ifdef RK_PROFILE
+namespace rk { __device__ unsigned long long g_rk_prof[16]; }
+extern "C" int rk_debug_profile(unsigned long long* out16, int reset) {
+    RK_CUDA(cudaDeviceSynchronize());
+    RK_CUDA(cudaMemcpyFromSymbol(out16, rk::g_rk_prof, sizeof(unsigned long long) * 16));
+    if (reset) {
+        unsigned long long z[16] = {0};
+        RK_CUDA(cudaMemcpyToSymbol(rk::g_rk_prof, z, sizeof(z)));
+    }
+    return 0;
+}
+#endif

@@ -11,6 +11,7 @@
 #include <string.h>
 #include "common.cuh"
 #include "umma.cuh"
+#include "prof.cuh"
 
 namespace rk {
 namespace tc {
@@ -18,6 +19,7 @@ namespace tc {
 constexpr int kAfmTcThreads = 128;
 constexpr int kAfmTcRows    = 128;
 constexpr int kAfmTcMaxS    = 16;
+constexpr int kAfmTcMaxSF   = 64;    // S * F <= 64 for every F in [2,16]
 
 struct AfmTcParams {
     FieldSet     fs;
@@ -32,6 +34,7 @@ struct AfmTcParams {
 struct AfmTcFwdSmem {
     uint8_t *a1, *b1t;              // [128][128 B], [Ap][128 B]  (b1t = W1 as the B operand)
     float   *e[2];                  // gathered rows of the tile, [S][F][estride], double buffered
+    int64_t *ix[2];                 // raw indices of the tiles after next
     float   *bias, *w2, *score, *attn;
     int     *pi, *pj;
     uint64_t* bar;
@@ -43,6 +46,8 @@ struct AfmTcFwdSmem {
         const size_t eb = sizeof(float) * p.S * p.fs.F * p.estride;
         e[0] = (float*)q;  q += eb;
         e[1] = (float*)q;  q += eb;
+        ix[0] = (int64_t*)q;  q += sizeof(int64_t) * kAfmTcMaxSF;
+        ix[1] = (int64_t*)q;  q += sizeof(int64_t) * kAfmTcMaxSF;
         bias = (float*)q;  q += sizeof(float) * p.Ap;
         w2 = (float*)q;    q += sizeof(float) * p.Ap;
         score = (float*)q; q += sizeof(float) * kAfmTcRows;
@@ -54,7 +59,7 @@ struct AfmTcFwdSmem {
     }
     static size_t bytes(const AfmTcParams& p) {
         return 1024 + 2 * 128 * 128 + 2 * sizeof(float) * p.S * p.fs.F * p.estride + sizeof(float) * (2 * p.Ap + 2 * kAfmTcRows) +
-               sizeof(int) * 256 + 16;
+               sizeof(int) * 256 + 16 + 2 * sizeof(int64_t) * 64;
     }
 };
 
@@ -75,18 +80,30 @@ __device__ __forceinline__ void store_line_split(uint8_t* tile, int r, const flo
     }
 }
 
-// Stage the embedding rows of tile `tile` (S samples x F fields) with 16-byte cp.async copies.
-__device__ __forceinline__ void afm_issue_rows(const AfmTcParams& p, float* e, int64_t tile, int tid, int32_t* err_flag) {
+// Input staging, two tiles deep: the indices of tile t+2 are copied to shared memory (8-byte
+// cp.async) while the rows of tile t+1 are gathered with 16-byte cp.async from the indices that
+// landed one tile earlier, all of it issued in the shadow of tile t's first MMA.  Only the very
+// first tile of a CTA reads its indices with ordinary loads.
+__device__ __forceinline__ void afm_issue_idx(const AfmTcParams& p, int64_t* ix, int64_t tile, int tid) {
+    const int F = p.fs.F;
+    const int64_t b0 = tile * p.S;
+    const int n_s = (int)((p.B - b0) < p.S ? (p.B - b0) : p.S);
+    for (int item = tid; item < n_s * F; item += kAfmTcThreads) {
+        const int s = item / F, f = item - s * F;
+        cp_async8(ix + item, p.fs.idx[f] + b0 + s);
+    }
+}
+__device__ __forceinline__ void afm_issue_rows(const AfmTcParams& p, float* e, const int64_t* ix, int64_t tile, int tid,
+                                               int32_t* err_flag) {
     const int F = p.fs.F, c4 = p.D >> 2;
     const int64_t b0 = tile * p.S;
     const int n_s = (int)((p.B - b0) < p.S ? (p.B - b0) : p.S);
     for (int item = tid; item < n_s * F * c4; item += kAfmTcThreads) {
         const int c = item % c4, sf = item / c4, f = sf % F, s = sf / F;
-        const int64_t row = checked_row(__ldg(p.fs.idx[f] + b0 + s), p.fs.rows[f], err_flag);
-        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;"
-                     ::"r"(smem_u32(e + (s * F + f) * p.estride + 4 * c)), "l"(p.fs.weight[f] + row * p.D + 4 * c) : "memory");
+        const int64_t raw = ix ? ix[sf] : __ldg(p.fs.idx[f] + b0 + s);
+        const int64_t row = checked_row(raw, p.fs.rows[f], err_flag);
+        cp_async16(e + (s * F + f) * p.estride + 4 * c, p.fs.weight[f] + row * p.D + 4 * c);
     }
-    asm volatile("cp.async.commit_group;" ::: "memory");
 }
 
 template <int KP>
@@ -95,20 +112,35 @@ afm_fwd_tc_kernel(const __grid_constant__ AfmTcParams p, float* __restrict__ out
     extern __shared__ uint8_t afm_tc_raw[];
     uint8_t* base = afm_tc_raw + ((1024u - (smem_u32(afm_tc_raw) & 1023u)) & 1023u);
     AfmTcFwdSmem sm(base, p);
+    PROF_DECL
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int F = p.fs.F, D = p.D, P = p.P;
     constexpr int LO = KP / 8;                       // 16-byte units from the hi half to the lo half of a line
 
     int64_t tile = blockIdx.x;
-    if (tile < p.n_tiles) afm_issue_rows(p, sm.e[0], tile, tid, err_flag);
+    if (tile < p.n_tiles) {
+        afm_issue_rows(p, sm.e[0], nullptr, tile, tid, err_flag);
+        if (tile + gridDim.x < p.n_tiles) afm_issue_idx(p, sm.ix[1], tile + gridDim.x, tid);
+        cp_async_commit();
+    }
 
     if (tid == 0) mbar_init(sm.bar, 1);
     if (warp == 0) tmem_alloc(sm.tmem_slot, 128);
-    for (int n = tid; n < p.Ap; n += kAfmTcThreads) {            // W1[n][:] -> B operand line n
-        float x[KP];
+    for (int item = tid; item < p.Ap * (KP / 8); item += kAfmTcThreads) {     // W1[n][8c..8c+7] -> B1 line n, chunks c (hi) and KP/8 + c (lo)
+        const int n = item / (KP / 8), c = item - n * (KP / 8);
+        float hi8[8], lo8[8];
 #pragma unroll
-        for (int d = 0; d < KP; ++d) x[d] = (n < p.A && d < D) ? __ldg(p.w1 + n * D + d) : 0.f;
-        store_line_split<KP>(sm.b1t, n, x);
+        for (int h = 0; h < 2; ++h) {
+            float4 w = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (n < p.A && 8 * c + 4 * h < D) w = __ldg(reinterpret_cast<const float4*>(p.w1 + n * D + 8 * c + 4 * h));
+            hi8[4 * h] = w.x; hi8[4 * h + 1] = w.y; hi8[4 * h + 2] = w.z; hi8[4 * h + 3] = w.w;
+        }
+#pragma unroll
+        for (int j = 0; j < 8; ++j) lo8[j] = hi8[j] - __bfloat162float(__float2bfloat16_rn(hi8[j]));
+        store_chunk(sm.b1t, n, c, hi8);
+        store_chunk(sm.b1t, n, KP / 8 + c, lo8);
+    }
+    for (int n = tid; n < p.Ap; n += kAfmTcThreads) {
         sm.bias[n] = n < p.A ? __ldg(p.b1 + n) : 0.f;
         sm.w2[n]   = n < p.A ? __ldg(p.w2 + n) : 0.f;
     }
@@ -129,6 +161,9 @@ afm_fwd_tc_kernel(const __grid_constant__ AfmTcParams p, float* __restrict__ out
     float* pool = reinterpret_cast<float*>(sm.a1);   // [128][32] floats, chunk-swizzled; A1 is free after the MMA
     uint32_t phase = 0;
     int buf = 0;
+    int parts = 1;                                   // power of two, <= 4, parts * S * D <= threads when possible
+    while (parts < 4 && 2 * parts * p.S * D <= kAfmTcThreads) parts <<= 1;
+    PROF(0);
 
     for (; tile < p.n_tiles; tile += gridDim.x, buf ^= 1) {
         const int64_t b0 = tile * p.S;
@@ -136,6 +171,7 @@ afm_fwd_tc_kernel(const __grid_constant__ AfmTcParams p, float* __restrict__ out
         const int n_rows = n_s * P;
         asm volatile("cp.async.wait_group 0;" ::: "memory");
         __syncthreads();                             // rows copied by every thread are visible
+        PROF(1); PROF_COUNT(12);
         // ---- this thread's pair row v = e_i * e_j, split into the A operand line
         const bool on = tid < n_rows;
         const int s = on ? tid / P : 0, pr = on ? tid - s * P : 0;
@@ -159,6 +195,7 @@ afm_fwd_tc_kernel(const __grid_constant__ AfmTcParams p, float* __restrict__ out
         __syncthreads();
         if (tid == 0) {
             fence_after();
+            PROF(2);
 #pragma unroll
             for (int term = 0; term < 3; ++term)         // hi.hi + lo.hi + hi.lo
 #pragma unroll
@@ -168,10 +205,15 @@ afm_fwd_tc_kernel(const __grid_constant__ AfmTcParams p, float* __restrict__ out
             umma_commit(sm.bar);
         }
         // while the tensor core works: the next tile's rows (the other e buffer was last read two barriers ago)
-        if (tile + gridDim.x < p.n_tiles) afm_issue_rows(p, sm.e[buf ^ 1], tile + gridDim.x, tid, err_flag);
+        if (tile + gridDim.x < p.n_tiles) {
+            afm_issue_rows(p, sm.e[buf ^ 1], sm.ix[buf ^ 1], tile + gridDim.x, tid, err_flag);
+            if (tile + 2 * (int64_t)gridDim.x < p.n_tiles) afm_issue_idx(p, sm.ix[buf], tile + 2 * (int64_t)gridDim.x, tid);
+            cp_async_commit();
+        }
         mbar_wait(sm.bar, phase);
         phase ^= 1;
         fence_after();
+        PROF(3);
         float sc = b2;
         for (int ch = 0; ch < p.Ap / 32; ++ch) {
             float h[32];
@@ -182,18 +224,27 @@ afm_fwd_tc_kernel(const __grid_constant__ AfmTcParams p, float* __restrict__ out
         sm.score[tid] = sc;
         fence_before();
         __syncthreads();
+        PROF(4);
         // ---- softmax over the sample's P rows: one warp per sample
         for (int ss = warp; ss < n_s; ss += kAfmTcThreads / 32) {
             const int r0 = ss * P;
             float mx = -INFINITY;
             for (int q = lane; q < P; q += 32) mx = fmaxf(mx, sm.score[r0 + q]);
             mx = warp_max(mx);
-            float sum = 0.f;
-            for (int q = lane; q < P; q += 32) sum += expf(sm.score[r0 + q] - mx);
+            float ex[4], sum = 0.f;
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const int q = lane + 32 * i;
+                ex[i] = q < P ? expf(sm.score[r0 + q] - mx) : 0.f;
+                sum += ex[i];
+            }
             const float inv = 1.0f / warp_sum(sum);
-            for (int q = lane; q < P; q += 32) sm.attn[r0 + q] = expf(sm.score[r0 + q] - mx) * inv;
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+                if (lane + 32 * i < P) sm.attn[r0 + lane + 32 * i] = ex[i] * inv;
         }
         __syncthreads();
+        PROF(5);
         // ---- out[s][:] = sum_p a_p v_p through the (now free) A tile
         {
             const float a = on ? sm.attn[tid] : 0.f;
@@ -203,19 +254,26 @@ afm_fwd_tc_kernel(const __grid_constant__ AfmTcParams p, float* __restrict__ out
                     make_float4(a * v[4 * c], a * v[4 * c + 1], a * v[4 * c + 2], a * v[4 * c + 3]);
         }
         __syncthreads();
-        for (int item = tid; item < n_s * D; item += kAfmTcThreads) {
-            const int ss = item / D, d = item - ss * D;
+        PROF(6);
+        // `parts` lanes share one output: lane part adds pairs part, part + parts, ...; fixed shuffle tree
+        for (int it0 = 0; it0 < n_s * D * parts; it0 += kAfmTcThreads) {
+            const int item = it0 + tid, o = item / parts, part = item - o * parts;
+            const int ss = o / D, d = o - ss * D;
             float acc = 0.f;
-            for (int q = 0; q < P; ++q) {
-                const int r = ss * P + q;
-                acc += pool[r * 32 + 4 * (((d >> 2) ^ r) & 7) + (d & 3)];
-            }
-            out[(b0 + ss) * D + d] = acc;
+            if (o < n_s * D)
+                for (int q = part; q < P; q += parts) {
+                    const int r = ss * P + q;
+                    acc += pool[r * 32 + 4 * (((d >> 2) ^ r) & 7) + (d & 3)];
+                }
+            for (int w = parts >> 1; w > 0; w >>= 1) acc += __shfl_xor_sync(kFull, acc, w);
+            if (o < n_s * D && part == 0) out[(b0 + ss) * D + d] = acc;
         }
         __syncthreads();                             // pool / score / attn are rewritten by the next tile
+        PROF(7);
     }
     asm volatile("cp.async.wait_group 0;" ::: "memory");
     fence_before();
+    PROF_END;
     __syncthreads();
     if (warp == 0) tmem_dealloc(tmem, 128);
 }
@@ -235,6 +293,7 @@ afm_fwd_tc_kernel(const __grid_constant__ AfmTcParams p, float* __restrict__ out
 struct AfmTcBwdSmem {
     uint8_t *b3, *a1, *b1t, *a2, *b2t;   // b3 panel 0 and a1 are adjacent: a1 doubles as b3's second panel
     float   *e[2], *gout[2];
+    int64_t *ix[2];
     float   *bias, *w2, *score, *attn, *ga, *gs, *dot, *red;
     int     *pi, *pj, *pidx;
     uint64_t* bar;
@@ -251,6 +310,8 @@ struct AfmTcBwdSmem {
         e[1] = (float*)q;  q += eb;
         gout[0] = (float*)q;  q += sizeof(float) * p.S * 32;
         gout[1] = (float*)q;  q += sizeof(float) * p.S * 32;
+        ix[0] = (int64_t*)q;  q += sizeof(int64_t) * kAfmTcMaxSF;
+        ix[1] = (int64_t*)q;  q += sizeof(int64_t) * kAfmTcMaxSF;
         bias = (float*)q;  q += sizeof(float) * 128;
         w2 = (float*)q;    q += sizeof(float) * 128;
         score = (float*)q; q += sizeof(float) * kAfmTcRows;
@@ -268,7 +329,7 @@ struct AfmTcBwdSmem {
     static size_t bytes(const AfmTcParams& p) {
         return 1024 + 3 * 128 * 128 + 2 * 128 * 128 + 2 * 64 * 128 + 2 * sizeof(float) * p.S * p.fs.F * p.estride +
                2 * sizeof(float) * p.S * 32 + sizeof(float) * (2 * 128 + 4 * kAfmTcRows + kAfmTcMaxS + kAfmTcThreads) +
-               sizeof(int) * 512 + 16;
+               sizeof(int) * 512 + 16 + 2 * sizeof(int64_t) * 64;
     }
 };
 
@@ -290,6 +351,7 @@ afm_bwd_tc_kernel(const __grid_constant__ AfmTcParams p, const float* __restrict
     extern __shared__ uint8_t afm_tc_raw[];
     uint8_t* base = afm_tc_raw + ((1024u - (smem_u32(afm_tc_raw) & 1023u)) & 1023u);
     AfmTcBwdSmem sm(base, p);
+    PROF_DECL
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int F = p.fs.F, D = p.D, P = p.P, A = p.A, Ap = p.Ap;
     constexpr int LO = KP / 8;                       // 16-byte units from the hi half to the lo half of a line
@@ -300,15 +362,27 @@ afm_bwd_tc_kernel(const __grid_constant__ AfmTcParams p, const float* __restrict
     int64_t tile = blockIdx.x;
     if (tile < p.n_tiles) {
         afm_issue_gout(p, sm.gout[0], g_out, tile, tid);
-        afm_issue_rows(p, sm.e[0], tile, tid, err_flag);
+        afm_issue_rows(p, sm.e[0], nullptr, tile, tid, err_flag);
+        if (tile + gridDim.x < p.n_tiles) afm_issue_idx(p, sm.ix[1], tile + gridDim.x, tid);
+        cp_async_commit();
     }
     if (tid == 0) mbar_init(sm.bar, 1);
     if (warp == 0) tmem_alloc(sm.tmem_slot, 256);
-    for (int n = tid; n < 128; n += kAfmTcThreads) {             // W1[n][:] -> B1 line n; bias, w2
-        float x[KP];
+    for (int item = tid; item < 128 * (KP / 8); item += kAfmTcThreads) {     // W1[n][8c..8c+7] -> B1 line n, chunks c (hi) and KP/8 + c (lo)
+        const int n = item / (KP / 8), c = item - n * (KP / 8);
+        float hi8[8], lo8[8];
 #pragma unroll
-        for (int d = 0; d < KP; ++d) x[d] = (n < A && d < D) ? __ldg(p.w1 + n * D + d) : 0.f;
-        store_line_split<KP>(sm.b1t, n, x);
+        for (int h = 0; h < 2; ++h) {
+            float4 w = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (n < A && 8 * c + 4 * h < D) w = __ldg(reinterpret_cast<const float4*>(p.w1 + n * D + 8 * c + 4 * h));
+            hi8[4 * h] = w.x; hi8[4 * h + 1] = w.y; hi8[4 * h + 2] = w.z; hi8[4 * h + 3] = w.w;
+        }
+#pragma unroll
+        for (int j = 0; j < 8; ++j) lo8[j] = hi8[j] - __bfloat162float(__float2bfloat16_rn(hi8[j]));
+        store_chunk(sm.b1t, n, c, hi8);
+        store_chunk(sm.b1t, n, KP / 8 + c, lo8);
+    }
+    for (int n = tid; n < 128; n += kAfmTcThreads) {
         sm.bias[n] = n < A ? __ldg(p.b1 + n) : 0.f;
         sm.w2[n]   = n < A ? __ldg(p.w2 + n) : 0.f;
     }
@@ -350,6 +424,7 @@ afm_bwd_tc_kernel(const __grid_constant__ AfmTcParams p, const float* __restrict
     int buf = 0;
     bool first_tile = true;
     float gb2_acc = 0.f;
+    PROF(0);
 
     for (; tile < p.n_tiles; tile += gridDim.x, buf ^= 1) {
         const int64_t b0 = tile * p.S;
@@ -357,6 +432,7 @@ afm_bwd_tc_kernel(const __grid_constant__ AfmTcParams p, const float* __restrict
         const int n_rows = n_s * P;
         asm volatile("cp.async.wait_group 0;" ::: "memory");
         __syncthreads();
+        PROF(1); PROF_COUNT(12);
         const bool on = tid < n_rows;
         const int s = on ? tid / P : 0, pr = on ? tid - s * P : 0;
         const float* esm = sm.e[buf];
@@ -386,6 +462,7 @@ afm_bwd_tc_kernel(const __grid_constant__ AfmTcParams p, const float* __restrict
         __syncthreads();
         if (tid == 0) {                                  // pre = V W1^T
             fence_after();
+            PROF(2);
 #pragma unroll
             for (int term = 0; term < 3; ++term)
 #pragma unroll
@@ -396,11 +473,14 @@ afm_bwd_tc_kernel(const __grid_constant__ AfmTcParams p, const float* __restrict
         }
         if (tile + gridDim.x < p.n_tiles) {              // while the tensor core works: the next tile's inputs
             afm_issue_gout(p, sm.gout[buf ^ 1], g_out, tile + gridDim.x, tid);
-            afm_issue_rows(p, sm.e[buf ^ 1], tile + gridDim.x, tid, err_flag);
+            afm_issue_rows(p, sm.e[buf ^ 1], sm.ix[buf ^ 1], tile + gridDim.x, tid, err_flag);
+            if (tile + 2 * (int64_t)gridDim.x < p.n_tiles) afm_issue_idx(p, sm.ix[buf], tile + 2 * (int64_t)gridDim.x, tid);
+            cp_async_commit();
         }
         mbar_wait(sm.bar, phase);
         phase ^= 1;
         fence_after();
+        PROF(3);
         // ---- score and the 0/1 mask line (bf16 1.0 = 0x3F80)
         float sc = b2;
         for (int ch = 0; ch < Ap / 32; ++ch) {
@@ -429,25 +509,38 @@ afm_bwd_tc_kernel(const __grid_constant__ AfmTcParams p, const float* __restrict
         sm.score[tid] = sc;
         fence_before();
         __syncthreads();
+        PROF(4);
         // ---- softmax over the sample's pairs and g_s: one warp per sample
         for (int ss = warp; ss < n_s; ss += kAfmTcThreads / 32) {
             const int r0 = ss * P;
             float mx = -INFINITY;
             for (int q = lane; q < P; q += 32) mx = fmaxf(mx, sm.score[r0 + q]);
             mx = warp_max(mx);
-            float sum = 0.f;
-            for (int q = lane; q < P; q += 32) sum += expf(sm.score[r0 + q] - mx);
+            float ex[4], gq[4], sum = 0.f;
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const int q = lane + 32 * i;
+                ex[i] = q < P ? expf(sm.score[r0 + q] - mx) : 0.f;
+                gq[i] = q < P ? sm.ga[r0 + q] : 0.f;
+                sum += ex[i];
+            }
             const float inv = 1.0f / warp_sum(sum);
             float dsum = 0.f;
-            for (int q = lane; q < P; q += 32) {
-                const float a = expf(sm.score[r0 + q] - mx) * inv;
-                sm.attn[r0 + q] = a;
-                dsum = fmaf(a, sm.ga[r0 + q], dsum);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                ex[i] *= inv;
+                dsum = fmaf(ex[i], gq[i], dsum);
             }
             dsum = warp_sum(dsum);
-            for (int q = lane; q < P; q += 32) sm.gs[r0 + q] = sm.attn[r0 + q] * (sm.ga[r0 + q] - dsum);
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+                if (lane + 32 * i < P) {
+                    sm.attn[r0 + lane + 32 * i] = ex[i];
+                    sm.gs[r0 + lane + 32 * i]   = ex[i] * (gq[i] - dsum);
+                }
         }
         __syncthreads();
+        PROF(5);
         // ---- X line: g_s * [v_hi | v_lo] in b3, [g_s hi, lo, 0...] in the second panel (the old A1 tile)
         const float gs = on ? sm.gs[tid] : 0.f;
         const float at = on ? sm.attn[tid] : 0.f;
@@ -473,6 +566,7 @@ afm_bwd_tc_kernel(const __grid_constant__ AfmTcParams p, const float* __restrict
         __syncthreads();
         if (tid == 0) {
             fence_after();
+            PROF(6);
             // g_v part: mask (K-major, K = a) x B2 -> columns [0, N2)
             for (int kk = 0; kk < Ap / 16; ++kk)
                 umma_bf16(tmem, umma_desc(smem_u32(sm.a2 + (kk >> 2) * (128 * 128))) + 2 * (kk & 3),
@@ -489,6 +583,7 @@ afm_bwd_tc_kernel(const __grid_constant__ AfmTcParams p, const float* __restrict
         mbar_wait(sm.bar, phase);
         phase ^= 1;
         fence_after();
+        PROF(7);
         // ---- g_v = a g_out + g_s (mask . B2): staged for the per-field sums
         {
             float gv[KP];
@@ -512,18 +607,25 @@ afm_bwd_tc_kernel(const __grid_constant__ AfmTcParams p, const float* __restrict
         }
         fence_before();
         __syncthreads();
+        PROF(8);
         // g_e[s][f][d] = sum_{g != f} g_v[pair(f,g)][d] * e[s][g][d]
-        for (int item = tid; item < n_s * F * D; item += kAfmTcThreads) {
-            const int d = item % D, sf = item / D, f = sf % F, ss = sf / F;
-            float acc = 0.f;
-            for (int g = 0; g < F; ++g) {
-                if (g == f) continue;
-                const int r = ss * P + sm.pidx[f * F + g];
-                acc = fmaf(stage[r * 32 + 4 * (((d >> 2) ^ r) & 7) + (d & 3)], esm[(ss * F + g) * p.estride + d], acc);
+        // one warp per (sample, field), lane = d: pair rows and partner rows are warp-uniform
+        for (int sf = warp; sf < n_s * F; sf += kAfmTcThreads / 32) {
+            const int ss = sf / F, f = sf - ss * F;
+            if (lane < D) {
+                const int d = lane;
+                float acc = 0.f;
+#pragma unroll 3
+                for (int g = 0; g < F; ++g) {
+                    if (g == f) continue;
+                    const int r = ss * P + sm.pidx[f * F + g];
+                    acc = fmaf(stage[r * 32 + 4 * (((d >> 2) ^ r) & 7) + (d & 3)], esm[(ss * F + g) * p.estride + d], acc);
+                }
+                g_rows[(b0 + ss) * F * D + f * D + d] = acc;
             }
-            g_rows[(b0 + ss) * F * D + f * D + d] = acc;
         }
         __syncthreads();                             // stage (b3), a1, score... are rewritten by the next tile
+        PROF(9);
     }
     asm volatile("cp.async.wait_group 0;" ::: "memory");
 
@@ -573,6 +675,8 @@ afm_bwd_tc_kernel(const __grid_constant__ AfmTcParams p, const float* __restrict
         for (int i = 0; i < kAfmTcThreads; ++i) t += sm.red[i];
         outp[A * D + 2 * A] = t;
     }
+    PROF(10);
+    PROF_END;
     fence_before();
     __syncthreads();
     if (warp == 0) tmem_dealloc(tmem, 256);

@@ -17,6 +17,7 @@
 #include <cuda_bf16.h>
 #include "tile_gemm.cuh"
 #include "umma.cuh"
+#include "prof.cuh"
 
 namespace rk {
 
@@ -647,9 +648,6 @@ __device__ __forceinline__ void wait_rows() { asm volatile("cp.async.wait_group 
 // 8-byte cp.async copies: issued one group ahead (during the last tile of the previous group), so
 // that a group starts with its indices in shared memory and pays one memory latency (the rows)
 // instead of an index -> row chain per feature.
-__device__ __forceinline__ void cp_async8(const void* dst_smem, const void* src) {
-    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(smem_u32(dst_smem)), "l"(src) : "memory");
-}
 __device__ __forceinline__ void issue_idx(const DinParams& p, const TcFwdSmem& sm, int64_t group, int tid) {
     const int64_t b0 = group * kTcGroup;
     const int n = (int)((p.B - b0) < kTcGroup ? (p.B - b0) : kTcGroup);
@@ -665,19 +663,6 @@ __device__ __forceinline__ void issue_idx(const DinParams& p, const TcFwdSmem& s
     asm volatile("cp.async.commit_group;" ::: "memory");
 }
 
-#ifdef RK_DIN_PROFILE
-__device__ unsigned long long g_din_prof[16];
-#define PROF_DECL __shared__ unsigned long long prof_acc[16]; long long prof_t0 = clock64(); const long long prof_start = prof_t0; \
-    if (threadIdx.x < 16) prof_acc[threadIdx.x] = 0;
-#define PROF(i) do { if (threadIdx.x == 0) { const long long t_ = clock64(); prof_acc[i] += t_ - prof_t0; prof_t0 = t_; } } while (0)
-#define PROF_COUNT(i) do { if (threadIdx.x == 0) prof_acc[i] += 1; } while (0)
-#define PROF_END do { if (threadIdx.x == 0) { prof_acc[11] = clock64() - prof_start; for (int i_ = 0; i_ < 16; ++i_) atomicAdd(&g_din_prof[i_], prof_acc[i_]); } } while (0)
-#else
-#define PROF_DECL
-#define PROF(i)
-#define PROF_COUNT(i)
-#define PROF_END
-#endif
 
 __global__ void __launch_bounds__(kTcThreads)
 din_fwd_tc_kernel(const __grid_constant__ DinParams p, float* __restrict__ concat_all,
@@ -1519,15 +1504,3 @@ int rk_din_bwd(const rk_din_args_t* args, const float* concat_all, const float* 
 }
 
 }  // extern "C"
-
-#ifdef RK_DIN_PROFILE
-extern "C" int rk_debug_din_profile(unsigned long long* out16, int reset) {
-    RK_CUDA(cudaDeviceSynchronize());
-    RK_CUDA(cudaMemcpyFromSymbol(out16, rk::tc::g_din_prof, sizeof(unsigned long long) * 16));
-    if (reset) {
-        unsigned long long z[16] = {0};
-        RK_CUDA(cudaMemcpyToSymbol(rk::tc::g_din_prof, z, sizeof(z)));
-    }
-    return 0;
-}
-#endif

@@ -126,6 +126,16 @@ __device__ __forceinline__ uint64_t umma_desc_mn(uint32_t smem_addr, uint32_t mn
     d |= (uint64_t)2 << 61;
     return d;
 }
+// asynchronous global -> shared copies (LDGSTS); completion through cp.async.commit_group / wait_group
+__device__ __forceinline__ void cp_async8(const void* dst_smem, const void* src) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(smem_u32(dst_smem)), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async16(const void* dst_smem, const void* src) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(dst_smem)), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
+
 // instruction-descriptor bits selecting MN-major A / B
 constexpr uint32_t kUmmaAMn = 1u << 15;
 constexpr uint32_t kUmmaBMn = 1u << 16;
