@@ -393,22 +393,6 @@ def run_reference(args, wl):
 
 
 # ------------------------------------------------------------------------------- our arm
-def batch_bytes(batch):
-    n = 0
-    for v in batch.values():
-        if torch.is_tensor(v):
-            n += v.numel() * v.element_size()
-        elif isinstance(v, dict):
-            n += batch_bytes(v)
-    return n
-
-
-def pin(batch):
-    if torch.is_tensor(batch):
-        return batch.pin_memory()
-    return {k: pin(v) for k, v in batch.items()}
-
-
 class Stepper:
     """One training step (zero_grad, forward, loss, backward) on static device buffers, replayed
     from a CUDA graph (default) or run eagerly (--no-graph).  The per-call random weights of
@@ -417,7 +401,9 @@ class Stepper:
 
     def __init__(self, model, wl, example, use_graph, reducer):
         self.model, self.wl, self.reducer = model, wl, reducer
-        self.static = clone_batch(example)
+        from rank_b200.staging import PackedBatch
+        self.packed = PackedBatch.like(example.host_views, example.device)   # fixed addresses: graph inputs
+        self.static = self.packed.device_views
         self.has_ephemeral = hasattr(model, "draw_ephemeral")
         self.graph = None
         self.grads = None
@@ -445,8 +431,10 @@ class Stepper:
         self.loss = self.wl.loss(self.model, self.static)
         self.loss.backward()
 
-    def load(self, batch):
-        copy_batch(self.static, batch)
+    def load(self, packed, from_host=False):
+        """ONE copy of the whole packed batch into the static inputs: pinned host -> device when
+        `from_host`, device -> device otherwise."""
+        self.packed.dev.copy_(packed.host if from_host else packed.dev, non_blocking=True)
 
     def run(self, seed):
         if self.graph is None:
@@ -461,18 +449,6 @@ class Stepper:
         if self.reducer is not None:
             self.reducer.allreduce(grads)
         return self.loss
-
-
-def clone_batch(b):
-    return b.clone() if torch.is_tensor(b) else {k: clone_batch(v) for k, v in b.items()}
-
-
-def copy_batch(dst, src):
-    if torch.is_tensor(dst):
-        dst.copy_(src, non_blocking=True)
-    else:
-        for k in dst:
-            copy_batch(dst[k], src[k])
 
 
 def run_ours(args, wl):
@@ -497,10 +473,17 @@ def run_ours(args, wl):
     reducer = GradientAllReducer(model) if world > 1 else None
 
     n_pool = 4
-    host = [pin(wl.make_batch(B, 1000 + 17 * rank + i)) for i in range(n_pool)]
-    resident = [synthetic.to_device(b, dev) for b in host]
+    # every batch of the pool is collated once into a packed pinned buffer (rank_b200.staging) and
+    # also kept on the device: `value` steps copy device -> device (untimed), `e2e` steps do the one
+    # host -> device copy inside the timed region
+    from rank_b200.staging import PackedBatch
+    raw = [wl.make_batch(B, 1000 + 17 * rank + i) for i in range(n_pool)]
+    pool = [PackedBatch.like(b, dev).fill(b) for b in raw]
+    for pb in pool:
+        pb.to_device()
+    torch.cuda.synchronize()
     flush = torch.empty(L2_FLUSH_BYTES, dtype=torch.uint8, device=dev)
-    stepper = Stepper(model, wl, resident[0], not args.no_graph, reducer)
+    stepper = Stepper(model, wl, pool[0], not args.no_graph, reducer)
 
     def barrier():
         if world > 1:
@@ -515,12 +498,12 @@ def run_ours(args, wl):
             s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             if from_host:
                 s.record()
-                stepper.load(host[i % n_pool])                       # H2D of this step's inputs (pinned)
+                stepper.load(pool[i % n_pool], from_host=True)       # ONE H2D copy of this step's inputs (pinned)
                 loss = stepper.run(first_seed + i)
                 loss_host = loss.detach().to("cpu", non_blocking=True)   # D2H read of the step's result
                 e.record()
             else:
-                stepper.load(resident[i % n_pool])                   # device-to-device, untimed
+                stepper.load(pool[i % n_pool])                       # device-to-device, untimed
                 s.record()
                 loss = stepper.run(first_seed + i)
                 e.record()
@@ -530,13 +513,13 @@ def run_ours(args, wl):
 
     with ClockSampler(local) as clocks:      # started before the warm-up, sampled through the timed region
         for i in range(args.warmup):
-            stepper.load(resident[i % n_pool])
+            stepper.load(pool[i % n_pool])
             stepper.run(i)
         if world > 1:
             # NCCL builds its channels lazily over the first collectives: settle them (and the host
             # threads of all ranks) before the timed region, beyond the W model steps above
             for i in range(10):
-                stepper.load(resident[i % n_pool])
+                stepper.load(pool[i % n_pool])
                 stepper.run(100 + i)
                 barrier()
         barrier()
@@ -558,14 +541,14 @@ def run_ours(args, wl):
 
     # Per-call device times of the hot path: eager steps queued behind a spin kernel, so the
     # kernels run back to back and the events bracketing each ABI call see device time only.
-    eager = Stepper(model, wl, resident[0], False, None)
+    eager = Stepper(model, wl, pool[0], False, None)
     if hasattr(model, "ephemeral_frozen"):
         model.ephemeral_frozen = False
     from rank_b200 import sparse
     sparse.PLAN_ON_SIDE_STREAM = False      # time the occurrence plan in-stream, not overlapped
     with _lib.CallTimer() as ct:
         for i in range(args.steps):
-            eager.load(resident[i % n_pool])
+            eager.load(pool[i % n_pool])
             flush.fill_(i & 0xff)
             _lib.check(lib.rk_debug_spin(4000, _lib.stream_ptr()), "rk_debug_spin")
             eager.run(30_000 + i)
@@ -575,7 +558,7 @@ def run_ours(args, wl):
     # previous step's buffers still in the 126 MB L2); reported next to the flushed figures
     with _lib.CallTimer() as ct_warm:
         for i in range(args.steps):
-            eager.load(resident[i % n_pool])
+            eager.load(pool[i % n_pool])
             _lib.check(lib.rk_debug_spin(4000, _lib.stream_ptr()), "rk_debug_spin")
             eager.run(40_000 + i)
             torch.cuda.synchronize()
@@ -604,7 +587,8 @@ def run_ours(args, wl):
                        "indices": "zipf(1.05), fresh batch each step from a pool of 4"},
             "clocks": clocks.summary(),
             "e2e": {"value": world * B * args.steps / (e2e_ms / 1e3), "unit": "samples/s",
-                    "h2d_bytes_per_step": batch_bytes(host[0]), "d2h_bytes_per_step": 4},
+                    "h2d_bytes_per_step": pool[0].nbytes, "d2h_bytes_per_step": 4,
+                    "h2d_copies_per_step": 1, "h2d_payload_bytes": pool[0].payload_bytes},
             "gpu_launches": int(launches),
             "roofline": {"bound": wl.bound, "achieved": achieved, "peak": pk["hbm_gbs"], "unit": "GB/s",
                          "frac": achieved / pk["hbm_gbs"], "traffic": traffic, "traffic_by_kernel": traffic_by,
@@ -634,7 +618,8 @@ def run_ours(args, wl):
 
 def stepper_launches_per_replay(stepper, lib):
     """Kernels of librank_b200 inside one captured step = what one eager step launches."""
-    probe = Stepper(stepper.model, stepper.wl, stepper.static, False, None)
+    probe = Stepper(stepper.model, stepper.wl, stepper.packed, False, None)
+    probe.load(stepper.packed)
     frozen = getattr(stepper.model, "ephemeral_frozen", None)
     n0 = lib.rk_launch_count()
     probe.run(1)
