@@ -8,6 +8,7 @@
 // Operand tiles: one 128-byte line per row holding [hi(Kp) | lo(Kp)] bf16 (Kp = D rounded up to
 // 16, <= 32), so the three split terms are three (A k-slice, B k-slice) pairings of the same two
 // tiles.  HBM traffic is the same as the SIMT kernel's (idx + rows in, out written once).
+#include <stdlib.h>
 #include <string.h>
 #include "common.cuh"
 #include "umma.cuh"
@@ -161,8 +162,9 @@ afm_fwd_tc_kernel(const __grid_constant__ AfmTcParams p, float* __restrict__ out
     float* pool = reinterpret_cast<float*>(sm.a1);   // [128][32] floats, chunk-swizzled; A1 is free after the MMA
     uint32_t phase = 0;
     int buf = 0;
-    int parts = 1;                                   // power of two, <= 4, parts * S * D <= threads when possible
-    while (parts < 4 && 2 * parts * p.S * D <= kAfmTcThreads) parts <<= 1;
+    const int c4 = D >> 2;
+    int parts = 1;                                   // power of two, <= 8, parts * S * D/4 <= threads when possible
+    while (parts < 8 && 2 * parts * p.S * c4 <= kAfmTcThreads) parts <<= 1;
     PROF(0);
 
     for (; tile < p.n_tiles; tile += gridDim.x, buf ^= 1) {
@@ -215,11 +217,17 @@ afm_fwd_tc_kernel(const __grid_constant__ AfmTcParams p, float* __restrict__ out
         fence_after();
         PROF(3);
         float sc = b2;
-        for (int ch = 0; ch < p.Ap / 32; ++ch) {
-            float h[32];
-            tmem_ld32(my_tmem + 32 * ch, h);
+        for (int ch = 0; ch < p.Ap / 64; ++ch) {
+            float h[64];
+            tmem_ld64(my_tmem + 64 * ch, h);
 #pragma unroll
-            for (int j = 0; j < 32; ++j) sc = fmaf(fmaxf(h[j] + sm.bias[32 * ch + j], 0.f), sm.w2[32 * ch + j], sc);
+            for (int j = 0; j < 64; ++j) sc = fmaf(fmaxf(h[j] + sm.bias[64 * ch + j], 0.f), sm.w2[64 * ch + j], sc);
+        }
+        if (p.Ap & 32) {
+            float h[32];
+            tmem_ld32(my_tmem + (p.Ap - 32), h);
+#pragma unroll
+            for (int j = 0; j < 32; ++j) sc = fmaf(fmaxf(h[j] + sm.bias[p.Ap - 32 + j], 0.f), sm.w2[p.Ap - 32 + j], sc);
         }
         sm.score[tid] = sc;
         fence_before();
@@ -255,18 +263,23 @@ afm_fwd_tc_kernel(const __grid_constant__ AfmTcParams p, float* __restrict__ out
         }
         __syncthreads();
         PROF(6);
-        // `parts` lanes share one output: lane part adds pairs part, part + parts, ...; fixed shuffle tree
-        for (int it0 = 0; it0 < n_s * D * parts; it0 += kAfmTcThreads) {
+        // `parts` adjacent lanes share one 16-byte output chunk: lane `part` adds pairs part, part + parts, ...
+        // and the parts are folded by a fixed shuffle tree
+        for (int it0 = 0; it0 < n_s * c4 * parts; it0 += kAfmTcThreads) {
             const int item = it0 + tid, o = item / parts, part = item - o * parts;
-            const int ss = o / D, d = o - ss * D;
-            float acc = 0.f;
-            if (o < n_s * D)
+            const int ss = o / c4, c = o - ss * c4;
+            float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (o < n_s * c4)
                 for (int q = part; q < P; q += parts) {
                     const int r = ss * P + q;
-                    acc += pool[r * 32 + 4 * (((d >> 2) ^ r) & 7) + (d & 3)];
+                    const float4 x = *reinterpret_cast<const float4*>(pool + r * 32 + 4 * ((c ^ r) & 7));
+                    acc.x += x.x; acc.y += x.y; acc.z += x.z; acc.w += x.w;
                 }
-            for (int w = parts >> 1; w > 0; w >>= 1) acc += __shfl_xor_sync(kFull, acc, w);
-            if (o < n_s * D && part == 0) out[(b0 + ss) * D + d] = acc;
+            for (int w = parts >> 1; w > 0; w >>= 1) {
+                acc.x += __shfl_xor_sync(kFull, acc.x, w); acc.y += __shfl_xor_sync(kFull, acc.y, w);
+                acc.z += __shfl_xor_sync(kFull, acc.z, w); acc.w += __shfl_xor_sync(kFull, acc.w, w);
+            }
+            if (o < n_s * c4 && part == 0) *reinterpret_cast<float4*>(out + (b0 + ss) * D + 4 * c) = acc;
         }
         __syncthreads();                             // pool / score / attn are rewritten by the next tile
         PROF(7);
@@ -353,7 +366,7 @@ afm_bwd_tc_kernel(const __grid_constant__ AfmTcParams p, const float* __restrict
     AfmTcBwdSmem sm(base, p);
     PROF_DECL
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int F = p.fs.F, D = p.D, P = p.P, A = p.A, Ap = p.Ap;
+    const int F = p.fs.F, D = p.D, P = p.P, A = p.A, Ap = p.Ap, c4 = p.D >> 2;
     constexpr int LO = KP / 8;                       // 16-byte units from the hi half to the lo half of a line
     constexpr int N2 = 2 * KP;                       // g_v product: [hi | lo] along N
     constexpr int N3 = 2 * KP + 16;                  // U product:   [v_hi | v_lo | 1_hi, 1_lo, 0 ...]
@@ -405,11 +418,15 @@ afm_bwd_tc_kernel(const __grid_constant__ AfmTcParams p, const float* __restrict
     if (tid == 0) {
         int q = 0;
         for (int i = 0; i < F; ++i)
-            for (int j = i + 1; j < F; ++j) {
-                sm.pi[q] = i; sm.pj[q] = j;
-                sm.pidx[i * F + j] = q; sm.pidx[j * F + i] = q;
-                ++q;
+            for (int j = i + 1; j < F; ++j) { sm.pi[q] = i; sm.pj[q] = j; ++q; }
+        for (int f = 0; f < F; ++f) {                    // pidx[f][k] = k-th partner of f | its pair row << 8
+            int k = 0;
+            for (int g = 0; g < F; ++g) {
+                if (g == f) continue;
+                const int i = f < g ? f : g, j = f < g ? g : f;
+                sm.pidx[f * 16 + k++] = g | ((i * (2 * F - i - 1) / 2 + (j - i - 1)) << 8);
             }
+        }
     }
     fence_async_smem();
     fence_before();
@@ -483,27 +500,41 @@ afm_bwd_tc_kernel(const __grid_constant__ AfmTcParams p, const float* __restrict
         PROF(3);
         // ---- score and the 0/1 mask line (bf16 1.0 = 0x3F80)
         float sc = b2;
-        for (int ch = 0; ch < Ap / 32; ++ch) {
-            float h[32];
-            tmem_ld32(my_tmem + 32 * ch, h);
-            uint32_t bits = 0;
+        for (int ch = 0; ch < Ap / 64; ++ch) {           // one 64-column panel of the mask per TMEM load
+            float h[64];
+            tmem_ld64(my_tmem + 64 * ch, h);
+            uint8_t* panel = sm.a2 + ch * (128 * 128);
 #pragma unroll
-            for (int j = 0; j < 32; ++j) {
-                const float x = h[j] + sm.bias[32 * ch + j];
-                bits |= (x > 0.f ? 1u : 0u) << j;
-                sc = fmaf(fmaxf(x, 0.f), sm.w2[32 * ch + j], sc);
+            for (int c = 0; c < 8; ++c) {
+                uint32_t w[4];
+#pragma unroll
+                for (int j2 = 0; j2 < 4; ++j2) {
+                    const int j = 8 * c + 2 * j2;
+                    const float x0 = h[j] + sm.bias[64 * ch + j], x1 = h[j + 1] + sm.bias[64 * ch + j + 1];
+                    sc = fmaf(fmaxf(x0, 0.f), sm.w2[64 * ch + j], sc);
+                    sc = fmaf(fmaxf(x1, 0.f), sm.w2[64 * ch + j + 1], sc);
+                    w[j2] = (x0 > 0.f ? 0x3F80u : 0u) | (x1 > 0.f ? 0x3F800000u : 0u);
+                }
+                *reinterpret_cast<uint4*>(panel + tid * 128 + ((c ^ (tid & 7)) << 4)) = make_uint4(w[0], w[1], w[2], w[3]);
             }
-            uint8_t* panel = sm.a2 + (ch >> 1) * (128 * 128);
+        }
+        if (Ap & 32) {                                   // Ap = 32 or 96: the last 32 columns
+            float h[32];
+            tmem_ld32(my_tmem + (Ap - 32), h);
+            uint8_t* panel = sm.a2 + ((Ap - 32) >> 6) * (128 * 128);
 #pragma unroll
             for (int c = 0; c < 4; ++c) {
-                uint4 w;
-                const uint32_t b8 = bits >> (8 * c);
-                w.x = ((b8 & 1u) ? 0x3F80u : 0u) | ((b8 & 2u) ? 0x3F800000u : 0u);
-                w.y = ((b8 & 4u) ? 0x3F80u : 0u) | ((b8 & 8u) ? 0x3F800000u : 0u);
-                w.z = ((b8 & 16u) ? 0x3F80u : 0u) | ((b8 & 32u) ? 0x3F800000u : 0u);
-                w.w = ((b8 & 64u) ? 0x3F80u : 0u) | ((b8 & 128u) ? 0x3F800000u : 0u);
-                const int cc = (ch & 1) * 4 + c;
-                *reinterpret_cast<uint4*>(panel + tid * 128 + ((cc ^ (tid & 7)) << 4)) = w;
+                uint32_t w[4];
+#pragma unroll
+                for (int j2 = 0; j2 < 4; ++j2) {
+                    const int j = 8 * c + 2 * j2;
+                    const float x0 = h[j] + sm.bias[Ap - 32 + j], x1 = h[j + 1] + sm.bias[Ap - 32 + j + 1];
+                    sc = fmaf(fmaxf(x0, 0.f), sm.w2[Ap - 32 + j], sc);
+                    sc = fmaf(fmaxf(x1, 0.f), sm.w2[Ap - 32 + j + 1], sc);
+                    w[j2] = (x0 > 0.f ? 0x3F80u : 0u) | (x1 > 0.f ? 0x3F800000u : 0u);
+                }
+                const int cc = (((Ap - 32) & 63) >> 3) + c;
+                *reinterpret_cast<uint4*>(panel + tid * 128 + ((cc ^ (tid & 7)) << 4)) = make_uint4(w[0], w[1], w[2], w[3]);
             }
         }
         sm.score[tid] = sc;
@@ -609,20 +640,20 @@ afm_bwd_tc_kernel(const __grid_constant__ AfmTcParams p, const float* __restrict
         __syncthreads();
         PROF(8);
         // g_e[s][f][d] = sum_{g != f} g_v[pair(f,g)][d] * e[s][g][d]
-        // one warp per (sample, field), lane = d: pair rows and partner rows are warp-uniform
-        for (int sf = warp; sf < n_s * F; sf += kAfmTcThreads / 32) {
-            const int ss = sf / F, f = sf - ss * F;
-            if (lane < D) {
-                const int d = lane;
-                float acc = 0.f;
+        // one thread per (sample, field, 16-byte chunk); partners in ascending field order (ptab)
+        for (int item = tid; item < n_s * F * c4; item += kAfmTcThreads) {
+            const int c = item % c4, sf = item / c4, f = sf % F, ss = sf / F;
+            float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll 3
-                for (int g = 0; g < F; ++g) {
-                    if (g == f) continue;
-                    const int r = ss * P + sm.pidx[f * F + g];
-                    acc = fmaf(stage[r * 32 + 4 * (((d >> 2) ^ r) & 7) + (d & 3)], esm[(ss * F + g) * p.estride + d], acc);
-                }
-                g_rows[(b0 + ss) * F * D + f * D + d] = acc;
+            for (int k = 0; k < F - 1; ++k) {
+                const int pt = sm.pidx[f * 16 + k];          // partner field | pair row << 8
+                const int g = pt & 255, r = ss * P + (pt >> 8);
+                const float4 x = *reinterpret_cast<const float4*>(stage + r * 32 + 4 * ((c ^ r) & 7));
+                const float4 y = *reinterpret_cast<const float4*>(esm + (ss * F + g) * p.estride + 4 * c);
+                acc.x = fmaf(x.x, y.x, acc.x); acc.y = fmaf(x.y, y.y, acc.y);
+                acc.z = fmaf(x.z, y.z, acc.z); acc.w = fmaf(x.w, y.w, acc.w);
             }
+            *reinterpret_cast<float4*>(g_rows + (b0 + ss) * F * D + f * D + 4 * c) = acc;
         }
         __syncthreads();                             // stage (b3), a1, score... are rewritten by the next tile
         PROF(9);
@@ -722,8 +753,17 @@ int rk_afm_tc_fwd(const rk_field_t* fields, int F, const float* w1, const float*
     RK_CHECK_ARG(smem <= 227 * 1024, "afm_tc_fwd: %zu bytes of shared memory", smem);
     auto kernel = p.Kp == 16 ? tc::afm_fwd_tc_kernel<16> : tc::afm_fwd_tc_kernel<32>;
     RK_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    // Tiles are strided statically over the CTAs, so the grid must not exceed what is co-resident
+    // (a second wave would redo the per-CTA set-up).  cudaOccupancyMaxActiveBlocksPerMultiprocessor
+    // reports 1 for kernels that allocate TMEM, so the bound is stated here: 4 x 128 TMEM columns,
+    // 4 x 128 threads x 128 registers, 4 x ~44 KB of shared memory per SM.
+    static const int occ = [] {
+        const char* e = getenv("RANK_B200_AFM_TC_CTAS_PER_SM");
+        const int v = e ? atoi(e) : 0;
+        return v >= 1 && v <= 4 ? v : 4;
+    }();
     int64_t grid = p.n_tiles;
-    const int64_t cap = (int64_t)sm_count() * 4;      // 4 x 128 TMEM columns per SM
+    const int64_t cap = (int64_t)sm_count() * occ;
     if (grid > cap) grid = cap;
     kernel<<<(int)grid, tc::kAfmTcThreads, smem, (cudaStream_t)stream_>>>(p, out, err_flag);
     RK_LAUNCH_CHECK();
