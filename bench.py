@@ -230,6 +230,7 @@ WORKLOADS = {"deepfm": DeepFMWorkload, "fwfm": FwFMWorkload, "dcn": DCNWorkload,
 TRAFFIC_KERNELS = {
     "dcn": ("crossnet_fwd_kernel", "crossnet_bwd_kernel"), "afm": ("afm_fwd_kernel", "afm_bwd_kernel"),
     "bst": ("bst_fwd_kernel", "bst_bwd_kernel"), "din_tc": ("din_fwd_tc_kernel", "din_bwd_tc_kernel"),
+    "afm_tc": ("afm_fwd_tc_kernel", "afm_bwd_tc_kernel"), "fwfm": ("fwfm_fwd_kernel", "fwfm_bwd_kernel"),
 }
 
 

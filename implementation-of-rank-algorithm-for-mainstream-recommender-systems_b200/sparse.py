@@ -33,7 +33,9 @@ def field_array(weights, indices, offsets):
             raise ValueError(f"table[{f}] must be [rows, dim], got {tuple(w.shape)}")
         keep += [w, i]
         arr[f].weight = w.data_ptr()
-        arr[f].idx = i.data_ptr()
+        # an empty batch has no index storage (data_ptr() == 0) but the ABI wants non-NULL pointers:
+        # any valid device address will do, it is never dereferenced when B == 0
+        arr[f].idx = i.data_ptr() if i.numel() else w.data_ptr()
         arr[f].rows = w.shape[0]
         arr[f].dim = w.shape[1]
         arr[f].out_off = int(offsets[f])
@@ -210,6 +212,8 @@ def gather_concat(weights, indices, offsets, dense=None, width=None) -> torch.Te
     width = d if width is None else width
     dev = keep[0].device if keep else dense.device
     out = torch.empty(B, width, dtype=torch.float32, device=dev)
+    if B == 0:                      # nothing to launch; empty tensors have no storage to point at
+        return out
     rc = lib.rk_gather_concat_fwd(arr, len(weights), _lib.ptr(dense), n_dense, B, out.data_ptr(),
                                   width, _lib.err_flag(dev).data_ptr(), _lib.stream_ptr())
     _lib.check(rc, "rk_gather_concat_fwd")

@@ -1,0 +1,38 @@
+#!/bin/bash
+# profiles/<tag>_ncu_summary.md + raw csv + traffic json from gpurun_out/<tag>/ncu (see round_measure.sh)
+tag=${1:-r01}
+src=gpurun_out/$tag/ncu
+out=profiles/${tag}_ncu_summary.md
+S=scripts/summarize_ncu.py
+{
+cat <<HDR
+# Round-${tag#r} profiles (B200, ncu from CUDA 12.9, \`--clock-control none\`)
+
+Commands (\`scripts/round_measure.sh\`, run through \`gpurun\`, each after the same command exited 0 without ncu):
+\`\`\`
+python bench.py --workload W --no-graph --steps 2 --warmup 3 --no-cpu-baseline
+ncu --metrics gpu__time_duration.sum --clock-control none -c 6000 --csv --log-file launches_W.csv <same>
+ncu --set full --clock-control none --import-source on -k regex:<kernels> -s N -c M -o full_W <same>
+\`\`\`
+Raw data: \`${tag}_launches_*.csv\` (every launch of the run), \`${tag}_full_*.raw.csv\` (\`ncu --page raw --csv\` of the
+full captures).  Summaries below are produced by \`scripts/summarize_ncu.py\` / \`scripts/make_ncu_report.sh\`.  ncu
+times are cold-cache and serialised: compare shares, not absolutes; the bench numbers in \`${tag}_bench.md\` are the
+measured ones.  Phase profiles (last section) come from \`scripts/phase_profile.py\` (clock64 per phase, thread 0).
+
+HDR
+echo "## Launch list — DCN step (eager, B = 8192; one step between two forward launches)"; echo
+python $S launches $src/launches_dcn.csv crossnet_fwd_kernel
+echo; echo "## Launch list — DIN step, tensor-core activation unit (eager, B = 8192, T = 50)"; echo
+python $S launches $src/launches_din_tc.csv din_fwd_tc_kernel
+echo; echo "## Launch list — AFM step, tensor-core attention (eager, B = 8192, F = 10, D = 32, A = 128)"; echo
+python $S launches $src/launches_afm_tc.csv afm_fwd_tc_kernel
+for w in dcn din_tc afm_tc fwfm; do
+  echo; echo "## Full capture — $w"
+  python $S full $src/full_$w.ncu-rep
+  ncu -i $src/full_$w.ncu-rep --page raw --csv > profiles/${tag}_full_$w.raw.csv 2>/dev/null
+done
+cp $src/launches_dcn.csv profiles/${tag}_launches_dcn.csv
+cp $src/launches_din_tc.csv profiles/${tag}_launches_din_tc.csv
+cp $src/launches_afm_tc.csv profiles/${tag}_launches_afm_tc.csv
+} > $out.new
+echo "wrote $out.new"

@@ -1,0 +1,143 @@
+"""Edge cases of the hot path on the GPU: empty batches, single rows, T = 1, lengths beyond T,
+all-empty / all-full histories, every index equal (one hot row), and the full-size properties the
+domain offers (linearity of the embedding-gradient reduction, idempotence of a repeated step)."""
+import copy
+
+import pytest
+import torch
+
+import rank_b200
+from rank_b200 import synthetic
+from conftest import rel_err, to_device
+from oracle import models as oracle_models
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+TOL = 1e-5
+
+
+def _pair(name, oracle_name, *args, **kw):
+    torch.manual_seed(0)
+    ours = getattr(rank_b200, name)(*args, **kw)
+    ref = getattr(oracle_models, oracle_name)(*args, **kw)
+    ref.load_state_dict(ours.state_dict(), strict=True)
+    return ours.to(DEV), ref
+
+
+def _grads(model):
+    return {k: p.grad.detach().cpu().clone() for k, p in model.named_parameters() if p.grad is not None}
+
+
+def _check(ours, ref, run, tol=TOL):
+    """Same seed, same inputs on both sides; judged by test_gpu_models.compare (fp32 bar, float64
+    arbiter for long sums, absolute bar for numerically-zero tensors)."""
+    from test_gpu_models import compare
+    res = []
+    for model, dev in ((ours, DEV), (ref, "cpu"), (copy.deepcopy(ref).double(), "f64")):
+        torch.manual_seed(3)
+        loss = run(model, dev)
+        model.zero_grad()
+        loss.backward()
+        res.append((loss.detach().cpu(), _grads(model)))
+    rank_b200.check_index_errors()
+    compare([res[0][0]], res[0][1], [res[1][0]], res[1][1], tol, res[2][1])
+
+
+def _dev(obj, dev):
+    """Inputs for one of the three runs: CUDA, CPU fp32, CPU float64 ("f64")."""
+    if dev != "f64":
+        return to_device(obj, dev)
+    if torch.is_tensor(obj):
+        return obj.double() if obj.is_floating_point() else obj
+    return {k: _dev(v, dev) for k, v in obj.items()}
+
+
+@pytest.mark.parametrize("B", [0, 1, 2])
+def test_tiny_batches_dcn_deepfm_fwfm(wechat_vocab_dir, B):
+    if B == 0:
+        # an empty batch is a no-op for every kernel: shapes come out right and nothing is launched on garbage
+        m = rank_b200.DCNModel(wechat_vocab_dir, hidden_units=[8], num_cross_layer=2).to(DEV).eval()
+        b = to_device(synthetic.side_batch(4), DEV)
+        empty = {k: v[:0] for k, v in b["category"].items()}
+        from rank_b200.sparse import gather_concat
+        cols = [c for c in m.embeddings if c in empty]
+        dims = [m.embeddings[c].weight.shape[1] for c in cols]
+        offs = [16 + sum(dims[:i]) for i in range(len(cols))]
+        out = gather_concat([m.embeddings[c].weight for c in cols], [empty[c] for c in cols], offs, dense=b["dense"][:0])
+        assert out.shape == (0, 16 + sum(dims))
+        rank_b200.check_index_errors()
+        return
+    ours, ref = _pair("DCNModel", "OracleDCN", wechat_vocab_dir, hidden_units=[16, 8], num_cross_layer=3)
+    batch = synthetic.side_batch(B)
+    ours.eval(); ref.eval()                      # BatchNorm needs B > 1 in training mode
+    _check(ours, ref, lambda m, d: m(_dev(batch["dense"], d), _dev(batch["category"], d))[1].sum())
+    ours, ref = _pair("FwFM", "OracleFwFM", synthetic.fwfm_field_dims(), 8)
+    fb = synthetic.fwfm_batch(B)
+    _check(ours, ref, lambda m, d: m(_dev(fb["x"], d)).sum())
+
+
+@pytest.mark.parametrize("soft", [False, True])
+@pytest.mark.parametrize("case", ["T1", "all_empty", "all_full", "len_beyond_T", "one_hot_row"])
+def test_din_history_edges(wechat_vocab_dir, case, soft):
+    T = 1 if case == "T1" else 12
+    B = 96
+    batch = synthetic.din_batch(B, T, 11)
+    seq = batch["sequence"]
+    if case == "all_empty":
+        seq["his_read_comment_7d_seq_length"].zero_()
+        seq["his_read_comment_7d_seq"].zero_()
+    elif case == "all_full":
+        seq["his_read_comment_7d_seq_length"].fill_(T)
+        seq["his_read_comment_7d_seq"].clamp_(min=1)
+    elif case == "len_beyond_T":                 # the reference's mask is arange(T) < len: longer = full
+        seq["his_read_comment_7d_seq_length"].fill_(T + 5)
+        seq["his_read_comment_7d_seq"].clamp_(min=1)
+    elif case == "one_hot_row":                  # every position of every sample hits the same row
+        seq["his_read_comment_7d_seq_length"].fill_(T)
+        seq["his_read_comment_7d_seq"].fill_(7)
+        batch["target"]["feedid"].fill_(7)
+    for prec in ("fp32", "bf16"):
+        ours, ref = _pair("DIN", "OracleDIN", wechat_vocab_dir, hidden_units=[16, 8], dropout_rate=0.0,
+                          use_softmax=soft, l2_lambda=0.2)
+        ours.activation_unit_precision = prec
+
+        def run(m, d):
+            prob, _, l2 = m(_dev(batch["dense"], d), _dev(batch["category"], d),
+                            _dev(batch["sequence"], d), _dev(batch["target"], d))
+            return prob.sum() + l2
+        _check(ours, ref, run, TOL if prec == "fp32" else 2e-2)
+
+
+def test_segment_reduce_is_linear_at_full_size():
+    """Property at BASELINE size (no oracle needed): the dense embedding gradient is linear in the
+    per-occurrence rows, and reducing with a shared plan twice gives identical bits."""
+    from rank_b200.sparse import GradSource, OccurrencePlan
+    gen = torch.Generator().manual_seed(0)
+    B, T, D, rows = 8192, 50, 16, 106445
+    idx = synthetic.zipf_indices(gen, rows, (B, T)).to(DEV)
+    plan = OccurrencePlan([idx.view(-1)], [rows])
+    g1 = torch.randn(B * T, D, generator=gen).to(DEV)
+    g2 = torch.randn(B * T, D, generator=gen).to(DEV)
+
+    def reduce(g):
+        return plan.reduce_to_dense([GradSource(g, 0, D, D, rows, 0)])[0].clone()
+    a, b, ab = reduce(g1), reduce(g2), reduce(g1 + g2)
+    assert torch.equal(reduce(g1), a)
+    assert rel_err(ab, a + b) <= 1e-5
+    counts = torch.bincount(idx.view(-1), minlength=rows).to(torch.float32)
+    ones = reduce(torch.ones(B * T, D, device=DEV))
+    assert torch.equal(ones[:, 0], counts)       # a checksum of checksums: occurrences per row, exactly
+
+
+def test_repeated_step_is_bit_identical(wechat_vocab_dir):
+    ours, _ = _pair("BSTModel", "OracleBST", wechat_vocab_dir, hidden_units=[16, 8], dropout_rate=0.0)
+    batch = to_device(synthetic.bst_batch(512, 20, 5), DEV)
+    outs = []
+    for _ in range(2):
+        ours.zero_grad()
+        logit = ours(batch["dense"], batch["category"], batch["seq_feedid"], batch["seq_length"])[1]
+        logit.sum().backward()
+        outs.append((logit.detach().clone(), copy.deepcopy(_grads(ours))))
+    assert torch.equal(outs[0][0], outs[1][0])
+    for k in outs[0][1]:
+        assert torch.equal(outs[0][1][k], outs[1][1][k]), k
