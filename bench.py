@@ -335,6 +335,9 @@ class ClockSampler:
 
 
 def dist_setup(n_gpus):
+    # stdout carries exactly one JSON line: whatever NCCL logs (its version banner at
+    # NCCL_DEBUG=VERSION, the transport lines at INFO) goes to stderr
+    os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
