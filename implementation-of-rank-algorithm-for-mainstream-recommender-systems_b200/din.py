@@ -23,6 +23,7 @@ from . import _lib
 from .dcn import NUM_DENSE, SIDE_COLUMNS, SIDE_TABLES
 from .ephemeral import EphemeralBuffer
 from .sparse import GradSource, OccurrencePlan, field_array
+from .tower import run_tower
 from .vocab import table_heights
 
 SEQ = "his_read_comment_7d_seq"
@@ -305,9 +306,7 @@ class DIN(nn.Module):
             cfg, mlp, *dense_cols, *[category[c] for c in cols], target['feedid'], sequence[SEQ],
             sequence[SEQ_LEN], *[self.embeddings[c].weight for c in cols],
             self.embeddings['feedid'].weight, self.embeddings[SEQ].weight)
-        net = concat_all
-        for layer in self.fcn:
-            net = layer(net)
+        net = run_tower(self.fcn, concat_all)      # the reference's `for layer in self.fcn` loop
         logit = self.output_layer(net)
         probability = torch.sigmoid(logit)
         l2_reg = 0.0

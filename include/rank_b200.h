@@ -216,6 +216,25 @@ int rk_afm_tc_bwd(const rk_field_t* fields, int F, const float* w1, const float*
                   float* g_b1, float* g_w2, float* g_b2, float* partials, int n_ctas,
                   int32_t* err_flag, rk_stream_t stream);
 
+/* ---- fused tower layers: Dice (DIN/din.py:26-36) and the BatchNorm1d that
+ *      follows it in the DIN tower (DIN/din.py:272-285), training mode ------------------------
+ * x, z: [B, units] row-major.  xh = batchnorm(x; eps1, no affine), p = sigmoid(xh),
+ * y = alpha*(1-p)*x + p*x, z = gamma * batchnorm(y; eps2) + beta; gamma = beta = NULL: z = y.
+ * Running statistics (may be NULL) are updated in place as nn.BatchNorm1d does (momentum,
+ * unbiased variance, num_batches += 1).  stats[4, units] = mean1 | rstd1 | mean2 | rstd2 is kept
+ * for the backward.  1 <= B <= rk_dice_bn_max_batch() (a CTA holds the whole batch of its
+ * columns in registers; every batch statistic is a fixed-order block reduction). */
+int rk_dice_bn_max_batch(void);
+int rk_dice_bn_fwd(const float* x, int64_t B, int units, const float* alpha, float eps1,
+                   const float* gamma, const float* beta, float eps2, float momentum1,
+                   float* running_mean1, float* running_var1, int64_t* num_batches1,
+                   float momentum2, float* running_mean2, float* running_var2,
+                   int64_t* num_batches2, float* z, float* stats, rk_stream_t stream);
+/* g_x[B, units]; g_alpha, g_gamma, g_beta: [units] (complete sums over the batch). */
+int rk_dice_bn_bwd(const float* x, const float* g_z, int64_t B, int units, const float* alpha,
+                   const float* gamma, const float* stats, float* g_x, float* g_alpha,
+                   float* g_gamma, float* g_beta, rk_stream_t stream);
+
 /* ---- row-sharded table (BASELINE config 5 "scaled": BST feedid table of 1e8 rows block-
  *      partitioned by row over the ranks; the reference itself is single-process) ------------
  * Bookkeeping around the two all-to-alls (indices out / rows back, mirrored for gradients):
