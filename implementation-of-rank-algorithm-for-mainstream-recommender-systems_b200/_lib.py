@@ -85,6 +85,8 @@ PROTOTYPES = {
     "rk_dice_bn_max_batch": (_I, []),
     "rk_dice_bn_fwd": (_I, [_P, _L, _I, _P, _F, _P, _P, _F, _F, _P, _P, _P, _F, _P, _P, _P, _P, _P, _P]),
     "rk_dice_bn_bwd": (_I, [_P, _P, _L, _I, _P, _P, _P, _P, _P, _P, _P, _P]),
+    "rk_bn_act_fwd": (_I, [_P, _L, _I, _P, _P, _F, _F, _P, _P, _P, _F, _P, _P, _P]),
+    "rk_bn_act_bwd": (_I, [_P, _P, _L, _I, _P, _P, _F, _P, _P, _P, _P, _P]),
     "rk_shard_owner": (_I, [_P, _L, _L, _L, _P, _P, _P]),
     "rk_shard_route": (_I, [_P, _P, _P, _L, _L, _L, _I, _P, _P, _P, _P]),
     "rk_plan_compact": (_I, [_P, _L, _L, _P, _P, _P, _P]),

@@ -25,6 +25,7 @@ from . import _lib
 from .dcn import NUM_DENSE, SIDE_COLUMNS, SIDE_TABLES
 from .sharded import RowShardedEmbedding
 from .sparse import GatherConcat, GradSource, OccurrencePlan
+from .tower import run_tower
 
 D_MODEL = 16
 _PARAM_ORDER = ("position_embedding.weight", "w_q.weight", "w_q.bias", "w_k.weight", "w_k.bias", "w_v.weight",
@@ -247,6 +248,6 @@ class BSTModel(nn.Module):
             x = block.run(x, seq_length, idx=idx, pool=pool if last else None)
             idx = None
         all_features = torch.cat([side, x], dim=1)
-        logits = self.dnn(all_features)
+        logits = run_tower(list(self.dnn), all_features)      # = self.dnn(all_features), BatchNorm1d+LeakyReLU fused
         probabilities = torch.sigmoid(logits)
         return probabilities, logits

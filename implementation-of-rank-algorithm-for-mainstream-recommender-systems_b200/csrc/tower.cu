@@ -277,6 +277,138 @@ dice_bn_bwd_kernel(const DiceBnArgs a, const float* __restrict__ g_z, const floa
     }
 }
 
+// ---- BatchNorm1d (affine, training) + ReLU / LeakyReLU: the DeepFM and BST towers
+//      (DeepFM/deepfm.py:100-110, BST/bst.py:203-214):  z = act(gamma * xh + beta),
+//      act(u) = u > 0 ? u : slope * u  (slope = 0: ReLU; 1: no activation).
+struct BnActArgs {
+    const float* x;
+    const float* gamma;
+    const float* beta;
+    float*   rm;  float* rv;  int64_t* nbt;
+    float    eps, mom, slope;
+    int64_t  B;
+    int32_t  units;
+};
+
+template <int COLS, int ROWS>
+__global__ void __launch_bounds__(kTowerThreads, 1)
+bn_act_fwd_kernel(const BnActArgs a, float* __restrict__ z, float* __restrict__ stats) {
+    __shared__ double scratch[32 * COLS];
+    const int c0 = blockIdx.x * COLS, tid = threadIdx.x;
+    const int64_t B = a.B;
+    const int U = a.units;
+    const float invB = 1.0f / (float)B;
+    Vec<COLS> x[ROWS];
+#pragma unroll
+    for (int r = 0; r < ROWS; ++r) {
+        const int64_t row = tid + (int64_t)r * kTowerThreads;
+        if (row < B) x[r].load(a.x + row * U + c0); else vec_zero(x[r]);
+    }
+    float mu[COLS], rstd[COLS], s[COLS];
+#pragma unroll
+    for (int c = 0; c < COLS; ++c) s[c] = 0.f;
+#pragma unroll
+    for (int r = 0; r < ROWS; ++r)
+#pragma unroll
+        for (int c = 0; c < COLS; ++c) s[c] += x[r].v[c];
+    block_sum<COLS>(s, scratch);
+#pragma unroll
+    for (int c = 0; c < COLS; ++c) { mu[c] = s[c] * invB; s[c] = 0.f; }
+#pragma unroll
+    for (int r = 0; r < ROWS; ++r) {
+        const bool live = tid + (int64_t)r * kTowerThreads < B;
+#pragma unroll
+        for (int c = 0; c < COLS; ++c) {
+            const float d = x[r].v[c] - mu[c];
+            s[c] += live ? d * d : 0.f;
+        }
+    }
+    block_sum<COLS>(s, scratch);
+    float g[COLS], b[COLS];
+#pragma unroll
+    for (int c = 0; c < COLS; ++c) {
+        const float var = s[c] * invB;
+        rstd[c] = 1.0f / sqrtf(var + a.eps);
+        g[c] = __ldg(a.gamma + c0 + c) * rstd[c];
+        b[c] = __ldg(a.beta + c0 + c);
+        if (tid == 0) {
+            stats[0 * U + c0 + c] = mu[c];
+            stats[1 * U + c0 + c] = rstd[c];
+            if (a.rm) {
+                a.rm[c0 + c] = (1.f - a.mom) * a.rm[c0 + c] + a.mom * mu[c];
+                a.rv[c0 + c] = (1.f - a.mom) * a.rv[c0 + c] + a.mom * (B > 1 ? var * (float)B / (float)(B - 1) : var);
+            }
+        }
+    }
+    if (tid == 0 && blockIdx.x == 0 && a.nbt) *a.nbt += 1;
+#pragma unroll
+    for (int r = 0; r < ROWS; ++r) {
+        const int64_t row = tid + (int64_t)r * kTowerThreads;
+        if (row < B) {
+            Vec<COLS> o;
+#pragma unroll
+            for (int c = 0; c < COLS; ++c) {
+                const float u = fmaf(x[r].v[c] - mu[c], g[c], b[c]);
+                o.v[c] = u > 0.f ? u : a.slope * u;
+            }
+            o.store(z + row * U + c0);
+        }
+    }
+}
+
+template <int COLS, int ROWS>
+__global__ void __launch_bounds__(kTowerThreads, 1)
+bn_act_bwd_kernel(const BnActArgs a, const float* __restrict__ g_z, const float* __restrict__ stats,
+                  float* __restrict__ g_x, float* __restrict__ g_gamma, float* __restrict__ g_beta) {
+    __shared__ double scratch[32 * 2 * COLS];
+    const int c0 = blockIdx.x * COLS, tid = threadIdx.x;
+    const int64_t B = a.B;
+    const int U = a.units;
+    const float invB = 1.0f / (float)B;
+    float mu[COLS], rstd[COLS], gam[COLS], bet[COLS];
+#pragma unroll
+    for (int c = 0; c < COLS; ++c) {
+        mu[c] = stats[0 * U + c0 + c];  rstd[c] = stats[1 * U + c0 + c];
+        gam[c] = __ldg(a.gamma + c0 + c);  bet[c] = __ldg(a.beta + c0 + c);
+    }
+    Vec<COLS> xh[ROWS], g[ROWS];
+    float s[2 * COLS];
+#pragma unroll
+    for (int i = 0; i < 2 * COLS; ++i) s[i] = 0.f;
+#pragma unroll
+    for (int r = 0; r < ROWS; ++r) {
+        const int64_t row = tid + (int64_t)r * kTowerThreads;
+        if (row < B) { xh[r].load(a.x + row * U + c0); g[r].load(g_z + row * U + c0); }
+        else { vec_zero(xh[r]); vec_zero(g[r]); }
+#pragma unroll
+        for (int c = 0; c < COLS; ++c) {
+            const float h = (xh[r].v[c] - mu[c]) * rstd[c];
+            const float u = fmaf(h, gam[c], bet[c]);
+            const float gu = row < B ? g[r].v[c] * (u > 0.f ? 1.0f : a.slope) : 0.f;
+            xh[r].v[c] = h;
+            g[r].v[c] = gu;
+            s[c] += gu;
+            s[COLS + c] += gu * h;
+        }
+    }
+    block_sum<2 * COLS>(s, scratch);
+    if (tid == 0) {
+#pragma unroll
+        for (int c = 0; c < COLS; ++c) { g_beta[c0 + c] = s[c]; g_gamma[c0 + c] = s[COLS + c]; }
+    }
+#pragma unroll
+    for (int r = 0; r < ROWS; ++r) {
+        const int64_t row = tid + (int64_t)r * kTowerThreads;
+        if (row < B) {
+            Vec<COLS> o;
+#pragma unroll
+            for (int c = 0; c < COLS; ++c)
+                o.v[c] = gam[c] * rstd[c] * (g[r].v[c] - s[c] * invB - xh[r].v[c] * s[COLS + c] * invB);
+            o.store(g_x + row * U + c0);
+        }
+    }
+}
+
 // Columns per CTA: the widest vector that divides the width, keeps the per-thread tile (rows x cols
 // values, twice that in the backward) within the register budget of a 1024-thread CTA, and still
 // leaves about one wave of CTAs.
@@ -342,6 +474,51 @@ int rk_dice_bn_bwd(const float* x, const float* g_z, int64_t B, int units, const
     if (cols == 4) RK_TOWER_ROWS(RK_TOWER_BWD, 4); else if (cols == 2) RK_TOWER_ROWS(RK_TOWER_BWD, 2);
     else RK_TOWER_ROWS(RK_TOWER_BWD, 1);
 #undef RK_TOWER_BWD
+#undef RK_TOWER_ROWS
+    RK_LAUNCH_CHECK();
+    return 0;
+}
+
+int rk_bn_act_fwd(const float* x, int64_t B, int units, const float* gamma, const float* beta, float eps,
+                  float momentum, float* running_mean, float* running_var, int64_t* num_batches, float slope,
+                  float* z, float* stats, rk_stream_t stream_) {
+    using namespace rk;
+    RK_CHECK_ARG(x && gamma && beta && z && stats, "bn_act_fwd: NULL pointer");
+    RK_CHECK_ARG(units >= 1 && B >= 1 && B <= rk_dice_bn_max_batch(), "bn_act_fwd: B=%lld units=%d (B <= %d)",
+                 (long long)B, units, rk_dice_bn_max_batch());
+    RK_CHECK_ARG((running_mean == nullptr) == (running_var == nullptr), "bn_act_fwd: running mean/var go together");
+    BnActArgs a{x, gamma, beta, running_mean, running_var, num_batches, eps, momentum, slope, B, units};
+    const int rows = (int)ceil_div(B, kTowerThreads);
+    const int cols = tower_cols(units, rows, 32, x, z, z);
+    const int grid = units / cols;
+    cudaStream_t s = (cudaStream_t)stream_;
+#define RK_TOWER_ROWS(M, C)                                            \
+    do {                                                               \
+        if (rows <= 1) M(C, 1); else if (rows <= 2) M(C, 2); else if (rows <= 4) M(C, 4);   \
+        else if (rows <= 8) M(C, 8); else M(C, 16);                    \
+    } while (0)
+#define RK_BN_FWD(C, R) bn_act_fwd_kernel<C, R><<<grid, kTowerThreads, 0, s>>>(a, z, stats)
+    if (cols == 4) RK_TOWER_ROWS(RK_BN_FWD, 4); else if (cols == 2) RK_TOWER_ROWS(RK_BN_FWD, 2);
+    else RK_TOWER_ROWS(RK_BN_FWD, 1);
+#undef RK_BN_FWD
+    RK_LAUNCH_CHECK();
+    return 0;
+}
+
+int rk_bn_act_bwd(const float* x, const float* g_z, int64_t B, int units, const float* gamma, const float* beta,
+                  float slope, const float* stats, float* g_x, float* g_gamma, float* g_beta, rk_stream_t stream_) {
+    using namespace rk;
+    RK_CHECK_ARG(x && g_z && gamma && beta && stats && g_x && g_gamma && g_beta, "bn_act_bwd: NULL pointer");
+    RK_CHECK_ARG(units >= 1 && B >= 1 && B <= rk_dice_bn_max_batch(), "bn_act_bwd: B=%lld units=%d", (long long)B, units);
+    BnActArgs a{x, gamma, beta, nullptr, nullptr, nullptr, 0.f, 0.f, slope, B, units};
+    const int rows = (int)ceil_div(B, kTowerThreads);
+    const int cols = tower_cols(units, rows, 16, x, g_z, g_x);
+    const int grid = units / cols;
+    cudaStream_t s = (cudaStream_t)stream_;
+#define RK_BN_BWD(C, R) bn_act_bwd_kernel<C, R><<<grid, kTowerThreads, 0, s>>>(a, g_z, stats, g_x, g_gamma, g_beta)
+    if (cols == 4) RK_TOWER_ROWS(RK_BN_BWD, 4); else if (cols == 2) RK_TOWER_ROWS(RK_BN_BWD, 2);
+    else RK_TOWER_ROWS(RK_BN_BWD, 1);
+#undef RK_BN_BWD
 #undef RK_TOWER_ROWS
     RK_LAUNCH_CHECK();
     return 0;

@@ -16,6 +16,7 @@ import torch.nn as nn
 
 from . import _lib
 from .sparse import GradSource, OccurrencePlan, field_array
+from .tower import run_tower
 from .vocab import table_heights
 
 DEEPFM_COLUMNS = ("userid", "feedid", "device", "authorid", "bgm_song_id", "bgm_singer_id")
@@ -116,9 +117,7 @@ class DeepFM(nn.Module):
                 + [self.first_order_embeddings[c].weight for c in cols]
                 + [self.second_order_embeddings[c].weight for c in cols])
         deep_input, fm_first_order_logit, fm_second_order_logit = _FMInteraction.apply(F, *args)
-        deep_output = deep_input
-        for layer in self.deep_layers:
-            deep_output = layer(deep_output)
+        deep_output = run_tower(self.deep_layers, deep_input)     # the reference's layer loop
         deep_logit = self.deep_output_layer(deep_output)
         total_logit = self.final_layer(
             torch.cat([fm_first_order_logit, fm_second_order_logit, deep_logit], dim=1))

@@ -235,6 +235,17 @@ int rk_dice_bn_bwd(const float* x, const float* g_z, int64_t B, int units, const
                    const float* gamma, const float* stats, float* g_x, float* g_alpha,
                    float* g_gamma, float* g_beta, rk_stream_t stream);
 
+/* BatchNorm1d (affine, training mode) fused with the ReLU / LeakyReLU that follows it in the DeepFM
+ * and BST towers (DeepFM/deepfm.py:100-110, BST/bst.py:203-214): z = act(gamma * batchnorm(x) + beta),
+ * act(u) = u > 0 ? u : slope * u (slope 0 = ReLU, 0.01 = the BST tower, 1 = batch norm alone).
+ * stats[2, units] = mean | rstd.  Same batch limit and determinism as rk_dice_bn_fwd. */
+int rk_bn_act_fwd(const float* x, int64_t B, int units, const float* gamma, const float* beta,
+                  float eps, float momentum, float* running_mean, float* running_var,
+                  int64_t* num_batches, float slope, float* z, float* stats, rk_stream_t stream);
+int rk_bn_act_bwd(const float* x, const float* g_z, int64_t B, int units, const float* gamma,
+                  const float* beta, float slope, const float* stats, float* g_x, float* g_gamma,
+                  float* g_beta, rk_stream_t stream);
+
 /* ---- row-sharded table (BASELINE config 5 "scaled": BST feedid table of 1e8 rows block-
  *      partitioned by row over the ranks; the reference itself is single-process) ------------
  * Bookkeeping around the two all-to-alls (indices out / rows back, mirrored for gradients):

@@ -15,6 +15,15 @@ DEV = "cuda"
 TOL = 1e-5
 
 
+@pytest.fixture(autouse=True)
+def _fuse_every_batch_size():
+    """The kernels are exercised at every size here; in the models small batches run the torch modules."""
+    saved = tower.MIN_BATCH
+    tower.MIN_BATCH = 2
+    yield
+    tower.MIN_BATCH = saved
+
+
 def _layers(units, with_bn2):
     torch.manual_seed(1)
     dice = rank_b200.Dice(units)
@@ -74,3 +83,37 @@ def test_eval_mode_and_switch_run_the_modules():
     for m in mods:
         b = m(b)
     assert torch.equal(a, b)
+
+
+@pytest.mark.parametrize("B,units,act", [(1024, 512, nn.ReLU()), (8192, 256, nn.LeakyReLU(0.01)), (8192, 1024, nn.ReLU()),
+                                         (777, 128, nn.LeakyReLU(0.2)), (16384, 96, nn.ReLU())])
+def test_fused_bn_activation_matches_modules(B, units, act):
+    torch.manual_seed(2)
+    bn = nn.BatchNorm1d(units)
+    with torch.no_grad():
+        bn.weight.uniform_(0.5, 1.5)
+        bn.bias.uniform_(-0.3, 0.3)
+    fused = nn.ModuleList([bn, act, nn.Linear(units, 3)]).to(DEV).train()
+    plain = copy.deepcopy(fused)
+    gen = torch.Generator().manual_seed(B + units)
+    x0 = (torch.randn(B, units, generator=gen) * 1.3 - 0.2).to(DEV)
+    cot = torch.randn(B, 3, generator=gen).to(DEV) / B
+    results = []
+    for mods, flag in ((fused, True), (plain, False)):
+        tower.FUSED = flag
+        try:
+            for step in range(2):
+                x = x0.clone().requires_grad_()
+                out = tower.run_tower(mods, x)
+                mods.zero_grad()
+                (out * cot).sum().backward()
+        finally:
+            tower.FUSED = True
+        results.append((out.detach(), x.grad.detach(), {k: p.grad.detach() for k, p in mods.named_parameters()},
+                        {k: b.detach().clone() for k, b in mods.named_buffers()}))
+    (o1, gx1, gp1, buf1), (o2, gx2, gp2, buf2) = results
+    assert rel_err(o1, o2) <= TOL and rel_err(gx1, gx2) <= TOL
+    for k in gp2:
+        assert rel_err(gp1[k], gp2[k]) <= TOL, k
+    for k in buf2:
+        assert (torch.equal(buf1[k], buf2[k]) if buf2[k].dtype == torch.int64 else rel_err(buf1[k], buf2[k]) <= TOL), k
