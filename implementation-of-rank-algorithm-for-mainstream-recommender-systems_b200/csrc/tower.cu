@@ -23,7 +23,7 @@ constexpr int kTowerMaxRows = 16;
 // pass run in double: gradients of biases / BN shifts are sums with heavy cancellation, and a float
 // tree would add ~1e-7 of sum|terms| to a result that can be 100x smaller.
 template <int N>
-__device__ __forceinline__ void block_sum(float (&v)[N], double* scratch /* [32][N] */) {
+__device__ __forceinline__ void block_sum(float (&v)[N], double* scratch /* [33][N] */) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     double d[N];
 #pragma unroll
@@ -38,13 +38,15 @@ __device__ __forceinline__ void block_sum(float (&v)[N], double* scratch /* [32]
         for (int i = 0; i < N; ++i) scratch[warp * N + i] = d[i];
     }
     __syncthreads();
-#pragma unroll
-    for (int i = 0; i < N; ++i) {
+    if (threadIdx.x < N) {                             // one thread per value adds the 32 warp sums in order
         double t = 0.0;
 #pragma unroll 8
-        for (int w = 0; w < kTowerThreads / 32; ++w) t += scratch[w * N + i];
-        v[i] = (float)t;
+        for (int w = 0; w < kTowerThreads / 32; ++w) t += scratch[w * N + threadIdx.x];
+        scratch[32 * N + threadIdx.x] = t;
     }
+    __syncthreads();
+#pragma unroll
+    for (int i = 0; i < N; ++i) v[i] = (float)scratch[32 * N + i];
 }
 
 struct DiceBnArgs {
@@ -62,7 +64,7 @@ struct DiceBnArgs {
 template <int COLS, int ROWS>
 __global__ void __launch_bounds__(kTowerThreads, 1)
 dice_bn_fwd_kernel(const DiceBnArgs a, float* __restrict__ z, float* __restrict__ stats) {
-    __shared__ double scratch[32 * COLS];
+    __shared__ double scratch[33 * COLS];
     const int c0 = blockIdx.x * COLS, tid = threadIdx.x;
     const int64_t B = a.B;
     const int U = a.units;
@@ -184,7 +186,7 @@ __global__ void __launch_bounds__(kTowerThreads, 1)
 dice_bn_bwd_kernel(const DiceBnArgs a, const float* __restrict__ g_z, const float* __restrict__ stats,
                    float* __restrict__ g_x, float* __restrict__ g_alpha, float* __restrict__ g_gamma,
                    float* __restrict__ g_beta) {
-    __shared__ double scratch[32 * 3 * COLS];
+    __shared__ double scratch[33 * 3 * COLS];
     const int c0 = blockIdx.x * COLS, tid = threadIdx.x;
     const int64_t B = a.B;
     const int U = a.units;
@@ -293,7 +295,7 @@ struct BnActArgs {
 template <int COLS, int ROWS>
 __global__ void __launch_bounds__(kTowerThreads, 1)
 bn_act_fwd_kernel(const BnActArgs a, float* __restrict__ z, float* __restrict__ stats) {
-    __shared__ double scratch[32 * COLS];
+    __shared__ double scratch[33 * COLS];
     const int c0 = blockIdx.x * COLS, tid = threadIdx.x;
     const int64_t B = a.B;
     const int U = a.units;
@@ -360,7 +362,7 @@ template <int COLS, int ROWS>
 __global__ void __launch_bounds__(kTowerThreads, 1)
 bn_act_bwd_kernel(const BnActArgs a, const float* __restrict__ g_z, const float* __restrict__ stats,
                   float* __restrict__ g_x, float* __restrict__ g_gamma, float* __restrict__ g_beta) {
-    __shared__ double scratch[32 * 2 * COLS];
+    __shared__ double scratch[33 * 2 * COLS];
     const int c0 = blockIdx.x * COLS, tid = threadIdx.x;
     const int64_t B = a.B;
     const int U = a.units;
