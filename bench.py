@@ -113,9 +113,12 @@ class DCNWorkload(Workload):
 
 
 class AFMWorkload(Workload):
-    # 10 fields, D=32, A=128: compute-bound on the fp32 FMA pipe once fused
+    # 10 fields, D=32, A=128.  Default module setting: attention MLP on tcgen05 (split-bf16 operands,
+    # fp32 TMEM accumulation, ReLU decisions re-checked in fp32), inside the 1e-5 parity bar.
     name, batch, bytes_per_sample, flops_per_sample = "afm_f10_d32_a128", 8192, 6816, 1_150_000
-    hot_calls = ("rk_afm_fwd", "rk_plan_build", "rk_afm_bwd", "rk_embgrad_segment_reduce")
+    hot_calls = ("rk_afm_tc_fwd", "rk_plan_build", "rk_afm_tc_bwd", "rk_embgrad_segment_reduce")
+    dtype = "bf16x3 tensor-core attention MLP (fp32 accumulate), f32 elsewhere"
+    precision = "tensor"
 
     def __init__(self):
         from rank_b200 import synthetic
@@ -123,7 +126,10 @@ class AFMWorkload(Workload):
 
     def model(self, ns, oracle, vocab_dir):
         cls = ns.OracleAFM if oracle else ns.AFM
-        return cls(self.fc, 32, 128)
+        m = cls(self.fc, 32, 128)
+        if not oracle:
+            m.attention_precision = self.precision
+        return m
 
     def make_batch(self, B, seed):
         from rank_b200 import synthetic
@@ -134,16 +140,10 @@ class AFMWorkload(Workload):
         return F.binary_cross_entropy(prob.squeeze(), batch["label"])
 
 
-class AFMTensorCoreWorkload(AFMWorkload):
-    # attention MLP on tcgen05 (split-bf16 operands, fp32 TMEM accumulation)
-    name, dtype = "afm_f10_d32_a128_tcgen05", "bf16x3 tensor-core MLP, f32 elsewhere"
-    hot_calls = ("rk_afm_tc_fwd", "rk_afm_tc_bwd", "rk_plan_build", "rk_afm_bwd", "rk_embgrad_segment_reduce")
-
-    def model(self, ns, oracle, vocab_dir):
-        m = super().model(ns, oracle, vocab_dir)
-        if not oracle:
-            m.attention_precision = "bf16"
-        return m
+class AFMFp32Workload(AFMWorkload):
+    # the fp32 SIMT kernels (csrc/afm.cu): compute-bound on the fp32 FMA pipe
+    name, dtype, precision = "afm_f10_d32_a128_fp32simt", "f32", "fp32"
+    hot_calls = ("rk_afm_fwd", "rk_plan_build", "rk_afm_bwd", "rk_embgrad_segment_reduce")
 
 
 class DINWorkload(Workload):
@@ -218,7 +218,7 @@ class DeepCrossingWorkload(Workload):
         return F.binary_cross_entropy_with_logits(logit.squeeze(), batch["label"])
 
 
-WORKLOADS = {"deepfm": DeepFMWorkload, "fwfm": FwFMWorkload, "dcn": DCNWorkload, "afm": AFMWorkload, "afm_tc": AFMTensorCoreWorkload, "din": DINWorkload,
+WORKLOADS = {"deepfm": DeepFMWorkload, "fwfm": FwFMWorkload, "dcn": DCNWorkload, "afm": AFMWorkload, "afm_fp32": AFMFp32Workload, "din": DINWorkload,
              "din_softmax": DINSoftmaxWorkload, "din_tc": DINTensorCoreWorkload,
              "din_softmax_tc": DINSoftmaxTensorCoreWorkload, "bst": BSTWorkload,
              "deepcrossing": DeepCrossingWorkload}
@@ -228,9 +228,9 @@ WORKLOADS = {"deepfm": DeepFMWorkload, "fwfm": FwFMWorkload, "dcn": DCNWorkload,
 # fused forward + backward kernels whose ncu dram__bytes (profiles/r01_traffic.json, one
 # `ncu --set full` capture per kernel) are reported as roofline.traffic
 TRAFFIC_KERNELS = {
-    "dcn": ("crossnet_fwd_kernel", "crossnet_bwd_kernel"), "afm": ("afm_fwd_kernel", "afm_bwd_kernel"),
+    "dcn": ("crossnet_fwd_kernel", "crossnet_bwd_kernel"), "afm_fp32": ("afm_fwd_kernel", "afm_bwd_kernel"),
     "bst": ("bst_fwd_kernel", "bst_bwd_kernel"), "din_tc": ("din_fwd_tc_kernel", "din_bwd_tc_kernel"),
-    "afm_tc": ("afm_fwd_tc_kernel", "afm_bwd_tc_kernel"), "fwfm": ("fwfm_fwd_kernel", "fwfm_bwd_kernel"),
+    "afm": ("afm_fwd_tc_kernel", "afm_bwd_tc_kernel"), "fwfm": ("fwfm_fwd_kernel", "fwfm_bwd_kernel"),
 }
 
 

@@ -20,6 +20,12 @@ from . import _lib
 from .sparse import GradSource, OccurrencePlan, field_array
 
 
+def _check_precision(name):
+    if name not in ("tensor", "bf16", "fp32"):
+        raise ValueError(f"AFM.attention_precision must be 'tensor' or 'fp32', got {name!r}")
+    return name
+
+
 class _AfmPooling(torch.autograd.Function):
     """(w1, b1, w2, b2, idx_0.., table_0..) -> pooled[B, D]."""
 
@@ -40,7 +46,7 @@ class _AfmPooling(torch.autograd.Function):
         B = int(idx[0].shape[0])
         dev = w1.device
         out = torch.empty(B, D, dtype=torch.float32, device=dev)
-        fwd = lib.rk_afm_tc_fwd if precision == "bf16" else lib.rk_afm_fwd
+        fwd = lib.rk_afm_tc_fwd if precision in ("tensor", "bf16") else lib.rk_afm_fwd
         rc = fwd(fields, F, w1.data_ptr(), b1.data_ptr(), w2.data_ptr(), b2.data_ptr(), A, B,
                  out.data_ptr(), _lib.err_flag(dev).data_ptr(), _lib.stream_ptr())
         _lib.check(rc, "rk_afm_fwd")
@@ -68,7 +74,7 @@ class _AfmPooling(torch.autograd.Function):
         g_out = _lib.require_cuda(g_out, "g_pooled", torch.float32)
         g_rows = torch.empty(B, F * D, dtype=torch.float32, device=dev)
         g_att = torch.empty(A * D + 2 * A + 1, dtype=torch.float32, device=dev)   # w1 | b1 | w2 | b2
-        tc = ctx.precision == "bf16"
+        tc = ctx.precision in ("tensor", "bf16")
         n_ctas = (lib.rk_afm_tc_bwd_ctas if tc else lib.rk_afm_bwd_ctas)(B, F)
         partials = torch.empty(n_ctas * g_att.numel(), dtype=torch.float32, device=dev)
         base = g_att.data_ptr()
@@ -103,15 +109,16 @@ class AFM(nn.Module):
         self.attention = nn.Sequential(
             nn.Linear(embedding_dim, attention_factor), nn.ReLU(), nn.Linear(attention_factor, 1))
         self.p = nn.Linear(embedding_dim, 1)
-        # "fp32": SIMT kernels (csrc/afm.cu), the reference's arithmetic; "bf16": the attention MLP on
-        # tcgen05 with split-bf16 operands and fp32 accumulation (csrc/afm_tc.cu).  Not a parameter.
-        self.attention_precision = "fp32"
+        # "tensor" (default): the attention MLP on tcgen05 (csrc/afm_tc.cu) — split-bf16 operands, fp32
+        # accumulation, ReLU decisions re-checked in fp32 — inside the 1e-5 bar against the reference;
+        # "fp32": the SIMT kernels (csrc/afm.cu).  ("bf16" is accepted as an alias of "tensor".)  Not a parameter.
+        self.attention_precision = "tensor"
 
     def forward(self, dense_input, category_input):
         dense_logit = self.dense_layer(dense_input)
         cols = self.category_features
         pooled = _AfmPooling.apply(
-            (len(cols), self.attention_precision), self.attention[0].weight, self.attention[0].bias, self.attention[2].weight,
+            (len(cols), _check_precision(self.attention_precision)), self.attention[0].weight, self.attention[0].bias, self.attention[2].weight,
             self.attention[2].bias, *[category_input[c] for c in cols],
             *[self.embeddings[c].weight for c in cols])
         total_logit = dense_logit + self.p(pooled)

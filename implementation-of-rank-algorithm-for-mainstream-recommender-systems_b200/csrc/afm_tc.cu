@@ -307,7 +307,7 @@ struct AfmTcBwdSmem {
     uint8_t *b3, *a1, *b1t, *a2, *b2t;   // b3 panel 0 and a1 are adjacent: a1 doubles as b3's second panel
     float   *e[2], *gout[2];
     int64_t *ix[2];
-    float   *bias, *w2, *score, *attn, *ga, *gs, *dot, *red;
+    float   *bias, *w2, *score, *attn, *ga, *gs, *dot, *red, *wmax;
     int     *pi, *pj, *pidx;
     uint64_t* bar;
     uint32_t* tmem_slot;
@@ -333,6 +333,7 @@ struct AfmTcBwdSmem {
         gs = (float*)q;    q += sizeof(float) * kAfmTcRows;
         dot = (float*)q;   q += sizeof(float) * kAfmTcMaxS;
         red = (float*)q;   q += sizeof(float) * kAfmTcThreads;
+        wmax = (float*)q;  q += sizeof(float) * 4;
         pi = (int*)q;      q += sizeof(int) * 128;
         pj = (int*)q;      q += sizeof(int) * 128;
         pidx = (int*)q;    q += sizeof(int) * 256;
@@ -342,7 +343,7 @@ struct AfmTcBwdSmem {
     static size_t bytes(const AfmTcParams& p) {
         return 1024 + 3 * 128 * 128 + 2 * 128 * 128 + 2 * 64 * 128 + 2 * sizeof(float) * p.S * p.fs.F * p.estride +
                2 * sizeof(float) * p.S * 32 + sizeof(float) * (2 * 128 + 4 * kAfmTcRows + kAfmTcMaxS + kAfmTcThreads) +
-               sizeof(int) * 512 + 16 + 2 * sizeof(int64_t) * 64;
+               sizeof(int) * 512 + 32 + 2 * sizeof(int64_t) * 64;
     }
 };
 
@@ -412,6 +413,18 @@ afm_bwd_tc_kernel(const __grid_constant__ AfmTcParams p, const float* __restrict
             x[j] = w;
         }
         store_chunk(sm.b2t + q * (64 * 128), n, c, x);
+    }
+    {   // max |W1|: scales the band around zero inside which a pre-activation is recomputed in fp32
+        float m = 0.f;
+        for (int i = tid; i < A * D; i += kAfmTcThreads) m = fmaxf(m, fabsf(__ldg(p.w1 + i)));
+        m = warp_max(m);
+        if (lane == 0) sm.red[warp] = m;
+        __syncthreads();
+        if (tid == 0) {
+            float t = 0.f;
+            for (int w = 0; w < kAfmTcThreads / 32; ++w) t = fmaxf(t, sm.red[w]);
+            sm.wmax[0] = t;
+        }
     }
     for (int i = tid; i < 2 * 128 * 128 / 16; i += kAfmTcThreads)       // mask columns >= Ap stay zero
         reinterpret_cast<uint4*>(sm.a2)[i] = make_uint4(0u, 0u, 0u, 0u);
@@ -498,12 +511,35 @@ afm_bwd_tc_kernel(const __grid_constant__ AfmTcParams p, const float* __restrict
         phase ^= 1;
         fence_after();
         PROF(3);
-        // ---- score and the 0/1 mask line (bf16 1.0 = 0x3F80)
+        // ---- score and the 0/1 mask line (bf16 1.0 = 0x3F80).  The ReLU decision is the one place where
+        // a 1e-6 error of the split-bf16 product can change a gradient by a whole term, so any
+        // pre-activation inside the error band around zero is recomputed in fp32 (about one element
+        // in 10^4): the mask is then the fp32 kernel's mask.
+        float band = 0.f;
+#pragma unroll
+        for (int d = 0; d < KP; ++d) band += fabsf(v[d]);
+        // worst case of the three-term split is ~1.9e-5 * sum|v_d W_d|; errors add like a random walk
+        // over the 32 terms, so a third of the worst case bounds them with a wide margin
+        band *= 7e-6f * sm.wmax[0];
+        // rare path: element a of this row was inside the band -> fp32 value decides the mask bit (the
+        // score is left alone: |relu(x)| < band there, far below its own rounding)
+        auto recheck = [&](int a) {
+            if (a >= A) return;
+            float t = 0.f;
+#pragma unroll
+            for (int d = 0; d < KP; ++d)
+                if (d < D) t = fmaf(v[d], __ldg(p.w1 + a * D + d), t);
+            const float x = t + sm.bias[a];
+            uint8_t* line = sm.a2 + (a >> 6) * (128 * 128) + tid * 128;
+            const int c = (a & 63) >> 3;
+            *reinterpret_cast<uint16_t*>(line + ((c ^ (tid & 7)) << 4) + (a & 7) * 2) = x > 0.f ? 0x3F80 : 0;
+        };
         float sc = b2;
         for (int ch = 0; ch < Ap / 64; ++ch) {           // one 64-column panel of the mask per TMEM load
             float h[64];
             tmem_ld64(my_tmem + 64 * ch, h);
             uint8_t* panel = sm.a2 + ch * (128 * 128);
+            float closest = INFINITY;                    // min |pre-activation| of this row in the chunk
 #pragma unroll
             for (int c = 0; c < 8; ++c) {
                 uint32_t w[4];
@@ -511,17 +547,26 @@ afm_bwd_tc_kernel(const __grid_constant__ AfmTcParams p, const float* __restrict
                 for (int j2 = 0; j2 < 4; ++j2) {
                     const int j = 8 * c + 2 * j2;
                     const float x0 = h[j] + sm.bias[64 * ch + j], x1 = h[j + 1] + sm.bias[64 * ch + j + 1];
+                    closest = fminf(closest, fminf(fabsf(x0), fabsf(x1)));
                     sc = fmaf(fmaxf(x0, 0.f), sm.w2[64 * ch + j], sc);
                     sc = fmaf(fmaxf(x1, 0.f), sm.w2[64 * ch + j + 1], sc);
                     w[j2] = (x0 > 0.f ? 0x3F80u : 0u) | (x1 > 0.f ? 0x3F800000u : 0u);
                 }
                 *reinterpret_cast<uint4*>(panel + tid * 128 + ((c ^ (tid & 7)) << 4)) = make_uint4(w[0], w[1], w[2], w[3]);
             }
+            if (__any_sync(kFull, closest < band)) {     // rare, warp-uniform: walk the chunk column by column
+#pragma unroll 1
+                for (int j = 0; j < 64; ++j) {
+                    const float x = tmem_ld1(my_tmem + 64 * ch + j) + sm.bias[64 * ch + j];
+                    if (fabsf(x) < band) recheck(64 * ch + j);
+                }
+            }
         }
         if (Ap & 32) {                                   // Ap = 32 or 96: the last 32 columns
             float h[32];
             tmem_ld32(my_tmem + (Ap - 32), h);
             uint8_t* panel = sm.a2 + ((Ap - 32) >> 6) * (128 * 128);
+            float closest = INFINITY;
 #pragma unroll
             for (int c = 0; c < 4; ++c) {
                 uint32_t w[4];
@@ -529,12 +574,20 @@ afm_bwd_tc_kernel(const __grid_constant__ AfmTcParams p, const float* __restrict
                 for (int j2 = 0; j2 < 4; ++j2) {
                     const int j = 8 * c + 2 * j2;
                     const float x0 = h[j] + sm.bias[Ap - 32 + j], x1 = h[j + 1] + sm.bias[Ap - 32 + j + 1];
+                    closest = fminf(closest, fminf(fabsf(x0), fabsf(x1)));
                     sc = fmaf(fmaxf(x0, 0.f), sm.w2[Ap - 32 + j], sc);
                     sc = fmaf(fmaxf(x1, 0.f), sm.w2[Ap - 32 + j + 1], sc);
                     w[j2] = (x0 > 0.f ? 0x3F80u : 0u) | (x1 > 0.f ? 0x3F800000u : 0u);
                 }
                 const int cc = (((Ap - 32) & 63) >> 3) + c;
                 *reinterpret_cast<uint4*>(panel + tid * 128 + ((cc ^ (tid & 7)) << 4)) = make_uint4(w[0], w[1], w[2], w[3]);
+            }
+            if (__any_sync(kFull, closest < band)) {
+#pragma unroll 1
+                for (int j = 0; j < 32; ++j) {
+                    const float x = tmem_ld1(my_tmem + (Ap - 32) + j) + sm.bias[Ap - 32 + j];
+                    if (fabsf(x) < band) recheck(Ap - 32 + j);
+                }
             }
         }
         sm.score[tid] = sc;

@@ -81,6 +81,13 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
 #pragma unroll
     for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
 }
+// one fp32 column of this thread's TMEM lane (slow paths that walk columns in a loop)
+__device__ __forceinline__ float tmem_ld1(uint32_t taddr) {
+    uint32_t r;
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x1.b32 {%0}, [%1];" : "=r"(r) : "r"(taddr));
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+    return __uint_as_float(r);
+}
 // 64 consecutive fp32 columns of this thread's TMEM lane in one instruction (one wait instead of two)
 __device__ __forceinline__ void tmem_ld64(uint32_t taddr, float (&v)[64]) {
     uint32_t r[64];

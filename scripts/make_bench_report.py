@@ -8,7 +8,7 @@ import os
 import sys
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-ORDER = ["dcn", "deepfm", "fwfm", "afm", "afm_tc", "din", "din_softmax", "din_tc", "din_softmax_tc", "bst", "deepcrossing"]
+ORDER = ["dcn", "deepfm", "fwfm", "afm", "afm_fp32", "din", "din_softmax", "din_tc", "din_softmax_tc", "bst", "deepcrossing"]
 
 
 def main(tag):

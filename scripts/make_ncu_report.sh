@@ -25,14 +25,14 @@ python $S launches $src/launches_dcn.csv crossnet_fwd_kernel
 echo; echo "## Launch list — DIN step, tensor-core activation unit (eager, B = 8192, T = 50)"; echo
 python $S launches $src/launches_din_tc.csv din_fwd_tc_kernel
 echo; echo "## Launch list — AFM step, tensor-core attention (eager, B = 8192, F = 10, D = 32, A = 128)"; echo
-python $S launches $src/launches_afm_tc.csv afm_fwd_tc_kernel
-for w in dcn din_tc afm_tc fwfm; do
+python $S launches $src/launches_afm.csv afm_fwd_tc_kernel
+for w in dcn din_tc afm fwfm; do
   echo; echo "## Full capture — $w"
   python $S full $src/full_$w.ncu-rep
   ncu -i $src/full_$w.ncu-rep --page raw --csv > profiles/${tag}_full_$w.raw.csv 2>/dev/null
 done
 cp $src/launches_dcn.csv profiles/${tag}_launches_dcn.csv
 cp $src/launches_din_tc.csv profiles/${tag}_launches_din_tc.csv
-cp $src/launches_afm_tc.csv profiles/${tag}_launches_afm_tc.csv
+cp $src/launches_afm.csv profiles/${tag}_launches_afm.csv
 } > $out.new
 echo "wrote $out.new"

@@ -5,7 +5,7 @@ deltas of thread 0 accumulated per phase), runs a workload's step a few times an
 of each phase.  Only ONE instrumented kernel may run per measurement (they share the counters):
     python scripts/phase_profile.py build                 # here (nvcc)
     python scripts/phase_profile.py run din_tc fwd        # on the GPU box: DIN tensor-core forward
-    python scripts/phase_profile.py run afm_tc fwd|bwd
+    python scripts/phase_profile.py run afm fwd|bwd
 """
 import ctypes, subprocess, sys, tempfile
 from pathlib import Path
@@ -15,8 +15,8 @@ PROF = ROOT / "scripts" / "_prof" / "librank_b200_prof.so"
 PHASES = {
     ("din_tc", "fwd"): ["setup", "group load", "wait rows", "build A1", "mma1+prefetch", "epilogue1", "mma2", "epilogue2",
                         "weights", "pooling", "assembly"],
-    ("afm_tc", "fwd"): ["setup", "wait rows", "build A1", "mma1+prefetch", "epilogue", "softmax", "pool store", "pool sum"],
-    ("afm_tc", "bwd"): ["setup", "wait rows", "build A1", "mma1+prefetch", "epilogue1+mask", "softmax+g_s", "X line",
+    ("afm", "fwd"): ["setup", "wait rows", "build A1", "mma1+prefetch", "epilogue", "softmax", "pool store", "pool sum"],
+    ("afm", "bwd"): ["setup", "wait rows", "build A1", "mma1+prefetch", "epilogue1+mask", "softmax+g_s", "X line",
                         "mma2+mma3", "epilogue2", "g_rows", "final"],
 }
 

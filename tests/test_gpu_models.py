@@ -198,14 +198,17 @@ def test_din_attention_function_gradients():
         assert rel_err(qa.grad, q.grad) <= FP32_TOL and rel_err(ka.grad, k.grad) <= FP32_TOL
 
 
+@pytest.mark.parametrize("precision", ["tensor", "fp32"])
 @pytest.mark.parametrize("B,F,D,A", [(2048, 10, 32, 128), (1000, 7, 16, 64), (513, 3, 8, 20), (300, 16, 4, 128)])
-def test_afm_vs_oracle(B, F, D, A):
+def test_afm_vs_oracle(B, F, D, A, precision):
+    """Both attention kernels (tcgen05 default, fp32 SIMT) against the oracle at the fp32 bar."""
     fc = synthetic.afm_feature_columns(F, extra_vocab=5000)
     torch.manual_seed(0)
     ours = rank_b200.AFM(fc, D, A)
     ref = oracle_models.OracleAFM(fc, D, A)
     ref.load_state_dict(ours.state_dict(), strict=True)
     ours.to(DEV)
+    ours.attention_precision = precision
     compare(*_run_both(ours, ref, "AFM", synthetic.afm_batch(B, fc)))
 
 
@@ -286,11 +289,11 @@ def test_afm_tensor_core_attention(B, F, D, A):
     ref = oracle_models.OracleAFM(fc, D, A)
     ref.load_state_dict(ours.state_dict(), strict=True)
     ours.to(DEV)
-    ours.attention_precision = "bf16"
+    ours.attention_precision = "tensor"
     o_outs, o_grads, r_outs, r_grads, _, g64 = _run_both(ours, ref, "AFM", synthetic.afm_batch(B, fc))
     print("afm tc: logit err %.3e" % rel_err(o_outs[1], r_outs[1]),
           {k: "%.2e" % rel_err(o_grads[k], r_grads[k]) for k in r_grads if k.startswith("attention")})
-    compare(o_outs, o_grads, r_outs, r_grads, BF16_TOL, g64)
+    compare(o_outs, o_grads, r_outs, r_grads, FP32_TOL, g64)
 
 
 # ---------------------------------------------------------------------------------- FwFM
