@@ -209,7 +209,10 @@ int rk_afm_tc_fwd(const rk_field_t* fields, int F, const float* w1, const float*
 /* The backward on the tensor cores: same arguments and outputs as rk_afm_bwd, with
  * n_ctas = rk_afm_tc_bwd_ctas(B, F).  The hidden layer only enters through its 0/1 ReLU mask
  * (exact in bf16), the other operands are split-bf16; the weight-gradient accumulator lives in
- * TMEM for the life of a CTA and the per-CTA partials are added in a fixed order. */
+ * TMEM for the life of a CTA and the per-CTA partials are added in a fixed order.  A ReLU
+ * decision whose pre-activation lies inside the error band of the split product is recomputed
+ * in fp32, so the masks are the fp32 kernel's masks and the results meet the fp32 parity bar
+ * (1e-5); these two entry points are what the AFM module uses by default. */
 int rk_afm_tc_bwd_ctas(int64_t B, int F);
 int rk_afm_tc_bwd(const rk_field_t* fields, int F, const float* w1, const float* b1, const float* w2,
                   const float* b2, int A, int64_t B, const float* g_out, float* g_rows, float* g_w1,
