@@ -400,19 +400,26 @@ afm_bwd_tc_kernel(const __grid_constant__ AfmTcParams p, const float* __restrict
         sm.bias[n] = n < A ? __ldg(p.b1 + n) : 0.f;
         sm.w2[n]   = n < A ? __ldg(p.w2 + n) : 0.f;
     }
-    // B2 lines n < KP: hi of w2[a] W1[a][n]; n >= KP: lo.  K = a, 64 per panel.
-    for (int item = tid; item < N2 * 16; item += kAfmTcThreads) {
-        const int n = item >> 4, c16 = item & 15, q = c16 >> 3, c = c16 & 7;
-        const int d = n < KP ? n : n - KP;
-        float x[8];
+    // B2 lines n < KP: hi of w2[a] W1[a][n]; n >= KP: lo.  K = a, 64 per panel.  W1 is read row-major
+    // (coalesced float4) and scattered into the transposed tile two bytes at a time.
+    for (int i = tid; i < 2 * 64 * 128 / 16; i += kAfmTcThreads)
+        reinterpret_cast<uint4*>(sm.b2t)[i] = make_uint4(0u, 0u, 0u, 0u);
+    __syncthreads();
+    for (int item = tid; item < A * (D >> 2); item += kAfmTcThreads) {
+        const int a = item / (D >> 2), d0 = 4 * (item - a * (D >> 2));
+        const float4 w4 = __ldg(reinterpret_cast<const float4*>(p.w1 + a * D + d0));
+        const float w2a = __ldg(p.w2 + a);
+        const float w[4] = {w2a * w4.x, w2a * w4.y, w2a * w4.z, w2a * w4.w};
+        uint8_t* panel = sm.b2t + (a >> 6) * (64 * 128);
+        const int c = (a & 63) >> 3, e = (a & 7) * 2;
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-            const int a = 64 * q + 8 * c + j;
-            float w = (a < A && d < D) ? __ldg(p.w2 + a) * __ldg(p.w1 + a * D + d) : 0.f;
-            if (n >= KP) w -= __bfloat162float(__float2bfloat16_rn(w));
-            x[j] = w;
+        for (int j = 0; j < 4; ++j) {
+            const __nv_bfloat16 hi = __float2bfloat16_rn(w[j]);
+            const __nv_bfloat16 lo = __float2bfloat16_rn(w[j] - __bfloat162float(hi));
+            const int nh = d0 + j, nl = KP + d0 + j;
+            *reinterpret_cast<__nv_bfloat16*>(panel + nh * 128 + ((c ^ (nh & 7)) << 4) + e) = hi;
+            *reinterpret_cast<__nv_bfloat16*>(panel + nl * 128 + ((c ^ (nl & 7)) << 4) + e) = lo;
         }
-        store_chunk(sm.b2t + q * (64 * 128), n, c, x);
     }
     {   // max |W1|: scales the band around zero inside which a pre-activation is recomputed in fp32
         float m = 0.f;
@@ -752,13 +759,10 @@ afm_bwd_tc_kernel(const __grid_constant__ AfmTcParams p, const float* __restrict
             outp[A * D + A + tid] = gw2;
         }
     }
-    sm.red[tid] = gb2_acc;
+    gb2_acc = warp_sum(gb2_acc);                      // fixed shuffle tree, then the four warp sums in order
+    if (lane == 0) sm.red[warp] = gb2_acc;
     __syncthreads();
-    if (tid == 0) {
-        float t = 0.f;
-        for (int i = 0; i < kAfmTcThreads; ++i) t += sm.red[i];
-        outp[A * D + 2 * A] = t;
-    }
+    if (tid == 0) outp[A * D + 2 * A] = (sm.red[0] + sm.red[1]) + (sm.red[2] + sm.red[3]);
     PROF(10);
     PROF_END;
     fence_before();

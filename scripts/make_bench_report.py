@@ -39,16 +39,23 @@ def main(tag):
             "%.0fx" % (d["e2e"]["value"] / cpu["value"]) if cpu else "-",
             1000 * r["hot_ms_per_step"], 1000 * r["hot_ms_per_step_warm_l2"], r["achieved"], r["frac"],
             d["gpu_launches"] / d["steps"]))
-    out += ["", "## Per-call device time of the hot path (us per step, L2 flushed before every step)", "",
-            "| workload | " + " | ".join(["forward", "backward", "rk_plan_build", "rk_embgrad_segment_reduce", "other"]) + " |",
-            "|---|---:|---:|---:|---:|---:|"]
+    out += ["", "## Per-call device time of the library calls of a step (us per step, L2 flushed before every step)", "",
+            "forward / backward = the fused interaction kernels; tower = the fused Dice / BatchNorm layers of the DNN tower",
+            "(`rk_dice_bn_*`, `rk_bn_act_*`: outside the hot-path roofline, inside the step).", "",
+            "| workload | " + " | ".join(["forward", "backward", "rk_plan_build", "rk_embgrad_segment_reduce", "other hot path",
+                                         "tower fwd", "tower bwd"]) + " |",
+            "|---|---:|---:|---:|---:|---:|---:|---:|"]
     for k in keys:
         calls = {n: 1000 * v["ms_per_step"] for n, v in rows[k]["hotpath_calls"].items()}
-        fwd = sum(v for n, v in calls.items() if n.endswith("_fwd"))
-        bwd = sum(v for n, v in calls.items() if n.endswith("_bwd"))
+        tower = lambda n: n.startswith("rk_dice_bn") or n.startswith("rk_bn_act")
+        fwd = sum(v for n, v in calls.items() if n.endswith("_fwd") and not tower(n))
+        bwd = sum(v for n, v in calls.items() if n.endswith("_bwd") and not tower(n))
+        tf = sum(v for n, v in calls.items() if n.endswith("_fwd") and tower(n))
+        tb = sum(v for n, v in calls.items() if n.endswith("_bwd") and tower(n))
         plan, seg = calls.get("rk_plan_build", 0.0), calls.get("rk_embgrad_segment_reduce", 0.0)
-        other = sum(calls.values()) - fwd - bwd - plan - seg
-        out.append("| %s | %.1f | %.1f | %.1f | %.1f | %.1f |" % (rows[k]["config"]["workload"], fwd, bwd, plan, seg, other))
+        other = max(0.0, sum(calls.values()) - fwd - bwd - plan - seg - tf - tb)
+        out.append("| %s | %.1f | %.1f | %.1f | %.1f | %.1f | %.1f | %.1f |" % (
+            rows[k]["config"]["workload"], fwd, bwd, plan, seg, other, tf, tb))
     if ref:
         out += ["", "## Reference arm (`bench.py --impl reference --workload dcn`)", "",
                 "%.3g samples/s on %d host cores (%s)." % (ref["value"], ref["cpu_baseline"]["cores"], ref["cpu_baseline"]["sample"])]
