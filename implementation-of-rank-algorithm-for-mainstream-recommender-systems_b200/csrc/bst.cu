@@ -13,6 +13,7 @@
 // fixed order (no atomics).
 #include <string.h>
 #include "common.cuh"
+#include "prof.cuh"
 
 namespace rk {
 
@@ -295,6 +296,7 @@ bst_bwd_kernel(const __grid_constant__ BstParams p, const float* __restrict__ g_
     constexpr int DH = 16 / H;
     extern __shared__ __align__(16) float smem_raw[];
     BstSmem sm(smem_raw, p.T, H, true);
+    PROF_DECL
     bst_stage_weights(p, sm, true);
     __syncthreads();
     const int r = threadIdx.x, T = p.T;
@@ -309,6 +311,7 @@ bst_bwd_kernel(const __grid_constant__ BstParams p, const float* __restrict__ g_
     float pacc[16];
 #pragma unroll
     for (int i = 0; i < 16; ++i) pacc[i] = 0.f;
+    PROF(0);
 
     for (int64_t tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
         const int64_t b0 = tile * p.S;
@@ -345,13 +348,14 @@ bst_bwd_kernel(const __grid_constant__ BstParams p, const float* __restrict__ g_
             store_row(sm.qks + r * kBstLd, zero16);
         }
         __syncthreads();
+        PROF(1); PROF_COUNT(12);
         if (on) {
             float q[16], qk[16], ctx[16], mh[H], lh[H];
             load_row(sm.qs + r * kBstLd, q);
             load_row(sm.qks + r * kBstLd, qk);
             bst_attend<H>(q, sm.ks, sm.vs, row0, L, ctx, mh, lh);
 #pragma unroll
-            for (int h = 0; h < H; ++h) { sm.mrow[r * H + h] = mh[h]; sm.lrow[r * H + h] = lh[h]; }
+            for (int h = 0; h < H; ++h) { sm.mrow[r * H + h] = mh[h]; sm.lrow[r * H + h] = 1.0f / lh[h]; }   // lrow holds 1 / sum
             store_row(sm.cs + r * kBstLd, ctx);
             float z[16], o1[16], hp[16], f[16], y[16];
             set_vec(z, sm.vec + VBO * 16);
@@ -375,6 +379,7 @@ bst_bwd_kernel(const __grid_constant__ BstParams p, const float* __restrict__ g_
             store_row(sm.cs + r * kBstLd, zero16);
         }
         // ---- B. upstream gradient of this row, LayerNorm 2 backward
+        PROF(2);
         float dy[16], dz[16];
 #pragma unroll
         for (int i = 0; i < 16; ++i) dy[i] = 0.f;
@@ -402,6 +407,7 @@ bst_bwd_kernel(const __grid_constant__ BstParams p, const float* __restrict__ g_
             for (int i = 0; i < 16; ++i) { dz[i] = 0.f; act[i] = 0.f; }
         }
         // ---- C. FFN backward
+        PROF(3);
         store_row(sm.gs + r * kBstLd, dz);
         store_row(sm.as + r * kBstLd, act);
         __syncthreads();
@@ -429,6 +435,7 @@ bst_bwd_kernel(const __grid_constant__ BstParams p, const float* __restrict__ g_
         for (int i = 0; i < 16; ++i) do1[i] = dz[i];
         if (on) matvec16(sm.w + M1 * 256, dh, do1);                  // + W1^T dh
         // ---- D. LayerNorm 1 backward, output projection backward
+        PROF(4);
         {
             float t0[16];
 #pragma unroll
@@ -462,6 +469,7 @@ bst_bwd_kernel(const __grid_constant__ BstParams p, const float* __restrict__ g_
         store_row(sm.dc + r * kBstLd, dctx);
         __syncthreads();
         // ---- E. attention backward: as a query (dq) and as a key (dk, dv)
+        PROF(5);
         float dq[16], dk[16], dv[16];
 #pragma unroll
         for (int i = 0; i < 16; ++i) { dq[i] = 0.f; dk[i] = 0.f; dv[i] = 0.f; }
@@ -470,40 +478,48 @@ bst_bwd_kernel(const __grid_constant__ BstParams p, const float* __restrict__ g_
             load_row(sm.qs + r * kBstLd, q);
             load_row(sm.ks + r * kBstLd, kme);
             load_row(sm.vs + r * kBstLd, vme);
+            // as a query: one pass over the L live keys, the H heads side by side (independent exp chains)
+            float mq[H], ilq[H], dlq[H];
 #pragma unroll
-            for (int h = 0; h < H; ++h) {
-                const float m = sm.mrow[r * H + h], inv_l = 1.0f / sm.lrow[r * H + h], dl = sm.delta[r * H + h];
-                for (int u = 0; u < L; ++u) {
-                    const float* kr = sm.ks + (row0 + u) * kBstLd + h * DH;
-                    const float* vr = sm.vs + (row0 + u) * kBstLd + h * DH;
+            for (int h = 0; h < H; ++h) { mq[h] = sm.mrow[r * H + h]; ilq[h] = sm.lrow[r * H + h]; dlq[h] = sm.delta[r * H + h]; }
+            for (int u = 0; u < L; ++u) {
+                float kr[16], vr[16];
+                load_row(sm.ks + (row0 + u) * kBstLd, kr);
+                load_row(sm.vs + (row0 + u) * kBstLd, vr);
+#pragma unroll
+                for (int h = 0; h < H; ++h) {
                     float sc = 0.f, dA = 0.f;
 #pragma unroll
                     for (int j = 0; j < DH; ++j) {
-                        sc = fmaf(q[h * DH + j], kr[j], sc);
-                        dA = fmaf(dctx[h * DH + j], vr[j], dA);
+                        sc = fmaf(q[h * DH + j], kr[h * DH + j], sc);
+                        dA = fmaf(dctx[h * DH + j], vr[h * DH + j], dA);
                     }
-                    const float a  = expf(sc * scale - m) * inv_l;
-                    const float dS = a * (dA - dl) * scale;
+                    const float a  = expf(sc * scale - mq[h]) * ilq[h];
+                    const float dS = a * (dA - dlq[h]) * scale;
 #pragma unroll
-                    for (int j = 0; j < DH; ++j) dq[h * DH + j] = fmaf(dS, kr[j], dq[h * DH + j]);
+                    for (int j = 0; j < DH; ++j) dq[h * DH + j] = fmaf(dS, kr[h * DH + j], dq[h * DH + j]);
                 }
-                if (t < L) {   // this row is a live key: every position of the sample queries it
-                    for (int tq = 0; tq < T; ++tq) {
-                        const int rq = row0 + tq;
-                        const float* qr = sm.qs + rq * kBstLd + h * DH;
-                        const float* dr = sm.dc + rq * kBstLd + h * DH;
+            }
+            if (t < L) {   // this row is a live key: every position of the sample queries it
+                for (int tq = 0; tq < T; ++tq) {
+                    const int rq = row0 + tq;
+                    float qr[16], dr[16];
+                    load_row(sm.qs + rq * kBstLd, qr);
+                    load_row(sm.dc + rq * kBstLd, dr);
+#pragma unroll
+                    for (int h = 0; h < H; ++h) {
                         float sc = 0.f, dA = 0.f;
 #pragma unroll
                         for (int j = 0; j < DH; ++j) {
-                            sc = fmaf(qr[j], kme[h * DH + j], sc);
-                            dA = fmaf(dr[j], vme[h * DH + j], dA);
+                            sc = fmaf(qr[h * DH + j], kme[h * DH + j], sc);
+                            dA = fmaf(dr[h * DH + j], vme[h * DH + j], dA);
                         }
-                        const float a  = expf(sc * scale - sm.mrow[rq * H + h]) / sm.lrow[rq * H + h];
+                        const float a  = expf(sc * scale - sm.mrow[rq * H + h]) * sm.lrow[rq * H + h];
                         const float dS = a * (dA - sm.delta[rq * H + h]) * scale;
 #pragma unroll
                         for (int j = 0; j < DH; ++j) {
-                            dv[h * DH + j] = fmaf(a, dr[j], dv[h * DH + j]);
-                            dk[h * DH + j] = fmaf(dS, qr[j], dk[h * DH + j]);
+                            dv[h * DH + j] = fmaf(a, dr[h * DH + j], dv[h * DH + j]);
+                            dk[h * DH + j] = fmaf(dS, qr[h * DH + j], dk[h * DH + j]);
                         }
                     }
                 }
@@ -511,6 +527,7 @@ bst_bwd_kernel(const __grid_constant__ BstParams p, const float* __restrict__ g_
         }
         __syncthreads();
         // ---- F. projection backward, input gradient, position-table gradient
+        PROF(6);
         store_row(sm.gs + r * kBstLd, dq);
         __syncthreads();
         bst_outer(sm.gs, sm.qks, rows, macc[MQ]);
@@ -527,6 +544,7 @@ bst_bwd_kernel(const __grid_constant__ BstParams p, const float* __restrict__ g_
         bst_colsum(sm.gs, nullptr, rows, sm.vsum[7 * 32 + (r & 31)]);               // d b_v
         __syncthreads();
         float dqk[16];
+        PROF(7);
 #pragma unroll
         for (int i = 0; i < 16; ++i) dqk[i] = dz1[i];                // residual path of LayerNorm 1
         if (on) {
@@ -540,6 +558,7 @@ bst_bwd_kernel(const __grid_constant__ BstParams p, const float* __restrict__ g_
         }
         store_row(sm.gs + r * kBstLd, dqk);
         __syncthreads();
+        PROF(8);
 #pragma unroll
         for (int i = 0; i < 16; ++i) {
             const int e = r + i * kBstThreads;
@@ -551,9 +570,12 @@ bst_bwd_kernel(const __grid_constant__ BstParams p, const float* __restrict__ g_
             }
         }
         __syncthreads();
+        PROF(9);
     }
 
     // ---- per-CTA partials of the registered parameters
+    PROF(10);
+    PROF_END;
     float* out = partials + (int64_t)blockIdx.x * (T * 16 + 6 * 256 + 160);
 #pragma unroll
     for (int i = 0; i < 16; ++i) {

@@ -15,6 +15,8 @@ PROF = ROOT / "scripts" / "_prof" / "librank_b200_prof.so"
 PHASES = {
     ("din_tc", "fwd"): ["setup", "group load", "wait rows", "build A1", "mma1+prefetch", "epilogue1", "mma2", "epilogue2",
                         "weights", "pooling", "assembly"],
+    ("bst", "bwd"): ["setup", "A1 recompute q/k/v", "A2 attention+ffn fwd", "B ln2 bwd", "C ffn bwd", "D ln1+wo bwd",
+                     "E attention bwd", "F1 dq/dk/dv outer", "F2 input grad", "F3 pos grad", "final"],
     ("afm", "fwd"): ["setup", "wait rows", "build A1", "mma1+prefetch", "epilogue", "softmax", "pool store", "pool sum"],
     ("afm", "bwd"): ["setup", "wait rows", "build A1", "mma1+prefetch", "epilogue1+mask", "softmax+g_s", "X line",
                         "mma2+mma3", "epilogue2", "g_rows", "final"],
