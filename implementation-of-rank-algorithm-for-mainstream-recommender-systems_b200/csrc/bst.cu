@@ -159,35 +159,45 @@ __device__ __forceinline__ void bst_attend(const float (&q)[16], const float* __
                                            float (&m_out)[H], float (&l_out)[H]) {
     constexpr int DH = 16 / H;
     const float scale = 1.0f / sqrtf((float)DH);
+    // two passes over the live keys, the H heads side by side (independent chains, one row load per key)
+    float m[H], l[H];
+#pragma unroll
+    for (int h = 0; h < H; ++h) { m[h] = -INFINITY; l[h] = 0.f; }
+#pragma unroll
+    for (int i = 0; i < 16; ++i) ctx[i] = 0.f;
+    for (int u = 0; u < L; ++u) {
+        float kr[16];
+        load_row(ks + (row0 + u) * kBstLd, kr);
+#pragma unroll
+        for (int h = 0; h < H; ++h) {
+            float s = 0.f;
+#pragma unroll
+            for (int j = 0; j < DH; ++j) s = fmaf(q[h * DH + j], kr[h * DH + j], s);
+            m[h] = fmaxf(m[h], s * scale);
+        }
+    }
+    for (int u = 0; u < L; ++u) {
+        float kr[16], vr[16];
+        load_row(ks + (row0 + u) * kBstLd, kr);
+        load_row(vs + (row0 + u) * kBstLd, vr);
+#pragma unroll
+        for (int h = 0; h < H; ++h) {
+            float s = 0.f;
+#pragma unroll
+            for (int j = 0; j < DH; ++j) s = fmaf(q[h * DH + j], kr[h * DH + j], s);
+            const float pr = expf(s * scale - m[h]);
+            l[h] += pr;
+#pragma unroll
+            for (int j = 0; j < DH; ++j) ctx[h * DH + j] = fmaf(pr, vr[h * DH + j], ctx[h * DH + j]);
+        }
+    }
+    // L == 0: every key masked -> 0/0 = NaN, exactly as softmax over all -inf in the reference
 #pragma unroll
     for (int h = 0; h < H; ++h) {
-        float m = -INFINITY;
-        for (int u = 0; u < L; ++u) {
-            const float* kr = ks + (row0 + u) * kBstLd + h * DH;
-            float s = 0.f;
 #pragma unroll
-            for (int j = 0; j < DH; ++j) s = fmaf(q[h * DH + j], kr[j], s);
-            m = fmaxf(m, s * scale);
-        }
-        float l = 0.f, c[DH];
-#pragma unroll
-        for (int j = 0; j < DH; ++j) c[j] = 0.f;
-        for (int u = 0; u < L; ++u) {
-            const float* kr = ks + (row0 + u) * kBstLd + h * DH;
-            const float* vr = vs + (row0 + u) * kBstLd + h * DH;
-            float s = 0.f;
-#pragma unroll
-            for (int j = 0; j < DH; ++j) s = fmaf(q[h * DH + j], kr[j], s);
-            const float pr = expf(s * scale - m);
-            l += pr;
-#pragma unroll
-            for (int j = 0; j < DH; ++j) c[j] = fmaf(pr, vr[j], c[j]);
-        }
-        // L == 0: every key masked -> 0/0 = NaN, exactly as softmax over all -inf in the reference
-#pragma unroll
-        for (int j = 0; j < DH; ++j) ctx[h * DH + j] = c[j] / l;
-        m_out[h] = m;
-        l_out[h] = l;
+        for (int j = 0; j < DH; ++j) ctx[h * DH + j] = ctx[h * DH + j] / l[h];
+        m_out[h] = m[h];
+        l_out[h] = l[h];
     }
 }
 
