@@ -393,7 +393,7 @@ def run_reference(args, wl):
                          "sample": f"{r['steps']} full steps of batch {B} (fwd+loss+bwd), host CPU"},
         "e2e": {"value": r["value"], "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 # ------------------------------------------------------------------------------- our arm
@@ -615,7 +615,7 @@ def run_ours(args, wl):
             line["cpu_baseline"] = {"value": r["value"], "unit": "samples/s", "cores": r["cores"], "kind": "port",
                                     "sample": f"{r['steps']} full steps of batch {B} (fwd+loss+bwd) of the oracle "
                                               "port, torch CPU fp32"}
-        print(json.dumps(line), flush=True)
+        emit(line)
     if world > 1:
         torch.distributed.destroy_process_group()
 
@@ -637,6 +637,28 @@ def stepper_launches_per_replay(stepper, lib):
     return n
 
 
+_JSON_FD = None
+
+
+def claim_stdout():
+    """stdout carries exactly ONE line, the JSON result.  Libraries write there too (NCCL prints its
+    version banner on stdout when the first communicator is created), so file descriptor 1 is pointed
+    at stderr for the whole run and the result line goes to a private duplicate of the real stdout."""
+    global _JSON_FD
+    sys.stdout.flush()
+    _JSON_FD = os.dup(1)
+    os.dup2(2, 1)
+
+
+def emit(line):
+    data = (json.dumps(line) + "\n").encode()
+    if _JSON_FD is None:
+        sys.stdout.write(data.decode())
+        sys.stdout.flush()
+    else:
+        os.write(_JSON_FD, data)
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -648,6 +670,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="launch every step eagerly instead of a CUDA graph")
     args = ap.parse_args()
+    claim_stdout()
     args.warmup = max(args.warmup, 3)
     wl = WORKLOADS[args.workload]()
     if args.impl == "reference":
