@@ -24,6 +24,7 @@ from .afm import AFM, create_feature_columns
 from .sharded import RowShardedEmbedding, shard_bst_feedid_table
 from .bst import BSTModel, BSTTransformer, leakyrelu, load_vocabulary
 from .staging import PackedBatch
+from .loader import EncodedWechat
 
 __all__ = [
     "RankB200Error", "check_index_errors", "library_path",
@@ -32,5 +33,5 @@ __all__ = [
     "DeepFM", "FwFM", "DCNModel", "cross_layer", "DeepCrossingModel", "residual_unit", "DIN", "Dice", "din_attention", "din_collate_fn", "set_activation_unit_precision",
     "get_activation_unit_precision",
     "AFM", "create_feature_columns", "RowShardedEmbedding", "shard_bst_feedid_table", "BSTModel", "BSTTransformer", "leakyrelu", "load_vocabulary",
-    "PackedBatch",
+    "PackedBatch", "EncodedWechat",
 ]

@@ -201,6 +201,22 @@ def main():
         fx = record(m, lambda: (m(x),), 29, dict(
             model="FwFM", ctor=dict(field_dims=dims, embed_dim=D), inputs=dict(x=x)))
         save(fx, f"fwfm_d{D}.pt")
+    # ---- loader: batches of the reference WechatDataset + DataLoader on the synthetic frame of tests/loader_cases.py
+    sys.path.insert(0, os.path.dirname(HERE))
+    import loader_cases
+    from torch.utils.data import DataLoader
+    ldir = tempfile.mkdtemp(prefix="rk_golden_loader_")
+    lvocab = loader_cases.write_vocab(os.path.join(ldir, "vocab")) + "/"
+    lpath = os.path.join(ldir, "frame.parquet")
+    loader_cases.make_frame("string").to_parquet(lpath)
+    recorded = {}
+    for kind, rel in (("deepfm", "DeepFM/deepfm.py"), ("dcn", "DCN/dcn.py"), ("deepcrossing", "DeepCrossing/deepcrossing.py"),
+                      ("din", "DIN/din.py"), ("bst", "BST/bst.py")):
+        ref = load_reference(rel, "ref_loader_" + kind)
+        ds = ref.WechatDataset(lpath, lvocab, 5) if kind == "bst" else ref.WechatDataset(lpath, lvocab)
+        kw = {"collate_fn": ref.din_collate_fn} if kind == "din" else {}
+        recorded[kind] = list(DataLoader(ds, batch_size=8, shuffle=False, **kw))
+    save(recorded, "loader_batches.pt")
     print("golden fixtures written to", HERE)
 
 
