@@ -11,7 +11,7 @@ import golden_cases
 from oracle import interactions as X
 from oracle import models as oracle_models
 
-MODEL_FIXTURES = [p for p in golden_files() if "smoke" not in p]
+MODEL_FIXTURES = [p for p in golden_files() if "smoke" not in p and "loader" not in p]
 TOL = 2e-6   # same torch ops in (almost) the same order: far inside the 1e-5 bar
 
 
