@@ -87,6 +87,7 @@ PROTOTYPES = {
     "rk_dice_bn_bwd": (_I, [_P, _P, _L, _I, _P, _P, _P, _P, _P, _P, _P, _P]),
     "rk_bn_act_fwd": (_I, [_P, _L, _I, _P, _P, _F, _F, _P, _P, _P, _F, _P, _P, _P]),
     "rk_bn_act_bwd": (_I, [_P, _P, _L, _I, _P, _P, _F, _P, _P, _P, _P, _P]),
+    "rk_rowwise_adam": (_I, [_P, _P, _P, _P, _P, _L, _I, _L, _F, _F, _F, _F, _L, _P, _P]),
     "rk_shard_owner": (_I, [_P, _L, _L, _L, _P, _P, _P]),
     "rk_shard_route": (_I, [_P, _P, _P, _L, _L, _L, _I, _P, _P, _P, _P]),
     "rk_plan_compact": (_I, [_P, _L, _L, _P, _P, _P, _P]),

@@ -249,6 +249,17 @@ int rk_bn_act_bwd(const float* x, const float* g_z, int64_t B, int units, const 
                   const float* beta, float slope, const float* stats, float* g_x, float* g_gamma,
                   float* g_beta, rk_stream_t stream);
 
+/* ---- row-wise Adam on the touched rows of a table (opt-in: the reference
+ *      uses dense optim.Adam, e.g. DeepFM/deepfm.py:226) ---------------------------------------
+ * rows[n]: distinct row numbers, grads[n, D]: their summed gradient rows (a coalesced sparse
+ * gradient: RowShardedEmbedding, nn.Embedding(sparse=True)).  torch.optim.SparseAdam's update:
+ *   m += (g - m)(1 - beta1); v += (g*g - v)(1 - beta2);
+ *   w -= lr * sqrt(1 - beta2^step) / (1 - beta1^step) * m / (sqrt(v) + eps)
+ * on those rows of weight / exp_avg / exp_avg_sq ([V, D] each) only; step >= 1 is the global step. */
+int rk_rowwise_adam(float* weight, float* exp_avg, float* exp_avg_sq, const int64_t* rows,
+                    const float* grads, int64_t n, int D, int64_t V, float lr, float beta1,
+                    float beta2, float eps, int64_t step, int32_t* err_flag, rk_stream_t stream);
+
 /* ---- row-sharded table (BASELINE config 5 "scaled": BST feedid table of 1e8 rows block-
  *      partitioned by row over the ranks; the reference itself is single-process) ------------
  * Bookkeeping around the two all-to-alls (indices out / rows back, mirrored for gradients):
