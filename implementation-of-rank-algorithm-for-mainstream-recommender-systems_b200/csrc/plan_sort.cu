@@ -168,16 +168,6 @@ constexpr int kSortRounds  = 8;
 constexpr int kSortTile    = kSortThreads * kSortRounds;   // 2048 keys per CTA
 constexpr int kMaxBins     = 1024;                         // up to 10-bit digits
 
-__global__ void __launch_bounds__(256)
-build_keys_kernel(const __grid_constant__ FieldKeys f, uint32_t* __restrict__ keys,
-                  uint32_t* __restrict__ vals, int32_t* err_flag) {
-    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < f.n;
-         i += (int64_t)gridDim.x * blockDim.x) {
-        keys[i] = local_key(f, i, err_flag);
-        vals[i] = (uint32_t)i;
-    }
-}
-
 __global__ void __launch_bounds__(kSortThreads)
 tile_hist_kernel(const uint32_t* __restrict__ keys, int64_t n, int shift, int bins, int n_tiles,
                  uint32_t* __restrict__ hist) {
@@ -189,6 +179,30 @@ tile_hist_kernel(const uint32_t* __restrict__ keys, int64_t n, int shift, int bi
     for (int r = 0; r < kSortRounds; ++r) {
         const int64_t i = base + r * kSortThreads + threadIdx.x;
         if (i < n) atomicAdd(&h[(keys[i] >> shift) & (bins - 1)], 1u);
+    }
+    __syncthreads();
+    for (int d = threadIdx.x; d < bins; d += kSortThreads)
+        hist[(int64_t)d * n_tiles + blockIdx.x] = h[d];
+}
+
+// build_keys fused with the first pass's tile histogram (same tiling as tile_hist_kernel): one
+// launch less per large field.
+__global__ void __launch_bounds__(kSortThreads)
+build_keys_hist_kernel(const __grid_constant__ FieldKeys f, uint32_t* __restrict__ keys, uint32_t* __restrict__ vals,
+                       int bins, int n_tiles, uint32_t* __restrict__ hist, int32_t* err_flag) {
+    __shared__ uint32_t h[kMaxBins];
+    for (int i = threadIdx.x; i < bins; i += kSortThreads) h[i] = 0;
+    __syncthreads();
+    const int64_t base = (int64_t)blockIdx.x * kSortTile;
+#pragma unroll
+    for (int r = 0; r < kSortRounds; ++r) {
+        const int64_t i = base + r * kSortThreads + threadIdx.x;
+        if (i < f.n) {
+            const uint32_t k = local_key(f, i, err_flag);
+            keys[i] = k;
+            vals[i] = (uint32_t)i;
+            atomicAdd(&h[k & (bins - 1)], 1u);
+        }
     }
     __syncthreads();
     for (int d = threadIdx.x; d < bins; d += kSortThreads)
@@ -401,20 +415,17 @@ int rk_plan_build(const int64_t* const* idx, const int64_t* n, const int64_t* ro
         const int     dbits  = (fk[f].bits + passes - 1) / passes;
         const int     bins   = 1 << dbits;
         const int     tiles  = (int)ceil_div(nf, kSortTile);
-        {
-            int grid = (int)ceil_div(nf, 256);
-            const int cap = sm_count() * 8;
-            if (grid > cap) grid = cap;
-            build_keys_kernel<<<grid, 256, 0, s>>>(fk[f], kA, vA, err_flag);
-            RK_LAUNCH_CHECK();
-        }
+        build_keys_hist_kernel<<<tiles, kSortThreads, 0, s>>>(fk[f], kA, vA, bins, tiles, hist, err_flag);
+        RK_LAUNCH_CHECK();
         uint32_t *kin = kA, *vin = vA;
         for (int p = 0; p < passes; ++p) {
             const bool last = p == passes - 1;
             uint32_t* kout = last ? sorted_keys + fk[f].start : (kin == kA ? kB : kA);
             uint32_t* vout = last ? perm + fk[f].start : (vin == vA ? vB : vA);
-            tile_hist_kernel<<<tiles, kSortThreads, 0, s>>>(kin, nf, p * dbits, bins, tiles, hist);
-            RK_LAUNCH_CHECK();
+            if (p > 0) {                     // pass 0's histogram came with the keys
+                tile_hist_kernel<<<tiles, kSortThreads, 0, s>>>(kin, nf, p * dbits, bins, tiles, hist);
+                RK_LAUNCH_CHECK();
+            }
             row_scan_kernel<<<bins, 256, 0, s>>>(hist, tiles, totals);
             RK_LAUNCH_CHECK();
             scatter_kernel<<<tiles, kSortThreads, (size_t)kSortWarps * bins * 4, s>>>(
