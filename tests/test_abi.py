@@ -50,3 +50,15 @@ def test_no_cpu_fallback():
     i = torch.zeros(3, dtype=torch.int64)
     with pytest.raises(rank_b200.RankB200Error):
         gather_concat([w], [i], [0])
+
+
+def test_argument_counts_match_the_header():
+    """Every ctypes prototype has as many arguments as the C declaration (catches binding drift)."""
+    text = open(os.path.join(ROOT, "include", "rank_b200.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    decls = dict(re.findall(r"\b(rk_[a-z0-9_]+)\s*\(([^;{]*?)\)\s*;", text, flags=re.S))
+    assert set(decls) == set(_lib.PROTOTYPES)
+    for name, params in decls.items():
+        params = " ".join(params.split())
+        n = 0 if params in ("", "void") else params.count(",") + 1
+        assert n == len(_lib.PROTOTYPES[name][1]), (name, n, len(_lib.PROTOTYPES[name][1]))
