@@ -549,6 +549,7 @@ def run_ours(args, wl):
         timed(1, 50 + i, from_host=True)
     barrier()
     with ClockSampler(local) as clocks_e2e:      # the end-to-end region is a timed region too: sample it as well
+        barrier()                                # (the samplers start at different speeds on different ranks)
         clocks_e2e.mark()
         e2e_ms, _ = timed(args.steps, 20_000, from_host=True)
         barrier()
