@@ -9,9 +9,15 @@ is part of the step).  Rank 0 prints ONE JSON line (see DESIGN.md "Measurement")
   value     : device-timed (CUDA events), inputs already resident in HBM, max over ranks
   e2e       : same metric through the public module API with pinned HOST inputs, H2D copies and
               the D2H read of the loss inside the timed region
-  roofline  : algorithmic bytes of the hot path / summed device time of the
-              hot-path ABI calls of a step, against MEASURED_PEAKS.json
+  roofline  : algorithmic bytes of the hot path / device time of a CUDA graph that
+              holds ONLY the hot path of a step (model.hot_path forward + its backward incl. the
+              embedding-gradient reduction), against MEASURED_PEAKS.json; by construction a subset of
+              the step, and checked to be <= ms_per_step
+  aten_cuda_baseline : the oracle port of the reference model on the SAME GPU through stock
+              ATen/cuBLAS kernels (what the reference does with --device cuda), eager and replayed
+              from a CUDA graph — the kernel-level bar of SURVEY.md §2.2 / §8d
   cpu_baseline / --impl reference : the oracle port of the reference model on the host cores
+  other_workloads : one-line summaries of the other configurations (N = 1, default workload only)
 """
 from __future__ import annotations
 
@@ -57,6 +63,10 @@ class Workload:
     def loss(self, model, batch):
         raise NotImplementedError
 
+    def hot(self, model, batch):
+        """The tensors model.hot_path hands to the torch tower (the librank_b200 part of forward)."""
+        raise NotImplementedError
+
 
 class DeepFMWorkload(Workload):
     name, batch, bytes_per_sample, flops_per_sample = "deepfm_d16", 1024, 2896, 600
@@ -73,6 +83,9 @@ class DeepFMWorkload(Workload):
     def loss(self, model, batch):
         prob = model(batch["category"])[0]
         return F.binary_cross_entropy(prob.squeeze(), batch["label"])
+
+    def hot(self, model, batch):
+        return model.hot_path(batch["category"])
 
 
 class FwFMWorkload(Workload):
@@ -94,6 +107,9 @@ class FwFMWorkload(Workload):
     def loss(self, model, batch):
         return F.binary_cross_entropy(model(batch["x"]), batch["label"])
 
+    def hot(self, model, batch):
+        return model.hot_path(batch["x"])
+
 
 class DCNWorkload(Workload):
     name, batch, bytes_per_sample, flops_per_sample = "dcn_l3_dnn512-256-128", 8192, 1704, 2300
@@ -110,6 +126,9 @@ class DCNWorkload(Workload):
     def loss(self, model, batch):
         logit = model(batch["dense"], batch["category"])[1]
         return F.binary_cross_entropy_with_logits(logit.squeeze(), batch["label"])
+
+    def hot(self, model, batch):
+        return model.hot_path(batch["dense"], batch["category"])
 
 
 class AFMWorkload(Workload):
@@ -139,6 +158,9 @@ class AFMWorkload(Workload):
         prob = model(batch["dense"], batch["category"])[0]
         return F.binary_cross_entropy(prob.squeeze(), batch["label"])
 
+    def hot(self, model, batch):
+        return model.hot_path(batch["dense"], batch["category"])
+
 
 class AFMFp32Workload(AFMWorkload):
     # the fp32 SIMT kernels (csrc/afm.cu): compute-bound on the fp32 FMA pipe
@@ -167,6 +189,9 @@ class DINWorkload(Workload):
     def loss(self, model, batch):
         prob, _, l2 = model(batch["dense"], batch["category"], batch["sequence"], batch["target"])
         return F.binary_cross_entropy(prob.squeeze(), batch["label"]) + l2
+
+    def hot(self, model, batch):
+        return model.hot_path(batch["dense"], batch["category"], batch["sequence"], batch["target"])
 
 
 class DINSoftmaxWorkload(DINWorkload):
@@ -199,6 +224,9 @@ class BSTWorkload(Workload):
         logit = model(batch["dense"], batch["category"], batch["seq_feedid"], batch["seq_length"])[1]
         return F.binary_cross_entropy_with_logits(logit.squeeze(), batch["label"])
 
+    def hot(self, model, batch):
+        return model.hot_path(batch["dense"], batch["category"], batch["seq_feedid"], batch["seq_length"])
+
 
 class DeepCrossingWorkload(Workload):
     name, batch, bytes_per_sample, flops_per_sample = "deepcrossing_h128_n2", 8192, 1304, 154_000
@@ -217,7 +245,13 @@ class DeepCrossingWorkload(Workload):
         logit = model(batch["dense"], batch["category"])[1]
         return F.binary_cross_entropy_with_logits(logit.squeeze(), batch["label"])
 
+    def hot(self, model, batch):
+        return model.hot_path(batch["dense"], batch["category"])
 
+
+# BASELINE.json configs[3]: DIN, history 50, local activation unit as a tensor-core MLP, batch 8192 — the
+# configuration the north star sets its roofline and 1->8 scaling targets on
+DEFAULT_WORKLOAD = "din_tc"
 WORKLOADS = {"deepfm": DeepFMWorkload, "fwfm": FwFMWorkload, "dcn": DCNWorkload, "afm": AFMWorkload, "afm_fp32": AFMFp32Workload, "din": DINWorkload,
              "din_softmax": DINSoftmaxWorkload, "din_tc": DINTensorCoreWorkload,
              "din_softmax_tc": DINSoftmaxTensorCoreWorkload, "bst": BSTWorkload,
@@ -228,6 +262,7 @@ WORKLOADS = {"deepfm": DeepFMWorkload, "fwfm": FwFMWorkload, "dcn": DCNWorkload,
 # fused forward + backward kernels whose ncu dram__bytes (profiles/r01_traffic.json, one
 # `ncu --set full` capture per kernel) are reported as roofline.traffic
 TRAFFIC_KERNELS = {
+    "din_softmax_tc": ("din_fwd_tc_kernel", "din_bwd_tc_kernel"),
     "dcn": ("crossnet_fwd_kernel", "crossnet_bwd_kernel"), "afm_fp32": ("afm_fwd_kernel", "afm_bwd_kernel"),
     "bst": ("bst_fwd_kernel", "bst_bwd_kernel"), "din_tc": ("din_fwd_tc_kernel", "din_bwd_tc_kernel"),
     "afm": ("afm_fwd_tc_kernel", "afm_bwd_tc_kernel"), "fwfm": ("fwfm_fwd_kernel", "fwfm_bwd_kernel"),
@@ -237,12 +272,15 @@ TRAFFIC_KERNELS = {
 def measured_traffic(workload_key):
     """DRAM bytes per launch (read + write) of the workload's fused fwd+bwd kernels, from the
     committed ncu capture of this round; None when no capture exists for them."""
-    path = os.path.join(ROOT, "profiles", "r01_traffic.json")
     names = TRAFFIC_KERNELS.get(workload_key)
-    if not names or not os.path.exists(path):
+    table = {}
+    for rnd in ("r01", "r02"):             # later rounds' captures override earlier ones, kernel by kernel
+        path = os.path.join(ROOT, "profiles", f"{rnd}_traffic.json")
+        if os.path.exists(path):
+            with open(path) as f:
+                table.update(json.load(f))
+    if not names or not table:
         return None, None
-    with open(path) as f:
-        table = json.load(f)
     if not all(n in table for n in names):
         return None, None
     per = {n: table[n]["dram_read_bytes"] + table[n]["dram_write_bytes"] for n in names}
@@ -409,16 +447,19 @@ class Stepper:
     """One training step (zero_grad, forward, loss, backward) on static device buffers, replayed
     from a CUDA graph (default) or run eagerly (--no-graph).  The per-call random weights of
     DCN / DeepCrossing / DIN are re-drawn on the CPU generator before every step, as the
-    reference does inside forward, and shipped to a fixed device buffer outside the graph."""
+    reference does inside forward, and shipped to a fixed device buffer outside the graph.
+    `hot_only`: the graph holds only model.hot_path forward + its backward against fixed cotangents
+    (no tower, no loss): the hot path of a step and nothing else."""
 
-    def __init__(self, model, wl, example, use_graph, reducer):
-        self.model, self.wl, self.reducer = model, wl, reducer
+    def __init__(self, model, wl, example, use_graph, reducer, hot_only=False):
+        self.model, self.wl, self.reducer, self.hot_only = model, wl, reducer, hot_only
         from rank_b200.staging import PackedBatch
         self.packed = PackedBatch.like(example.host_views, example.device)   # fixed addresses: graph inputs
         self.static = self.packed.device_views
         self.has_ephemeral = hasattr(model, "draw_ephemeral")
         self.graph = None
         self.grads = None
+        self.cots = None
         if use_graph:
             side = torch.cuda.Stream()
             side.wait_stream(torch.cuda.current_stream())
@@ -433,15 +474,25 @@ class Stepper:
                 model.ephemeral_frozen = True
             self.graph = torch.cuda.CUDAGraph()
             with torch.cuda.graph(self.graph):
-                self.loss = wl.loss(model, self.static)
-                self.loss.backward()
+                self._body()
             self.grads = [p.grad for p in model.parameters()]
+
+    def _body(self):
+        if self.hot_only:
+            outs = [o for o in self.wl.hot(self.model, self.static) if o.requires_grad]
+            if self.cots is None:
+                gen = torch.Generator(device=outs[0].device).manual_seed(7)
+                self.cots = [torch.randn(o.shape, generator=gen, device=o.device) / o.shape[0] for o in outs]
+            self.loss = outs[0]
+            torch.autograd.backward(outs, self.cots)
+        else:
+            self.loss = self.wl.loss(self.model, self.static)
+            self.loss.backward()
 
     def _eager(self, seed):
         self.model.zero_grad(set_to_none=True)
         torch.default_generator.manual_seed(seed)
-        self.loss = self.wl.loss(self.model, self.static)
-        self.loss.backward()
+        self._body()
 
     def load(self, packed, from_host=False):
         """ONE copy of the whole packed batch into the static inputs: pinned host -> device when
@@ -453,7 +504,7 @@ class Stepper:
             self._eager(seed)
             grads = None
         else:
-            if self.has_ephemeral:
+            if self.has_ephemeral and not self.hot_only:
                 torch.default_generator.manual_seed(seed)   # same draw on every rank
                 self.model.draw_ephemeral()
             self.graph.replay()
@@ -463,21 +514,111 @@ class Stepper:
         return self.loss
 
 
-def run_ours(args, wl):
-    import rank_b200
-    from rank_b200 import _lib, synthetic
-    from rank_b200.parallel import GradientAllReducer
+def aten_cuda_run(wl, B, steps, warmup, dev, flush, vocab):
+    """The oracle port of the reference model on THIS GPU through stock ATen/cuBLAS kernels — what the
+    reference does when its scripts run with --device cuda (e.g. DCN/dcn.py:161-180, DIN/din.py:294-323):
+    zero_grad + forward + loss + backward per step, eager (per-call weights drawn on the CPU and moved to
+    the device inside forward, as the reference does) and replayed from a CUDA graph (per-call weights
+    frozen to one draw: a graph cannot hold the CPU draws; everything else identical).  L2 is flushed
+    between steps as for our arm."""
+    from oracle import models as oracle_models
+    from rank_b200 import synthetic
+    torch.manual_seed(0)
+    model = wl.model(oracle_models, True, vocab).to(dev)
+    model.train()
+    pool = [synthetic.to_device(wl.make_batch(B, 1000 + i), dev) for i in range(4)]
 
-    world, rank, local = dist_setup(args.gpus)
-    assert torch.cuda.is_available(), "bench.py needs a CUDA device (no CPU fallback)"
-    torch.cuda.set_device(local)
-    dev = torch.device("cuda", local)
-    if world > 1:
-        import torch.distributed as dist
-        dist.init_process_group("nccl", device_id=dev)
+    def step(batch, seed):
+        model.zero_grad(set_to_none=True)
+        torch.manual_seed(seed)
+        loss = wl.loss(model, batch)
+        loss.backward()
+        return loss
+
+    def timed(fn, n):
+        evs = []
+        for i in range(n):
+            flush.fill_(i & 0xff)
+            s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            s.record()
+            fn(i)
+            e.record()
+            evs.append((s, e))
+        torch.cuda.synchronize()
+        return sum(s.elapsed_time(e) for s, e in evs) / n
+
+    for i in range(warmup):
+        step(pool[i % 4], i)
+    torch.cuda.synchronize()
+    eager_ms = timed(lambda i: step(pool[i % 4], 100 + i), steps)
+    out = {"eager_ms_per_step": eager_ms, "eager_value": B / (eager_ms * 1e-3), "unit": "samples/s",
+           "what": "oracle port of the reference nn.Module on cuda: stock ATen/cuBLAS kernels, fwd+loss+bwd, "
+                   "same batch, dropout 0; eager = per-call weights drawn on the CPU and copied inside forward "
+                   "(as the reference), graph = the same step captured with one frozen draw",
+           "steps": steps}
+    try:
+        if hasattr(model, "last_ephemeral"):
+            model.frozen_ephemeral = model.last_ephemeral
+        static = synthetic.to_device(wl.make_batch(B, 999), dev)
+
+        def copy_in(dst, src):
+            if torch.is_tensor(dst):
+                dst.copy_(src)
+            else:
+                for k in dst:
+                    copy_in(dst[k], src[k])
+
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            for i in range(3):
+                step(static, i)
+        torch.cuda.current_stream().wait_stream(side)
+        torch.cuda.synchronize()
+        model.zero_grad(set_to_none=True)
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph):
+            loss = wl.loss(model, static)
+            loss.backward()
+
+        def replay(i):
+            graph.replay()
+
+        for i in range(3):
+            copy_in(static, pool[i % 4])
+            graph.replay()
+        torch.cuda.synchronize()
+        evs = []
+        for i in range(steps):
+            copy_in(static, pool[i % 4])
+            flush.fill_(i & 0xff)
+            s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            s.record()
+            graph.replay()
+            e.record()
+            evs.append((s, e))
+        torch.cuda.synchronize()
+        graph_ms = sum(s.elapsed_time(e) for s, e in evs) / steps
+        out.update(graph_ms_per_step=graph_ms, graph_value=B / (graph_ms * 1e-3))
+        del graph
+    except Exception as exc:       # a capture failure of the stock path is a result, not a bench failure
+        out["graph_error"] = f"{type(exc).__name__}: {exc}"[:300]
+        torch.cuda.synchronize()
+    del model
+    return out
+
+
+def measure_ours(args, wl, key, world, rank, local, dev, primary):
+    """Everything measured for one workload.  `primary`: the workload of the JSON line (all legs);
+    otherwise a shorter run for the `other_workloads` summaries."""
+    import rank_b200
+    from rank_b200 import _lib, sparse
+    from rank_b200.parallel import GradientAllReducer
+    from rank_b200.staging import PackedBatch
+
     lib = _lib.load()
     B = args.batch or wl.batch
-
+    steps = args.steps if primary else min(args.steps, 50)
     vocab = rank_b200.write_vocab_dir(tempfile.mkdtemp(prefix="rk_vocab_")) + "/"
     torch.manual_seed(0)                    # identical replicas on every rank
     model = wl.model(rank_b200, False, vocab).to(dev)
@@ -488,12 +629,15 @@ def run_ours(args, wl):
     # every batch of the pool is collated once into a packed pinned buffer (rank_b200.staging) and
     # also kept on the device: `value` steps copy device -> device (untimed), `e2e` steps do the one
     # host -> device copy inside the timed region
-    from rank_b200.staging import PackedBatch
     raw = [wl.make_batch(B, 1000 + 17 * rank + i) for i in range(n_pool)]
     pool = [PackedBatch.like(b, dev).fill(b) for b in raw]
     for pb in pool:
         pb.to_device()
     torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for i in range(8):
+        pool[i % n_pool].fill(raw[i % n_pool])
+    fill_ms = (time.perf_counter() - t0) / 8 * 1e3      # host-side collate into the pinned buffer
     flush = torch.empty(L2_FLUSH_BYTES, dtype=torch.uint8, device=dev)
     stepper = Stepper(model, wl, pool[0], not args.no_graph, reducer)
 
@@ -502,26 +646,26 @@ def run_ours(args, wl):
             torch.distributed.barrier()
         torch.cuda.synchronize()
 
-    def timed(n_steps, first_seed, from_host):
+    def timed(st, n_steps, first_seed, from_host):
         evs = []
-        loss_host = None
+        loss = None
         for i in range(n_steps):
             flush.fill_(i & 0xff)           # evict L2 between steps; outside the timed events
             s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             if from_host:
                 s.record()
-                stepper.load(pool[i % n_pool], from_host=True)       # ONE H2D copy of this step's inputs (pinned)
-                loss = stepper.run(first_seed + i)
-                loss_host = loss.detach().to("cpu", non_blocking=True)   # D2H read of the step's result
+                st.load(pool[i % n_pool], from_host=True)       # ONE H2D copy of this step's inputs (pinned)
+                loss = st.run(first_seed + i)
+                loss.detach().to("cpu", non_blocking=True)      # D2H read of the step's result
                 e.record()
             else:
-                stepper.load(pool[i % n_pool])                       # device-to-device, untimed
+                st.load(pool[i % n_pool])                       # device-to-device, untimed
                 s.record()
-                loss = stepper.run(first_seed + i)
+                loss = st.run(first_seed + i)
                 e.record()
             evs.append((s, e))
         torch.cuda.synchronize()
-        return sum(s.elapsed_time(e) for s, e in evs), float(loss.detach())
+        return sum(s.elapsed_time(e) for s, e in evs), float(loss.detach().reshape(-1)[0])
 
     with ClockSampler(local) as clocks:      # started before the warm-up, sampled through the timed region
         for i in range(args.warmup):
@@ -535,99 +679,183 @@ def run_ours(args, wl):
                 stepper.run(100 + i)
                 barrier()
         barrier()
-        launches0 = lib.rk_launch_count()
+        clocks.mark()
+        total_ms, last_loss = timed(stepper, steps, 10_000, from_host=False)
         barrier()
         clocks.mark()
-        total_ms, last_loss = timed(args.steps, 10_000, from_host=False)
-        barrier()
-        clocks.mark()
-    launches = lib.rk_launch_count() - launches0
-    if stepper.graph is not None:
-        launches = stepper_launches_per_replay(stepper, lib) * args.steps
+    launches = stepper_launches_per_replay(stepper, lib) * steps if stepper.graph is not None else None
     # end to end: pinned host inputs -> H2D -> step -> D2H loss
     for i in range(3):
-        timed(1, 50 + i, from_host=True)
+        timed(stepper, 1, 50 + i, from_host=True)
     barrier()
     with ClockSampler(local) as clocks_e2e:      # the end-to-end region is a timed region too: sample it as well
         barrier()                                # (the samplers start at different speeds on different ranks)
         clocks_e2e.mark()
-        e2e_ms, _ = timed(args.steps, 20_000, from_host=True)
+        e2e_ms, _ = timed(stepper, steps, 20_000, from_host=True)
         barrier()
         clocks_e2e.mark()
     clocks.absorb(clocks_e2e)
-
-    # Per-call device times of the hot path: eager steps queued behind a spin kernel, so the
-    # kernels run back to back and the events bracketing each ABI call see device time only.
-    eager = Stepper(model, wl, pool[0], False, None)
-    if hasattr(model, "ephemeral_frozen"):
-        model.ephemeral_frozen = False
-    from rank_b200 import sparse
-    sparse.PLAN_ON_SIDE_STREAM = False      # time the occurrence plan in-stream, not overlapped
-    with _lib.CallTimer() as ct:
-        for i in range(args.steps):
-            eager.load(pool[i % n_pool])
-            flush.fill_(i & 0xff)
-            _lib.check(lib.rk_debug_spin(4000, _lib.stream_ptr()), "rk_debug_spin")
-            eager.run(30_000 + i)
-            torch.cuda.synchronize()
-    calls = ct.summary()
-    # the same pass without the L2 flush: what a running training job sees (tables, code and the
-    # previous step's buffers still in the 126 MB L2); reported next to the flushed figures
-    with _lib.CallTimer() as ct_warm:
-        for i in range(args.steps):
-            eager.load(pool[i % n_pool])
-            _lib.check(lib.rk_debug_spin(4000, _lib.stream_ptr()), "rk_debug_spin")
-            eager.run(40_000 + i)
-            torch.cuda.synchronize()
-    calls_warm = ct_warm.summary()
 
     t = torch.tensor([total_ms, e2e_ms], dtype=torch.float64, device=dev)
     if world > 1:
         torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
     total_ms, e2e_ms = float(t[0]), float(t[1])
+    ms_per_step = total_ms / steps
 
+    # ---- the hot path alone: a CUDA graph of model.hot_path forward + backward (incl. the embedding-
+    # gradient reduction) against fixed cotangents; same static inputs, same L2 flush between replays
+    hot = Stepper(model, wl, pool[0], True, None, hot_only=True)
+    for i in range(3):
+        hot.load(pool[i % n_pool])
+        hot.run(i)
+    hot_total, _ = timed(hot, steps, 0, from_host=False)
+    hot_ms = hot_total / steps
+    hot_launches = stepper_launches_per_replay(hot, lib)
+    evs = []
+    for i in range(steps):                    # the same graph without the flush: tables / code still in L2
+        hot.load(pool[i % n_pool])
+        s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s.record()
+        hot.run(i)
+        e.record()
+        evs.append((s, e))
+    torch.cuda.synchronize()
+    hot_warm_ms = sum(s.elapsed_time(e) for s, e in evs) / steps
+    del hot
+
+    # ---- per-call diagnostic: eager steps queued behind a spin kernel, CUDA events around each ABI call.
+    # Every bracket also holds the launch gaps around its kernels (~3-6 us per call on this box), so these
+    # are upper bounds used for the SHARES of the calls, not for the roofline.
+    calls = {}
+    if primary or args.calls:
+        eager = Stepper(model, wl, pool[0], False, None)
+        if hasattr(model, "ephemeral_frozen"):
+            model.ephemeral_frozen = False
+        side_was = sparse.PLAN_ON_SIDE_STREAM
+        sparse.PLAN_ON_SIDE_STREAM = False      # time the occurrence plan in-stream, not overlapped
+        n_diag = min(steps, 20)
+        with _lib.CallTimer() as ct:
+            for i in range(n_diag):
+                eager.load(pool[i % n_pool])
+                flush.fill_(i & 0xff)
+                _lib.check(lib.rk_debug_spin(4000, _lib.stream_ptr()), "rk_debug_spin")
+                eager.run(30_000 + i)
+                torch.cuda.synchronize()
+        sparse.PLAN_ON_SIDE_STREAM = side_was
+        calls = {k: {"calls_per_step": n / n_diag, "ms_per_step": ms / n_diag} for k, (n, ms) in sorted(ct.summary().items())}
+
+    pk = peaks()
+    achieved = (B * wl.bytes_per_sample) / (hot_ms * 1e-3) / 1e9 if hot_ms > 0 else 0.0
+    res = {
+        "workload": wl.name, "batch_per_gpu": B, "steps": steps, "value": world * B * steps / (total_ms / 1e3),
+        "ms_per_step": ms_per_step, "e2e_value": world * B * steps / (e2e_ms / 1e3), "loss": last_loss,
+        "dtype": wl.dtype, "clocks": clocks.summary(),
+        "gpu_launches": int(launches) if launches is not None else None,
+        "h2d_bytes": pool[0].nbytes, "h2d_payload": pool[0].payload_bytes, "fill_ms": fill_ms,
+        "graph": stepper.graph is not None,
+        "roofline": {
+            "bound": wl.bound, "achieved": achieved, "peak": pk["hbm_gbs"], "unit": "GB/s",
+            "frac": achieved / pk["hbm_gbs"], "peak_source": pk["source"],
+            "what": "hot path = CUDA graph of model.hot_path forward + backward incl. the embedding-gradient "
+                    "reduction (" + ", ".join(wl.hot_calls) + "), replayed with the L2 flushed before each replay",
+            "algorithmic_bytes_per_sample": wl.bytes_per_sample, "hot_ms_per_step": hot_ms,
+            "hot_ms_per_step_warm_l2": hot_warm_ms, "hot_launches_per_step": int(hot_launches),
+            "hot_share_of_step": hot_ms / ms_per_step if ms_per_step > 0 else None,
+            "hot_le_step": bool(hot_ms <= ms_per_step),
+            "frac_warm_l2": (B * wl.bytes_per_sample) / (hot_warm_ms * 1e-3) / 1e9 / pk["hbm_gbs"] if hot_warm_ms > 0 else None,
+        },
+        "hotpath_calls_eager_events": calls,
+    }
+    if wl.flops_per_sample >= 100_000:       # the dense part: share of the tensor / FMA roof as well
+        res["roofline"]["flops_per_sample"] = wl.flops_per_sample
+        res["roofline"]["achieved_tflops"] = B * wl.flops_per_sample / (hot_ms * 1e-3) / 1e12
+    traffic, traffic_by = measured_traffic(key)
+    res["roofline"]["traffic"] = traffic
+    res["roofline"]["traffic_by_kernel"] = traffic_by
+    if traffic is not None:
+        res["roofline"]["traffic_note"] = ("ncu dram__bytes_read+write of the fused fwd+bwd kernels (one --set full "
+                                           "capture, cold cache); below the algorithmic bytes where tables and "
+                                           "outputs live in the 126 MB L2")
+    if world == 1 and rank == 0 and not args.no_aten:
+        del stepper
+        model.zero_grad(set_to_none=True)
+        res["aten_cuda_baseline"] = aten_cuda_run(wl, B, min(steps, 50), 3, dev, flush, vocab)
+        a = res["aten_cuda_baseline"]
+        a["ours_over_aten_eager"] = a["eager_ms_per_step"] / ms_per_step
+        if "graph_ms_per_step" in a:
+            a["ours_over_aten_graph"] = a["graph_ms_per_step"] / ms_per_step
+    del model, pool, flush
+    torch.cuda.empty_cache()
+    return res
+
+
+OTHERS = ("din_softmax_tc", "din", "dcn", "deepfm", "fwfm", "afm", "bst", "deepcrossing")
+
+
+def run_ours(args, wl):
+    world, rank, local = dist_setup(args.gpus)
+    assert torch.cuda.is_available(), "bench.py needs a CUDA device (no CPU fallback)"
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=dev)
+    r = measure_ours(args, wl, args.workload, world, rank, local, dev, primary=True)
     if rank == 0:
-        pk = peaks()
-        traffic, traffic_by = measured_traffic(args.workload)
-        hot_ms = sum(ms for name, (n, ms) in calls.items() if name in wl.hot_calls) / args.steps
-        achieved = (B * wl.bytes_per_sample) / (hot_ms * 1e-3) / 1e9 if hot_ms > 0 else 0.0
-        hot_warm_ms = sum(ms for name, (n, ms) in calls_warm.items() if name in wl.hot_calls) / args.steps
+        B, steps = r["batch_per_gpu"], r["steps"]
         line = {
-            "metric": METRIC, "value": world * B * args.steps / (total_ms / 1e3), "unit": "samples/s",
-            "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": total_ms / args.steps,
-            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": wl.dtype,
+            "metric": METRIC, "value": r["value"], "unit": "samples/s",
+            "n_gpus": world, "steps": steps, "warmup": args.warmup, "ms_per_step": r["ms_per_step"],
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": r["dtype"],
             "data": "synthetic",
-            "config": {"workload": wl.name, "batch_per_gpu": B, "global_batch": world * B, "dropout": 0.0,
+            "config": {"workload": r["workload"], "batch_per_gpu": B, "global_batch": world * B, "dropout": 0.0,
                        "parallelism": f"dp{world}", "l2": "256 MiB written between steps, outside the timed events",
                        "step": "zero_grad+fwd+loss+bwd" + ("+grad allreduce" if world > 1 else ""),
-                       "launch": "eager" if stepper.graph is None else "cuda graph replay per step",
+                       "launch": "cuda graph replay per step" if r["graph"] else "eager",
                        "indices": "zipf(1.05), fresh batch each step from a pool of 4"},
-            "clocks": clocks.summary(),
-            "e2e": {"value": world * B * args.steps / (e2e_ms / 1e3), "unit": "samples/s",
-                    "h2d_bytes_per_step": pool[0].nbytes, "d2h_bytes_per_step": 4,
-                    "h2d_copies_per_step": 1, "h2d_payload_bytes": pool[0].payload_bytes},
-            "gpu_launches": int(launches),
-            "roofline": {"bound": wl.bound, "achieved": achieved, "peak": pk["hbm_gbs"], "unit": "GB/s",
-                         "frac": achieved / pk["hbm_gbs"], "traffic": traffic, "traffic_by_kernel": traffic_by,
-                         "traffic_note": "ncu dram__bytes_read+write of the fused fwd+bwd kernels (one capture, "
-                                         "cold cache); below the algorithmic bytes because tables and outputs "
-                                         "live in the 126 MB L2",
-                         "peak_source": pk["source"],
-                         "what": "hot path (all ABI calls of a step: " + ", ".join(wl.hot_calls) + ")",
-                         "algorithmic_bytes_per_sample": wl.bytes_per_sample, "hot_ms_per_step": hot_ms,
-                         "hot_ms_per_step_warm_l2": hot_warm_ms,
-                         "frac_warm_l2": (B * wl.bytes_per_sample) / (hot_warm_ms * 1e-3) / 1e9 / pk["hbm_gbs"]
-                         if hot_warm_ms > 0 else None},
-            "hotpath_calls": {k: {"calls_per_step": n / args.steps, "ms_per_step": ms / args.steps}
-                              for k, (n, ms) in sorted(calls.items())},
-            "hotpath_calls_warm_l2": {k: ms / args.steps for k, (n, ms) in sorted(calls_warm.items())},
-            "loss": last_loss,
+            "clocks": r["clocks"],
+            "e2e": {"value": r["e2e_value"], "unit": "samples/s",
+                    "h2d_bytes_per_step": r["h2d_bytes"], "d2h_bytes_per_step": 4,
+                    "h2d_copies_per_step": 1, "h2d_payload_bytes": r["h2d_payload"],
+                    "note": "timed per step: ONE H2D copy of the packed pinned batch + graph replay + D2H of the "
+                            "loss.  Collating a dict batch into the pinned buffer (PackedBatch.fill, host side, "
+                            "overlappable with the previous step) is outside the events",
+                    "host_fill_ms_per_batch": r["fill_ms"]},
+            "gpu_launches": r["gpu_launches"],
+            "roofline": r["roofline"],
+            "hotpath_calls_eager_events": r["hotpath_calls_eager_events"],
+            "loss": r["loss"],
         }
+        if "aten_cuda_baseline" in r:
+            line["aten_cuda_baseline"] = r["aten_cuda_baseline"]
         if world == 1 and not args.no_cpu_baseline:
-            r = cpu_reference_run(wl, 50, 2, B, budget_s=15.0)
-            line["cpu_baseline"] = {"value": r["value"], "unit": "samples/s", "cores": r["cores"], "kind": "port",
-                                    "sample": f"{r['steps']} full steps of batch {B} (fwd+loss+bwd) of the oracle "
+            c = cpu_reference_run(wl, 50, 2, B, budget_s=15.0)
+            line["cpu_baseline"] = {"value": c["value"], "unit": "samples/s", "cores": c["cores"], "kind": "port",
+                                    "sample": f"{c['steps']} full steps of batch {B} (fwd+loss+bwd) of the oracle "
                                               "port, torch CPU fp32"}
+    if world == 1 and args.workload == DEFAULT_WORKLOAD and not args.no_others and not args.batch:
+        others = {}
+        for k in OTHERS:
+            if k == args.workload:
+                continue
+            try:
+                o = measure_ours(args, WORKLOADS[k](), k, world, rank, local, dev, primary=False)
+                a = o.get("aten_cuda_baseline", {})
+                others[k] = {
+                    "workload": o["workload"], "batch": o["batch_per_gpu"], "steps": o["steps"],
+                    "value": o["value"], "ms_per_step": o["ms_per_step"], "e2e_value": o["e2e_value"],
+                    "hot_ms_per_step": o["roofline"]["hot_ms_per_step"], "hot_share_of_step": o["roofline"]["hot_share_of_step"],
+                    "roofline_frac": o["roofline"]["frac"], "hot_launches_per_step": o["roofline"]["hot_launches_per_step"],
+                    "gpu_launches_per_step": (o["gpu_launches"] or 0) / o["steps"],
+                    "aten_cuda_eager_ms": a.get("eager_ms_per_step"), "aten_cuda_graph_ms": a.get("graph_ms_per_step"),
+                    "ours_over_aten_eager": a.get("ours_over_aten_eager"), "ours_over_aten_graph": a.get("ours_over_aten_graph"),
+                    "sm_mhz": o["clocks"].get("sm_mhz"), "reasons": o["clocks"].get("reasons"),
+                }
+            except Exception as exc:      # one workload failing must not lose the line
+                others[k] = {"error": f"{type(exc).__name__}: {exc}"[:300]}
+                torch.cuda.synchronize()
+        line["other_workloads"] = others
+    if rank == 0:
         emit(line)
     if world > 1:
         torch.distributed.destroy_process_group()
@@ -635,7 +863,8 @@ def run_ours(args, wl):
 
 def stepper_launches_per_replay(stepper, lib):
     """Kernels of librank_b200 inside one captured step = what one eager step launches."""
-    probe = Stepper(stepper.model, stepper.wl, stepper.packed, False, None)
+    probe = Stepper(stepper.model, stepper.wl, stepper.packed, False, None, hot_only=stepper.hot_only)
+    probe.cots = stepper.cots
     probe.load(stepper.packed)
     frozen = getattr(stepper.model, "ephemeral_frozen", None)
     n0 = lib.rk_launch_count()
@@ -645,8 +874,9 @@ def stepper_launches_per_replay(stepper, lib):
     if frozen is not None:
         stepper.model.ephemeral_frozen = frozen
     stepper.model.zero_grad(set_to_none=True)
-    for p, g in zip(stepper.model.parameters(), stepper.grads):
-        p.grad = g
+    if stepper.grads is not None:
+        for p, g in zip(stepper.model.parameters(), stepper.grads):
+            p.grad = g
     return n
 
 
@@ -675,12 +905,15 @@ def emit(line):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
-    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="dcn", choices=sorted(WORKLOADS))
+    ap.add_argument("--workload", default=DEFAULT_WORKLOAD, choices=sorted(WORKLOADS))
     ap.add_argument("--batch", type=int, default=0, help="per-GPU batch (default: the workload's)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-aten", action="store_true", help="skip the reference-on-CUDA (stock ATen) baseline")
+    ap.add_argument("--no-others", action="store_true", help="skip the other workloads' one-line summaries")
+    ap.add_argument("--calls", action="store_true", help="per-call event diagnostic for the other workloads too")
     ap.add_argument("--no-graph", action="store_true", help="launch every step eagerly instead of a CUDA graph")
     args = ap.parse_args()
     claim_stdout()

@@ -114,13 +114,17 @@ class AFM(nn.Module):
         # "fp32": the SIMT kernels (csrc/afm.cu).  ("bf16" is accepted as an alias of "tensor".)  Not a parameter.
         self.attention_precision = "tensor"
 
-    def forward(self, dense_input, category_input):
-        dense_logit = self.dense_layer(dense_input)
+    def hot_path(self, dense_input, category_input):
+        """The part of forward that runs in librank_b200: the attention-pooled pair interactions [B, D]."""
         cols = self.category_features
-        pooled = _AfmPooling.apply(
+        return (_AfmPooling.apply(
             (len(cols), _check_precision(self.attention_precision)), self.attention[0].weight, self.attention[0].bias, self.attention[2].weight,
             self.attention[2].bias, *[category_input[c] for c in cols],
-            *[self.embeddings[c].weight for c in cols])
+            *[self.embeddings[c].weight for c in cols]),)
+
+    def forward(self, dense_input, category_input):
+        dense_logit = self.dense_layer(dense_input)
+        (pooled,) = self.hot_path(dense_input, category_input)
         total_logit = dense_logit + self.p(pooled)
         prediction = torch.sigmoid(total_logit)
         return prediction, total_logit

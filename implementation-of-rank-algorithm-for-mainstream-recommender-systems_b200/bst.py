@@ -228,7 +228,8 @@ class BSTModel(nn.Module):
         layers.append(nn.Linear(width, 1))
         self.dnn = nn.Sequential(*layers)
 
-    def forward(self, dense, category, seq_feedid, seq_length):
+    def hot_path(self, dense, category, seq_feedid, seq_length):
+        """The part of forward that runs in librank_b200: (side features [B,50], pooled sequence [B,16])."""
         cols = [c for c in self.embeddings if c in category]
         side = GatherConcat.apply(len(cols), dense, *[category[c] for c in cols],
                                   *[self.embeddings[c].weight for c in cols])
@@ -247,6 +248,10 @@ class BSTModel(nn.Module):
             last = i == len(blocks) - 1
             x = block.run(x, seq_length, idx=idx, pool=pool if last else None)
             idx = None
+        return side, x
+
+    def forward(self, dense, category, seq_feedid, seq_length):
+        side, x = self.hot_path(dense, category, seq_feedid, seq_length)
         all_features = torch.cat([side, x], dim=1)
         logits = run_tower(list(self.dnn), all_features)      # = self.dnn(all_features), BatchNorm1d+LeakyReLU fused
         probabilities = torch.sigmoid(logits)

@@ -163,14 +163,16 @@ class DCNModel(nn.Module):
         self._ephemeral = EphemeralBuffer()
         self.ephemeral_frozen = False   # True: reuse the weights of the last draw_ephemeral()
 
-    def draw_ephemeral(self, device=None, width=None):
+    def draw_ephemeral(self, device=None, width=None, fresh=False):
         """Replay one forward's CPU-generator draws (DCN/dcn.py:37-41, once per cross layer) and
-        ship them to the GPU.  Returns device views (w[L,d], b[L,d])."""
+        ship them to the GPU.  Returns device views (w[L,d], b[L,d]) — of the fixed-address buffer a
+        frozen (CUDA-graph) forward reads, or of a new tensor when `fresh` (every eager forward)."""
         device = self.output_layer.weight.device if device is None else device
         w, b = draw_cross_weights(self.input_dim if width is None else width, self.num_cross_layer)
-        return self._ephemeral.upload([w, b], device)
+        return self._ephemeral.upload([w, b], device, fresh=fresh)
 
-    def forward(self, dense, category):
+    def hot_path(self, dense, category):
+        """The part of forward that runs in librank_b200: (concat_all, cross_vec)."""
         cols = [c for c in self.embeddings if c in category]
         offsets, off = [], int(dense.shape[1])
         for c in cols:
@@ -179,10 +181,13 @@ class DCNModel(nn.Module):
         if self.ephemeral_frozen and self._ephemeral.ready:
             w, b = self._ephemeral.views([(self.num_cross_layer, off)] * 2)
         else:
-            w, b = self.draw_ephemeral(dense.device, off)
-        concat_all, cross_vec = _CrossNet.apply(
+            w, b = self.draw_ephemeral(dense.device, off, fresh=True)
+        return _CrossNet.apply(
             len(cols), offsets, dense, w, b, *[category[c] for c in cols],
             *[self.embeddings[c].weight for c in cols])
+
+    def forward(self, dense, category):
+        concat_all, cross_vec = self.hot_path(dense, category)
         dnn_vec = self.dnn(concat_all)
         logit = self.output_layer(torch.cat([cross_vec, dnn_vec], dim=1))
         probability = torch.sigmoid(logit)

@@ -120,17 +120,19 @@ class DeepCrossingModel(nn.Module):
         self._ephemeral = EphemeralBuffer()
         self.ephemeral_frozen = False
 
-    def draw_ephemeral(self, device=None, width=None):
-        """Replay one forward's CPU-generator draws (two nn.Linear per unit) onto the GPU."""
+    def draw_ephemeral(self, device=None, width=None, fresh=False):
+        """Replay one forward's CPU-generator draws (two nn.Linear per unit) onto the GPU (`fresh`: into a
+        new tensor instead of the fixed-address buffer of the frozen / CUDA-graph path)."""
         device = self.output_layer.weight.device if device is None else device
         pack = draw_residual_units(self.input_dim if width is None else width, self.residual_internal_dim,
                                    self.residual_network_num)
         self._pack_numel = int(pack.numel())
         if not pack.numel():
             return torch.zeros(0, device=device)
-        return self._ephemeral.upload([pack], device)[0]
+        return self._ephemeral.upload([pack], device, fresh=fresh)[0]
 
-    def forward(self, dense, category):
+    def hot_path(self, dense, category):
+        """The part of forward that runs in librank_b200: the output of the residual stack."""
         cols = [c for c in self.embeddings if c in category]
         offsets, off = [], int(dense.shape[1])
         for c in cols:
@@ -139,10 +141,13 @@ class DeepCrossingModel(nn.Module):
         if self.ephemeral_frozen and self._ephemeral.ready:
             units = self._ephemeral.views([(self._pack_numel,)])[0]
         else:
-            units = self.draw_ephemeral(dense.device, off)
-        net = _ResidualStack.apply(len(cols), tuple(offsets), self.residual_internal_dim,
-                                   self.residual_network_num, dense, units, *[category[c] for c in cols],
-                                   *[self.embeddings[c].weight for c in cols])
+            units = self.draw_ephemeral(dense.device, off, fresh=True)
+        return (_ResidualStack.apply(len(cols), tuple(offsets), self.residual_internal_dim,
+                                     self.residual_network_num, dense, units, *[category[c] for c in cols],
+                                     *[self.embeddings[c].weight for c in cols]),)
+
+    def forward(self, dense, category):
+        (net,) = self.hot_path(dense, category)
         logit = self.output_layer(net)
         probability = torch.sigmoid(logit)
         return probability, logit

@@ -110,13 +110,17 @@ class DeepFM(nn.Module):
         self.deep_output_layer = nn.Linear(width, 1)
         self.final_layer = nn.Linear(3, 1)
 
-    def forward(self, category):
+    def hot_path(self, category):
+        """The part of forward that runs in librank_b200: (deep_input, fm_first, fm_second)."""
         cols = [c for c in self.first_order_embeddings if c in category]
         F = len(cols)
         args = ([category[c] for c in cols]
                 + [self.first_order_embeddings[c].weight for c in cols]
                 + [self.second_order_embeddings[c].weight for c in cols])
-        deep_input, fm_first_order_logit, fm_second_order_logit = _FMInteraction.apply(F, *args)
+        return _FMInteraction.apply(F, *args)
+
+    def forward(self, category):
+        deep_input, fm_first_order_logit, fm_second_order_logit = self.hot_path(category)
         deep_output = run_tower(self.deep_layers, deep_input)     # the reference's layer loop
         deep_logit = self.deep_output_layer(deep_output)
         total_logit = self.final_layer(

@@ -120,8 +120,13 @@ def _din_args(cat_tables, cat_idx, cat_offsets, dense_cols, target_w, target_idx
     a.T = int(hi.shape[1])
     a.att_off, a.width, a.l2_from, a.use_softmax = att_off, width, l2_from, int(bool(use_softmax))
     precision = _PRECISION if precision is None else precision
-    # the tensor-core unit exists for D = 16 (the model's dim); other dims run the fp32 kernel
-    a.precision = 1 if (precision == "bf16" and int(his_w.shape[1]) == 16) else 0
+    if precision not in ("fp32", "bf16"):
+        raise ValueError("activation-unit precision must be 'fp32' or 'bf16'")
+    if precision == "bf16" and int(his_w.shape[1]) != 16:
+        # the tensor-core unit is built for D = 16 (the model's dim): no silent fp32 fallback
+        raise _lib.RankB200Error(f"the tcgen05 activation unit needs embedding dim 16, got {int(his_w.shape[1])}; "
+                                 "use precision 'fp32' for other dims")
+    a.precision = 1 if precision == "bf16" else 0
     mlp = _lib.require_cuda(mlp, "attention mlp", torch.float32)
     if mlp.numel() != _lib.load().rk_din_mlp_floats(int(hw.shape[1])):
         raise ValueError("packed attention weights have the wrong size")
@@ -172,14 +177,14 @@ class _DinHotPath(torch.autograd.Function):
                                       live_mode=[_lib.LIVE_ALL] * (F + 1) + [mode])
             ctx.dims = [int(t.shape[1]) for t in cat_tabs]
             ctx.rows = rows
-            ctx.save_for_backward(concat_all, norm, att_w, masks)
+            ctx.save_for_backward(concat_all, norm, att_w, masks, mlp)
         return concat_all, norm
 
     @staticmethod
     def backward(ctx, g_concat, g_norm):
         lib = _lib.load()
         n_dense, F, offsets = ctx.cfg[:3]
-        concat_all, norm, att_w, masks = ctx.saved_tensors
+        concat_all, norm, att_w, masks, mlp = ctx.saved_tensors      # mlp: version-checked by autograd
         B, T, D, width, tgt_off = ctx.shape
         n_in = 2 + n_dense + 2 * F + 5
         if g_concat is None and g_norm is None:
@@ -222,13 +227,13 @@ class _DinAttention(torch.autograd.Function):
                             _lib.err_flag(dev).data_ptr(), _lib.stream_ptr())
         _lib.check(rc, "rk_din_fwd")
         ctx.args, ctx.keep, ctx.shape = a, keep, (B, T, D)
-        ctx.save_for_backward(out, att_w, masks)
+        ctx.save_for_backward(out, att_w, masks, mlp)
         return out[:, D:].contiguous()
 
     @staticmethod
     def backward(ctx, g_out):
         lib = _lib.load()
-        out, att_w, masks = ctx.saved_tensors
+        out, att_w, masks, mlp = ctx.saved_tensors
         B, T, D = ctx.shape
         dev = out.device
         g_concat = torch.zeros(B, 2 * D, dtype=torch.float32, device=dev)
@@ -283,13 +288,15 @@ class DIN(nn.Module):
         self.ephemeral_frozen = False
         self.activation_unit_precision = None     # None: follow set_activation_unit_precision()
 
-    def draw_ephemeral(self, device=None):
-        """Replay one forward's CPU-generator draws (att_net, DIN/din.py:61-67) onto the GPU."""
+    def draw_ephemeral(self, device=None, fresh=False):
+        """Replay one forward's CPU-generator draws (att_net, DIN/din.py:61-67) onto the GPU (`fresh`:
+        into a new tensor instead of the fixed-address buffer of the frozen / CUDA-graph path)."""
         device = self.output_layer.weight.device if device is None else device
         mlp = draw_attention_mlp(self.embeddings[SEQ].embedding_dim)
-        return self._ephemeral.upload([mlp], device)[0]
+        return self._ephemeral.upload([mlp], device, fresh=fresh)[0]
 
-    def forward(self, dense, category, sequence, target):
+    def hot_path(self, dense, category, sequence, target):
+        """The part of forward that runs in librank_b200: (concat_all[B,82], per-sample L2 norm[B])."""
         dense_cols = [dense[c] for c in dense]
         cols = [c for c in self.embeddings if c in category]
         offsets, off = [], len(dense_cols)
@@ -300,12 +307,15 @@ class DIN(nn.Module):
         if self.ephemeral_frozen and self._ephemeral.ready:
             mlp = self._ephemeral.views([(_lib.load().rk_din_mlp_floats(self.embeddings[SEQ].embedding_dim),)])[0]
         else:
-            mlp = self.draw_ephemeral(dev)
+            mlp = self.draw_ephemeral(dev, fresh=True)
         cfg = (len(dense_cols), len(cols), tuple(offsets), bool(self.use_softmax), self.activation_unit_precision)
-        concat_all, norm = _DinHotPath.apply(
+        return _DinHotPath.apply(
             cfg, mlp, *dense_cols, *[category[c] for c in cols], target['feedid'], sequence[SEQ],
             sequence[SEQ_LEN], *[self.embeddings[c].weight for c in cols],
             self.embeddings['feedid'].weight, self.embeddings[SEQ].weight)
+
+    def forward(self, dense, category, sequence, target):
+        concat_all, norm = self.hot_path(dense, category, sequence, target)
         net = run_tower(self.fcn, concat_all)      # the reference's `for layer in self.fcn` loop
         logit = self.output_layer(net)
         probability = torch.sigmoid(logit)

@@ -17,22 +17,34 @@ class EphemeralBuffer:
     def __init__(self):
         self._dev = None
 
-    def upload(self, tensors, device):
-        """Copy CPU fp32 tensors to `device`; returns device views with the same shapes."""
+    def upload(self, tensors, device, fresh=False):
+        """Copy CPU fp32 tensors to `device`; returns device views with the same shapes.
+        `fresh=False`: into the buffer with the fixed address (what a captured CUDA graph reads; the
+        previous draw is overwritten in place).  `fresh=True`: into a newly allocated device tensor,
+        as the reference does with its per-call parameters — two forwards before a backward then
+        keep two sets of weights, and autograd's saved-tensor version check guards them."""
         flat = torch.cat([t.detach().reshape(-1).to(torch.float32) for t in tensors])
-        if self._dev is None or self._dev.numel() != flat.numel() or self._dev.device != device:
-            self._dev = torch.empty(flat.numel(), dtype=torch.float32, device=device)
+        if fresh:
+            dev = torch.empty(flat.numel(), dtype=torch.float32, device=device)
+        else:
+            if self._dev is None or self._dev.numel() != flat.numel() or self._dev.device != device:
+                self._dev = torch.empty(flat.numel(), dtype=torch.float32, device=device)
+            dev = self._dev
         # a fresh pinned tensor per call: torch's host allocator keeps it alive until the copy ran
-        self._dev.copy_(flat.pin_memory(), non_blocking=True)
-        return self.views([t.shape for t in tensors])
+        dev.copy_(flat.pin_memory() if torch.cuda.is_available() else flat, non_blocking=True)
+        return self._carve(dev, [t.shape for t in tensors])
 
     def views(self, shapes):
+        return self._carve(self._dev, shapes)
+
+    @staticmethod
+    def _carve(dev, shapes):
         out, pos = [], 0
         for shp in shapes:
             n = 1
             for s in shp:
                 n *= int(s)
-            out.append(self._dev[pos:pos + n].view(*shp))
+            out.append(dev[pos:pos + n].view(*shp))
             pos += n
         return out
 

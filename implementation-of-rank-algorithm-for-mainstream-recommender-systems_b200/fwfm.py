@@ -98,6 +98,10 @@ class FwFM(nn.Module):
         self.field_weight = nn.Parameter(torch.randn(self.num_pairs), requires_grad=True)
         self.bias = nn.Parameter(torch.zeros(1))
 
+    def hot_path(self, x):
+        """FwFM has no torch tower: the whole forward runs in librank_b200."""
+        return (self.forward(x),)
+
     def forward(self, x):
         F = self.num_fields
         if F > len(FWFM_COLUMNS):     # the reference indexes a list of six columns (fwfm.py:118-121)

@@ -51,6 +51,7 @@ class PackedBatch:
         self.dev = torch.empty(nbytes, dtype=torch.uint8, device=self.device)
         self.host_views = _build(self._views(self.host))
         self.device_views = _build(self._views(self.dev))
+        self._copied = None       # CUDA event recorded behind the last host -> device copy of `host`
 
     @classmethod
     def like(cls, batch, device, pin=True):
@@ -81,8 +82,19 @@ class PackedBatch:
             total += n * torch.empty(0, dtype=dtype).element_size()
         return total
 
+    def wait_host_free(self):
+        """Block the host until the last asynchronous copy out of the pinned buffer has run: the copy
+        of step k is queued behind step k-1's kernels, so a host that runs ahead of the GPU (any loop
+        without a .item(), every CUDA-graph replay loop) would otherwise overwrite batch k with batch
+        k+1 before the GPU has read it.  Call before writing `host` / `host_views` directly."""
+        if self._copied is not None:
+            self._copied.synchronize()
+            self._copied = None
+
     def fill(self, batch):
-        """Host-side collate into the pinned buffer (what a loader would do directly)."""
+        """Host-side collate into the pinned buffer (what a loader would do directly).  Waits for the
+        previous to_device() copy of this buffer first (see wait_host_free)."""
+        self.wait_host_free()
         leaves = dict(_leaves(batch))
         for path, dtype, shape, _ in self.layout:
             src = leaves[path]
@@ -98,6 +110,9 @@ class PackedBatch:
     def to_device(self, non_blocking=True):
         """One host-to-device copy of the whole batch on the current stream; returns the device views."""
         self.dev.copy_(self.host, non_blocking=non_blocking)
+        if non_blocking and self.dev.is_cuda:
+            self._copied = torch.cuda.Event()
+            self._copied.record(torch.cuda.current_stream(self.dev.device))
         return self.device_views
 
     def load_from(self, other: "PackedBatch", non_blocking=True):
@@ -106,4 +121,7 @@ class PackedBatch:
             raise ValueError("PackedBatch.load_from: layouts differ")
         src = other.dev if other.dev.device == self.dev.device and other is not self else other.host
         self.dev.copy_(src, non_blocking=non_blocking)
+        if src is other.host and non_blocking and self.dev.is_cuda:
+            other._copied = torch.cuda.Event()
+            other._copied.record(torch.cuda.current_stream(self.dev.device))
         return self.device_views

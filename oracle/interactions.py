@@ -139,7 +139,7 @@ def din_local_activation(query, keys, keys_length, mlp, use_softmax):
     cross = torch.cat([q, keys, q - keys, q * keys], dim=2)                        # :59
     score = F.linear(torch.relu(F.linear(torch.relu(F.linear(cross, w1, b1)), w2, b2)), w3, b3)
     score = score.squeeze(2)                                                       # :69
-    mask = torch.arange(T).expand(B, T) < keys_length.unsqueeze(1)                 # :71
+    mask = torch.arange(T, device=keys.device).expand(B, T) < keys_length.unsqueeze(1)                 # :71
     if use_softmax:
         pad = torch.ones_like(score) * (-2 ** 32 + 1)                              # :74
         score = torch.where(mask, score, pad) / (D ** 0.5)                         # :75-76
@@ -163,7 +163,7 @@ def bst_transformer_block(x, pad_mask, p, nhead, dropout_p=0.0):
     if dropout_p:
         raise ValueError("the oracle is defined for dropout 0 only")
     B, T, d = x.shape
-    pos = p["position_embedding.weight"][torch.arange(T)]                          # :68-69
+    pos = p["position_embedding.weight"][torch.arange(T, device=p["position_embedding.weight"].device)]                          # :68-69
     qk_in = x + pos                                                                # :70-71 (not values)
     q = F.linear(qk_in, p["w_q.weight"], p["w_q.bias"]).view(B, T, nhead, -1).transpose(1, 2)
     k = F.linear(qk_in, p["w_k.weight"], p["w_k.bias"]).view(B, T, nhead, -1).transpose(1, 2)
@@ -183,7 +183,7 @@ def bst_sequence_feature(seq_rows, seq_length, blocks, nhead, pooling):
     """BSTModel.forward sequence branch (BST/bst.py:224-241): key-padding mask t >= len, the
     transformer blocks, then sum (or sum / len) over ALL T positions."""
     B, T, _ = seq_rows.shape
-    mask = torch.arange(T).expand(B, T) >= seq_length.unsqueeze(1)                 # :226-227
+    mask = torch.arange(T, device=seq_length.device).expand(B, T) >= seq_length.unsqueeze(1)                 # :226-227
     out = seq_rows
     for p in blocks:
         out = bst_transformer_block(out, mask, p, nhead)

@@ -116,11 +116,15 @@ class OracleDCN(nn.Module):             # DCN/dcn.py:114-180
         cols = [c for c in self.embeddings if c in category]
         x0 = X.concat_features(dense, [self.embeddings[c].weight for c in cols], [category[c] for c in cols])
         ws, bs = [], []
-        for _ in range(self.num_cross_layer):                      # draws of DCN/dcn.py:37-41
+        frozen = getattr(self, "frozen_ephemeral", None)           # bench.py's CUDA-graph leg: last draw kept
+        for _ in range(self.num_cross_layer if frozen is None else 0):   # draws of DCN/dcn.py:37-41
             w = torch.zeros(x0.shape[-1], 1)
             nn.init.xavier_normal_(w)
-            ws.append(w.to(x0.dtype))
-            bs.append(torch.zeros(x0.shape[-1], 1, dtype=x0.dtype))
+            ws.append(w.to(x0.dtype).to(x0.device))                # ".to(x0.device)" as DCN/dcn.py:44-45
+            bs.append(torch.zeros(x0.shape[-1], 1, dtype=x0.dtype).to(x0.device))
+        if frozen is not None:
+            ws, bs = frozen
+        self.last_ephemeral = (ws, bs)
         cross = X.cross_network(x0, ws, bs)
         logit = self.output_layer(torch.cat([cross, self.dnn(x0)], dim=1))
         return torch.sigmoid(logit), logit
@@ -140,10 +144,14 @@ class OracleDeepCrossing(nn.Module):    # DeepCrossing/deepcrossing.py:106-163
         cols = [c for c in self.embeddings if c in category]
         x = X.concat_features(dense, [self.embeddings[c].weight for c in cols], [category[c] for c in cols])
         units = []
-        for _ in range(self.residual_network_num):                 # draws of deepcrossing.py:37,39
+        frozen = getattr(self, "frozen_ephemeral", None)           # bench.py's CUDA-graph leg: last draw kept
+        for _ in range(self.residual_network_num if frozen is None else 0):   # draws of deepcrossing.py:37,39
             l1 = nn.Linear(x.shape[-1], self.residual_internal_dim)
             l2 = nn.Linear(self.residual_internal_dim, x.shape[-1])
-            units.append(tuple(t.detach().to(x.dtype) for t in (l1.weight, l1.bias, l2.weight, l2.bias)))
+            units.append(tuple(t.detach().to(x.dtype).to(x.device) for t in (l1.weight, l1.bias, l2.weight, l2.bias)))
+        if frozen is not None:
+            units = frozen
+        self.last_ephemeral = units
         logit = self.output_layer(X.residual_units(x, units))
         return torch.sigmoid(logit), logit
 
@@ -210,10 +218,14 @@ class OracleDIN(nn.Module):             # DIN/din.py:225-323
         tgt = X.gather_rows(self.embeddings["feedid"].weight, target["feedid"])
         keys = X.gather_rows(self.embeddings["his_read_comment_7d_seq"].weight,
                              sequence["his_read_comment_7d_seq"])
-        att_net = nn.Sequential(nn.Linear(4 * keys.shape[-1], 64), nn.ReLU(), nn.Linear(64, 32), nn.ReLU(),
-                                nn.Linear(32, 1))                   # draws of DIN/din.py:61-67
-        mlp = tuple(t.detach().to(keys.dtype) for t in (att_net[0].weight, att_net[0].bias, att_net[2].weight,
-                                                        att_net[2].bias, att_net[4].weight, att_net[4].bias))
+        mlp = getattr(self, "frozen_ephemeral", None)               # bench.py's CUDA-graph leg: last draw kept
+        if mlp is None:
+            att_net = nn.Sequential(nn.Linear(4 * keys.shape[-1], 64), nn.ReLU(), nn.Linear(64, 32), nn.ReLU(),
+                                    nn.Linear(32, 1))               # draws of DIN/din.py:61-67 (+ .to(device) :68)
+            mlp = tuple(t.detach().to(keys.dtype).to(keys.device) for t in (
+                att_net[0].weight, att_net[0].bias, att_net[2].weight, att_net[2].bias, att_net[4].weight,
+                att_net[4].bias))
+        self.last_ephemeral = mlp
         att = X.din_local_activation(tgt, keys, sequence["his_read_comment_7d_seq_length"], mlp,
                                      self.use_softmax)
         net = torch.cat([dense_input] + cat_rows + [tgt, att], dim=1)

@@ -78,3 +78,22 @@ def rel_err(a, b, floor=1e-30):
         return 0.0
     scale = max(float(b.abs().max()), floor)
     return float((a - b).abs().max()) / scale
+
+
+def pytest_terminal_summary(terminalreporter, exitstatus, config):
+    """How often the float64 arbiter of tests/test_gpu_models.py::compare decided a gradient
+    comparison (fp32 comparison > tol, accepted against the float64 run), and the worst errors."""
+    mod = sys.modules.get("test_gpu_models")
+    stats = getattr(mod, "ARBITER", None)
+    if not stats or not stats["comparisons"]:
+        return
+    tr = terminalreporter
+    tr.write_line(f"float64 arbiter: fired {stats['fired']} of {stats['comparisons']} gradient comparisons; "
+                  f"worst e_ref {stats['worst_e_ref']:.3e}, worst e_ours {stats['worst_e_ours']:.3e}")
+    for case in stats["cases"]:
+        tr.write_line("  arbiter: %s %s fp32-vs-fp32 %.3e, ours-vs-f64 %.3e, oracle-vs-f64 %.3e" % case)
+    out_dir = os.path.join(ROOT, "gpurun_out")
+    if os.path.isdir(out_dir):
+        import json
+        with open(os.path.join(out_dir, "arbiter_stats.json"), "w") as f:
+            json.dump(stats, f, indent=1)

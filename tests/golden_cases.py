@@ -41,3 +41,20 @@ def replay(model, fx, inputs, cotangents):
     loss.backward()
     grads = {k: p.grad for k, p in model.named_parameters() if p.grad is not None}
     return outs, grads
+
+
+def expand_sparse(entry):
+    """A sparsely stored table of tests/golden/checkpoint_*.pt -> the full [height, dim] tensor
+    (zeros in the rows the recorded batch never touches)."""
+    if not isinstance(entry, dict):
+        return entry
+    full = torch.zeros(entry["height"], entry["dim"], dtype=entry["values"].dtype)
+    full[entry["rows"]] = entry["values"]
+    return full
+
+
+def expand_checkpoint(fx):
+    """In place: state_dict and grads of a checkpoint fixture as dense tensors."""
+    fx["state_dict"] = {k: expand_sparse(v) for k, v in fx["state_dict"].items()}
+    fx["grads"] = {k: expand_sparse(v) for k, v in fx["grads"].items()}
+    return fx

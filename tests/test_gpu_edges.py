@@ -149,3 +149,42 @@ def test_repeated_step_is_bit_identical(wechat_vocab_dir):
     assert torch.equal(outs[0][0], outs[1][0])
     for k in outs[0][1]:
         assert torch.equal(outs[0][1][k], outs[1][1][k]), k
+
+
+@pytest.mark.parametrize("name", ["DIN", "DCNModel", "DeepCrossingModel"])
+def test_two_forwards_before_one_backward(wechat_vocab_dir, name):
+    """Per-call random weights (DIN/din.py:61-67, DCN/dcn.py:37-41, DeepCrossing/deepcrossing.py:37-39)
+    belong to their own forward: loss(model(a)) + loss(model(b)) with one backward must equal the sum of
+    the two single steps (gradient accumulation), not use the second draw for both."""
+    kw = dict(dropout_rate=0.0) if name == "DIN" else {}
+    torch.manual_seed(0)
+    model = getattr(rank_b200, name)(wechat_vocab_dir, **kw).to(DEV).train()
+    for m in model.modules():                      # batch statistics do not depend on the call order,
+        if isinstance(m, torch.nn.BatchNorm1d):    # but keep running stats out of the comparison
+            m.momentum = 0.0
+    make = (lambda s: synthetic.din_batch(256, 20, s)) if name == "DIN" else (lambda s: synthetic.side_batch(256, s))
+    a, b = to_device(make(1), DEV), to_device(make(2), DEV)
+
+    def loss_of(batch):
+        if name == "DIN":
+            p, _, l2 = model(batch["dense"], batch["category"], batch["sequence"], batch["target"])
+            return torch.nn.functional.binary_cross_entropy(p.squeeze(1), batch["label"]) + l2
+        return torch.nn.functional.binary_cross_entropy_with_logits(
+            model(batch["dense"], batch["category"])[1].squeeze(1), batch["label"])
+
+    single = {}
+    torch.manual_seed(11)                          # draw order: a's weights, then b's
+    for batch in (a, b):
+        model.zero_grad()
+        state = torch.get_rng_state()
+        loss_of(batch).backward()
+        for k, p in model.named_parameters():
+            if p.grad is not None:
+                single[k] = single.get(k, 0) + p.grad.detach().clone()
+        del state
+    model.zero_grad()
+    torch.manual_seed(11)
+    (loss_of(a) + loss_of(b)).backward()
+    for k, p in model.named_parameters():
+        if p.grad is not None:
+            assert rel_err(p.grad, single[k]) <= TOL, k

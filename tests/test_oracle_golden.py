@@ -11,7 +11,7 @@ import golden_cases
 from oracle import interactions as X
 from oracle import models as oracle_models
 
-MODEL_FIXTURES = [p for p in golden_files() if "smoke" not in p and "loader" not in p]
+MODEL_FIXTURES = [p for p in golden_files() if "smoke" not in p and "loader" not in p and "checkpoint" not in p]
 TOL = 2e-6   # same torch ops in (almost) the same order: far inside the 1e-5 bar
 
 
@@ -90,3 +90,21 @@ def test_oracle_loads_shipped_checkpoint_and_matches_reference(which):
     torch.manual_seed(99)
     pb, lb = b(dense, cat)
     assert rel_err(lb, la) <= TOL and rel_err(pb, pa) <= TOL
+
+
+@pytest.mark.parametrize("which", ["dcn", "deepcrossing"])
+def test_oracle_matches_shipped_checkpoint_fixture(which, tmp_path):
+    """tests/golden/checkpoint_*.pt: the reference's two trained state_dicts run through the unmodified
+    reference classes (make_checkpoint_golden.py) — outputs and every gradient."""
+    import golden_cases
+    import rank_b200
+    fx = golden_cases.expand_checkpoint(load_golden(os.path.join(GOLDEN_DIR, f"checkpoint_{which}.pt")))
+    vocab = rank_b200.write_vocab_dir(str(tmp_path), fx["vocab_lines"]) + "/"
+    model = golden_cases.build(fx, oracle_models, vocab, oracle=True)
+    model.load_state_dict(fx["state_dict"], strict=True)
+    outs, grads = golden_cases.replay(model, fx, fx["inputs"], fx["cotangents"])
+    for o, r in zip(outs, fx["outputs"]):
+        assert rel_err(o, r) <= TOL
+    assert set(grads) == set(fx["grads"])
+    for k, g in fx["grads"].items():
+        assert rel_err(grads[k], g) <= TOL, k

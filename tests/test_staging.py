@@ -52,3 +52,23 @@ def test_one_copy_feeds_the_model_bit_exact(wechat_vocab_dir):
         prob, _, l2 = model(inp["dense"], inp["category"], inp["sequence"], inp["target"])
         outs.append((prob.detach().clone(), l2.detach().clone()))
     assert torch.equal(outs[0][0], outs[1][0]) and torch.equal(outs[0][1], outs[1][1])
+
+
+@pytest.mark.gpu
+def test_refill_waits_for_the_previous_copy():
+    """fill -> to_device -> fill with the copy still queued behind a busy stream: the second fill must
+    not overwrite the pinned buffer before the first copy has read it."""
+    from rank_b200 import _lib
+    dev = torch.device("cuda", 0)
+    a, b = synthetic.side_batch(4096, 1), synthetic.side_batch(4096, 2)
+    packed = PackedBatch.like(a, dev)
+    lib = _lib.load()
+    packed.fill(a)
+    _lib.check(lib.rk_debug_spin(50_000, _lib.stream_ptr()), "rk_debug_spin")   # 50 ms ahead of the copy
+    views = packed.to_device()
+    snap = {k: v.clone() for k, v in dict(_leaves(views)).items()}              # queued behind the copy
+    packed.fill(b)                                                              # must wait for the copy
+    torch.cuda.synchronize()
+    want = dict(_leaves(a))
+    for k, v in snap.items():
+        assert torch.equal(v.cpu(), want[k]), k
