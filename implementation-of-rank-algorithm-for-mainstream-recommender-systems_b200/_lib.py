@@ -18,6 +18,7 @@ LIB_PATH = PKG_DIR / "librank_b200.so"
 RK_MAX_FIELDS = 24
 RK_MAX_TABLES = 32
 RK_MAX_LAYERS = 8
+RK_DIRECT_MAX_N = 8192
 ABI_VERSION = 1
 
 
@@ -29,6 +30,11 @@ class RkField(C.Structure):
 class RkGradTable(C.Structure):
     _fields_ = [("g", C.c_void_p), ("ld", C.c_int64), ("dw", C.c_void_p),
                 ("dim", C.c_int32), ("field", C.c_int32)]
+
+
+class RkDirectTable(C.Structure):
+    _fields_ = [("idx", C.c_void_p), ("g", C.c_void_p), ("ld", C.c_int64), ("dw", C.c_void_p),
+                ("rows", C.c_int64), ("n", C.c_int64), ("dim", C.c_int32), ("reserved", C.c_int32)]
 
 
 class RkDinArgs(C.Structure):
@@ -66,6 +72,7 @@ PROTOTYPES = {
     "rk_plan_build": (_I, [_P, _P, _P, _I, _P, _P, _P, _P, _P, _P, _Z, _P, _P]),
     "rk_reduce_workspace_bytes": (_Z, [_P, _I, _P, _I]),
     "rk_embgrad_segment_reduce": (_I, [_P, _P, _P, _P, _I, _P, _I, _P, _Z, _P]),
+    "rk_embgrad_direct_reduce": (_I, [_P, _I, _P, _P]),
     "rk_gather_concat_fwd": (_I, [_P, _I, _P, _I, _L, _P, _I, _P, _P]),
     "rk_deepfm_fwd": (_I, [_P, _P, _I, _L, _P, _P, _P, _P, _P]),
     "rk_deepfm_bwd": (_I, [_P, _P, _P, _I, _I, _L, _P, _P]),

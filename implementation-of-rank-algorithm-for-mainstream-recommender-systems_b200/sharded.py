@@ -42,7 +42,7 @@ class CudaShardOps:
         rc = lib.rk_shard_owner(idx.data_ptr(), n, rows_total, rows_per_rank, owner.data_ptr(),
                                 _lib.err_flag(dev).data_ptr(), _lib.stream_ptr())
         _lib.check(rc, "rk_shard_owner")
-        plan = OccurrencePlan([owner], [world])
+        plan = OccurrencePlan([owner], [world], direct=False)
         plan.join()
         send_local = torch.empty(n, dtype=torch.int64, device=dev)
         inv = torch.empty(n, dtype=torch.int64, device=dev)
@@ -63,7 +63,7 @@ class CudaShardOps:
         """Sorted order of the requests this rank serves; for sparse gradients also the compact
         ranks and the unique rows (host-synchronising: the unique count sizes the gradient)."""
         lib = _lib.load()
-        plan = OccurrencePlan([recv_local], [rows])
+        plan = OccurrencePlan([recv_local], [rows], direct=False)
         uniq = None
         if sparse:
             plan.join()
@@ -75,7 +75,7 @@ class CudaShardOps:
                                      uniq_rows.data_ptr(), n_uniq.data_ptr(), _lib.stream_ptr())
             _lib.check(rc, "rk_plan_compact")
             u = int(n_uniq.item())
-            plan.sorted_keys, plan.rows = rank_keys, [max(u, 1)]
+            plan.sorted_keys, plan.rows, plan.s_rows = rank_keys, [max(u, 1)], [max(u, 1)]
             uniq = uniq_rows[:u]
         return plan, uniq
 

@@ -72,10 +72,20 @@ class GradSource:
     field: int           # which plan field's occurrences feed this table
 
 
-class OccurrencePlan:
-    """Sorted order of all index occurrences of a batch (one entry per field)."""
+DIRECT_REDUCE = os.environ.get("RANK_B200_DIRECT", "1") != "0"
 
-    def __init__(self, indices: list[torch.Tensor], rows: list[int], seq_len=None, live_mode=None):
+
+class OccurrencePlan:
+    """How the embedding gradients of a batch's index columns will be reduced (one entry per field).
+
+    * per-sample columns (n <= RK_DIRECT_MAX_N occurrences, all live): nothing to prepare — their dense
+      gradients come from rk_embgrad_direct_reduce in one launch, which also writes the zeros;
+    * longer columns (DIN / BST histories, batches beyond 8192) and padded sequence fields: the stable
+      (field, row) order of rk_plan_build, computed here (it depends on the indices only) on a side
+      stream while the forward runs, consumed by rk_embgrad_segment_reduce.
+    `direct=False` sorts every field (the order is then available as sorted_keys / perm)."""
+
+    def __init__(self, indices: list[torch.Tensor], rows: list[int], seq_len=None, live_mode=None, direct=None):
         """`seq_len[f]` (int64 [B]) and `live_mode[f]` (_lib.LIVE_*) mark field f as a padded
         sequence field whose dead positions are left out of the reduction."""
         lib = _lib.load()
@@ -87,47 +97,71 @@ class OccurrencePlan:
         self.n = [int(i.numel()) for i in self.indices]
         self.rows = [int(r) for r in rows]
         dev = self.indices[0].device
-        total = sum(self.n)
+        self.device = dev
+        modes_all = [_lib.LIVE_ALL] * self.F if live_mode is None else [int(m) for m in live_mode]
+        use_direct = DIRECT_REDUCE if direct is None else bool(direct)
+        self.direct = [use_direct and self.n[f] <= _lib.RK_DIRECT_MAX_N and modes_all[f] == _lib.LIVE_ALL
+                       for f in range(self.F)]
+        # ---- the fields that need the sorted order
+        self.sort_fields = [f for f in range(self.F) if not self.direct[f]]
+        self.sort_pos = {f: k for k, f in enumerate(self.sort_fields)}
+        self._event = None
+        self._ws = None
+        self.sorted_keys = self.perm = None
+        if not self.sort_fields:
+            self.total = 0
+            return
+        S = len(self.sort_fields)
+        s_idx = [self.indices[f] for f in self.sort_fields]
+        self.s_n = [self.n[f] for f in self.sort_fields]
+        self.s_rows = [self.rows[f] for f in self.sort_fields]
+        total = sum(self.s_n)
         self.total = total
         self.sorted_keys = torch.empty(max(total, 1), dtype=torch.int32, device=dev)
         self.perm = torch.empty(max(total, 1), dtype=torch.int32, device=dev)
         ws_bytes = lib.rk_plan_workspace_bytes(total)
         ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
-        idx_ptrs = (C.c_void_p * self.F)(*[i.data_ptr() for i in self.indices])
+        idx_ptrs = (C.c_void_p * S)(*[i.data_ptr() for i in s_idx])
         len_ptrs = seq_T = modes = None
-        if live_mode is not None and any(live_mode):
-            lens = [None if m == _lib.LIVE_ALL else _lib.require_cuda(l, f"seq_len[{k}]", torch.int64)
-                    for k, (l, m) in enumerate(zip(seq_len, live_mode))]
+        lens = []
+        s_modes = [modes_all[f] for f in self.sort_fields]
+        if any(s_modes):
+            lens = [None if m == _lib.LIVE_ALL else _lib.require_cuda(seq_len[f], f"seq_len[{f}]", torch.int64)
+                    for f, m in zip(self.sort_fields, s_modes)]
             self._lens = lens
-            len_ptrs = (C.c_void_p * self.F)(*[None if l is None else l.data_ptr() for l in lens])
-            seq_T = (C.c_int32 * self.F)(*[0 if l is None else self.n[k] // max(int(l.numel()), 1)
-                                           for k, l in enumerate(lens)])
-            modes = (C.c_int32 * self.F)(*[int(m) for m in live_mode])
+            len_ptrs = (C.c_void_p * S)(*[None if l is None else l.data_ptr() for l in lens])
+            seq_T = (C.c_int32 * S)(*[0 if l is None else self.s_n[k] // max(int(l.numel()), 1)
+                                      for k, l in enumerate(lens)])
+            modes = (C.c_int32 * S)(*s_modes)
         # The order depends on the indices only, so it is built on a side stream while the main
-        # stream runs the forward kernel and the tower; reduce_to_dense() joins.  Every buffer was
-        # allocated above on the main stream and stays referenced until the join, so the caching
-        # allocator cannot hand it out early; inside a CUDA-graph capture the fork/join is captured.
+        # stream runs the forward kernel and the tower; reduce_to_dense() joins.  Every buffer the
+        # side stream touches is recorded on it, so the caching allocator cannot hand a block back to the
+        # main stream while rk_plan_build may still be using it, even if the plan is dropped without a join
+        # (a grad-enabled forward that never runs backward); inside a CUDA-graph capture the fork/join is
+        # captured.
         main = torch.cuda.current_stream(dev)
         side = _plan_stream(dev)
         self._ws = ws
-        self._event = None
         if side is None:
-            rc = lib.rk_plan_build(idx_ptrs, _i64_array(self.n), _i64_array(self.rows), self.F,
+            rc = lib.rk_plan_build(idx_ptrs, _i64_array(self.s_n), _i64_array(self.s_rows), S,
                                    len_ptrs, seq_T, modes, self.sorted_keys.data_ptr(), self.perm.data_ptr(),
                                    ws.data_ptr(), ws_bytes, _lib.err_flag(dev).data_ptr(), main.cuda_stream)
         else:
             side.wait_stream(main)
             with torch.cuda.stream(side):
-                rc = lib.rk_plan_build(idx_ptrs, _i64_array(self.n), _i64_array(self.rows), self.F,
+                rc = lib.rk_plan_build(idx_ptrs, _i64_array(self.s_n), _i64_array(self.s_rows), S,
                                        len_ptrs, seq_T, modes, self.sorted_keys.data_ptr(), self.perm.data_ptr(),
                                        ws.data_ptr(), ws_bytes, _lib.err_flag(dev).data_ptr(), side.cuda_stream)
                 self._event = side.record_event()
+            if not torch.cuda.is_current_stream_capturing():
+                for t in [ws, self.sorted_keys, self.perm, *s_idx, *[l for l in lens if l is not None]]:
+                    t.record_stream(side)
         _lib.check(rc, "rk_plan_build")
 
     def join(self):
         """Make the current stream wait for the plan (no-op when it was built in-stream)."""
         if self._event is not None:
-            torch.cuda.current_stream(self.sorted_keys.device).wait_event(self._event)
+            torch.cuda.current_stream(self.device).wait_event(self._event)
             self._event = None
         self._ws = None
 
@@ -138,31 +172,59 @@ class OccurrencePlan:
         if not 1 <= T <= _lib.RK_MAX_TABLES:
             raise ValueError(f"{T} gradient tables (max {_lib.RK_MAX_TABLES})")
         self.join()
-        dev = self.sorted_keys.device
-        # one zero-filled slab for all dense gradients (a single memset), carved per table
-        sizes = [s.rows * s.dim for s in sources]
-        starts, acc = [], 0
-        for sz in sizes:
-            starts.append(acc)
-            acc += (sz + 3) // 4 * 4          # keep every table 16-byte aligned
-        slab = torch.zeros(acc, dtype=torch.float32, device=dev)
-        grads = [slab[st:st + sz].view(s.rows, s.dim) for st, sz, s in zip(starts, sizes, sources)]
-        tabs = (_lib.RkGradTable * T)()
-        for t, (s, g) in enumerate(zip(sources, grads)):
+        dev = self.device
+        for s in sources:
             if s.rows != self.rows[s.field]:
                 raise ValueError("gradient table height does not match its plan field")
-            tabs[t].g = s.base.data_ptr() + 4 * s.offset
-            tabs[t].ld = s.ld
-            tabs[t].dw = g.data_ptr()
-            tabs[t].dim = s.dim
-            tabs[t].field = s.field
-        n_arr = _i64_array(self.n)
-        ws_bytes = lib.rk_reduce_workspace_bytes(n_arr, self.F, tabs, T)
-        ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
-        rc = lib.rk_embgrad_segment_reduce(self.sorted_keys.data_ptr(), self.perm.data_ptr(),
-                                           n_arr, _i64_array(self.rows), self.F, tabs, T,
-                                           ws.data_ptr(), ws_bytes, _lib.stream_ptr())
-        _lib.check(rc, "rk_embgrad_segment_reduce")
+        # one slab for all dense gradients (contiguous for the data-parallel all-reduce), carved per table:
+        # the tables reduced directly first (their kernel writes the zeros too), then the sorted ones, whose
+        # part of the slab is zero-filled by one memset
+        order = [t for t, s in enumerate(sources) if self.direct[s.field]] + \
+                [t for t, s in enumerate(sources) if not self.direct[s.field]]
+        n_direct = sum(self.direct[s.field] for s in sources)
+        starts, acc, sorted_from = {}, 0, 0
+        for k, t in enumerate(order):
+            if k == n_direct:
+                sorted_from = acc
+            starts[t] = acc
+            acc += (sources[t].rows * sources[t].dim + 3) // 4 * 4          # keep every table 16-byte aligned
+        if n_direct == T:
+            sorted_from = acc
+        slab = torch.empty(acc, dtype=torch.float32, device=dev)
+        if sorted_from < acc:
+            slab[sorted_from:].zero_()
+        grads = [slab[starts[t]:starts[t] + s.rows * s.dim].view(s.rows, s.dim) for t, s in enumerate(sources)]
+        if n_direct:
+            tabs = (_lib.RkDirectTable * n_direct)()
+            for k, t in enumerate(order[:n_direct]):
+                s, g = sources[t], grads[t]
+                tabs[k].idx = self.indices[s.field].data_ptr() if self.n[s.field] else None
+                tabs[k].g = s.base.data_ptr() + 4 * s.offset if self.n[s.field] else None
+                tabs[k].ld = s.ld
+                tabs[k].dw = g.data_ptr()
+                tabs[k].rows = s.rows
+                tabs[k].n = self.n[s.field]
+                tabs[k].dim = s.dim
+            rc = lib.rk_embgrad_direct_reduce(tabs, n_direct, _lib.err_flag(dev).data_ptr(), _lib.stream_ptr())
+            _lib.check(rc, "rk_embgrad_direct_reduce")
+        if n_direct < T:
+            S = T - n_direct
+            tabs = (_lib.RkGradTable * S)()
+            for k, t in enumerate(order[n_direct:]):
+                s, g = sources[t], grads[t]
+                tabs[k].g = s.base.data_ptr() + 4 * s.offset
+                tabs[k].ld = s.ld
+                tabs[k].dw = g.data_ptr()
+                tabs[k].dim = s.dim
+                tabs[k].field = self.sort_pos[s.field]
+            n_arr = _i64_array(self.s_n)
+            F = len(self.sort_fields)
+            ws_bytes = lib.rk_reduce_workspace_bytes(n_arr, F, tabs, S)
+            ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+            rc = lib.rk_embgrad_segment_reduce(self.sorted_keys.data_ptr(), self.perm.data_ptr(),
+                                               n_arr, _i64_array(self.s_rows), F, tabs, S,
+                                               ws.data_ptr(), ws_bytes, _lib.stream_ptr())
+            _lib.check(rc, "rk_embgrad_segment_reduce")
         return grads
 
 

@@ -88,6 +88,29 @@ int rk_embgrad_segment_reduce(const uint32_t* sorted_keys, const uint32_t* perm,
                               const rk_grad_table_t* tables, int n_tables, void* ws,
                               size_t ws_bytes, rk_stream_t stream);
 
+/* One-launch reduction for per-sample index columns (n <= RK_DIRECT_MAX_N occurrences per table; every
+ * per-sample field at batch <= 8192), replacing rk_plan_build + a memset + rk_embgrad_segment_reduce for
+ * those tables (same reference code: embedding_dense_backward under loss.backward(), e.g. DCN/dcn.py:166).
+ * Output-partitioned: every CTA owns 256 rows of one table, scans the whole index column, orders the
+ * occurrences that fall into its rows by (row, occurrence) and sums their gradient rows in that order
+ * (runs longer than 32 occurrences: fixed interleaved slots + a fixed tree).  dw is written completely —
+ * zeros for rows no occurrence touches — so it need NOT be pre-zeroed.  Tables of one launch that share
+ * idx, rows and n (DeepFM / FwFM: the [rows,1] and [rows,D] tables of a field) share the scan and the order.
+ * Deterministic, no float atomics.  Out-of-range indices count as row 0 and raise *err_flag. */
+#define RK_DIRECT_MAX_N 8192
+typedef struct rk_direct_table {
+    const int64_t* idx;   /* [n] index column */
+    const float*   g;     /* gradient row of occurrence o at g + o*ld (+0..dim-1) */
+    int64_t        ld;
+    float*         dw;    /* [rows, dim], written completely */
+    int64_t        rows;
+    int64_t        n;
+    int32_t        dim;
+    int32_t        reserved;
+} rk_direct_table_t;
+int rk_embgrad_direct_reduce(const rk_direct_table_t* tables, int n_tables, int32_t* err_flag,
+                             rk_stream_t stream);
+
 /* ---- gather + concat (the per-field lookup loops + torch.cat, DCN/dcn.py:163-169,
  *      DeepCrossing/deepcrossing.py:148-155) ------------------------------------------------
  * out[b, 0:n_dense] = dense[b, :]; out[b, off_f:off_f+dim_f] = W_f[idx_f[b], :]. */

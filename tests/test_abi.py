@@ -34,6 +34,7 @@ def test_library_exports_every_declared_symbol():
 def test_struct_layouts_match_header():
     assert ctypes.sizeof(_lib.RkField) == 32
     assert ctypes.sizeof(_lib.RkGradTable) == 32
+    assert ctypes.sizeof(_lib.RkDirectTable) == 56       # rk_direct_table_t
 
 
 def test_workspace_queries_need_no_gpu():

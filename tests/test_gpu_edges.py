@@ -124,6 +124,7 @@ def test_segment_reduce_is_linear_at_full_size():
     B, T, D, rows = 8192, 50, 16, 106445
     idx = synthetic.zipf_indices(gen, rows, (B, T)).to(DEV)
     plan = OccurrencePlan([idx.view(-1)], [rows])
+    assert plan.direct == [False]                # 409600 occurrences: the sorted path
     g1 = torch.randn(B * T, D, generator=gen).to(DEV)
     g2 = torch.randn(B * T, D, generator=gen).to(DEV)
 

@@ -26,7 +26,7 @@ def _u32(t):
 def test_plan_is_the_stable_order(sizes, rows):
     gen = torch.Generator().manual_seed(1)
     cols = [torch.randint(0, r, (n,), generator=gen, dtype=torch.int64) for n, r in zip(sizes, rows)]
-    plan = OccurrencePlan([c.to(DEV) for c in cols], rows)
+    plan = OccurrencePlan([c.to(DEV) for c in cols], rows, direct=False)
     torch.cuda.synchronize()
     keys, perm = X.stable_occurrence_order([c.numpy() for c in cols], rows)
     n = sum(sizes)
@@ -37,21 +37,34 @@ def test_plan_is_the_stable_order(sizes, rows):
 
 def test_plan_flags_out_of_range_index():
     idx = torch.tensor([0, 5, 2], dtype=torch.int64, device=DEV)
-    OccurrencePlan([idx], [4])
+    OccurrencePlan([idx], [4], direct=False)
     with pytest.raises(IndexError):
         rank_b200.check_index_errors()
     rank_b200.check_index_errors()    # the flag is cleared by the raise
+    # the one-launch reduction reports it too (and counts the occurrence as row 0, like the forward)
+    g = torch.ones(3, 2, device=DEV)
+    (dw,) = OccurrencePlan([idx], [4]).reduce_to_dense([GradSource(g, 0, 2, 2, 4, 0)])
+    assert dw.cpu().tolist() == [[2.0, 2.0], [0.0, 0.0], [1.0, 1.0], [0.0, 0.0]]
+    with pytest.raises(IndexError):
+        rank_b200.check_index_errors()
 
 
+@pytest.mark.parametrize("direct", [True, False], ids=["direct", "sorted"])
 @pytest.mark.parametrize("n,rows,dim", [(1, 1, 1), (100, 3, 2), (5000, 3, 16), (8192, 351, 4),
-                                         (8192, 19627, 16), (3000, 40, 32), (777, 11, 5),
+                                         (8192, 19627, 16), (3000, 40, 32), (777, 11, 5), (8192, 1, 4),
+                                         (8192, 257, 1), (33, 256, 8), (8191, 106445, 16),
                                          (65536, 106445, 1)])
-def test_segment_reduce_matches_sequential_sum(n, rows, dim):
+def test_segment_reduce_matches_sequential_sum(n, rows, dim, direct):
+    """Both reductions — the one-launch output-partitioned kernel for per-sample columns (n <= 8192) and
+    the sorted segment reduction — against the sequential CPU sum."""
     gen = torch.Generator().manual_seed(n + dim)
     idx = torch.randint(0, rows, (n,), generator=gen, dtype=torch.int64)
+    if n >= 1000:
+        idx[: n // 3] = idx[0]                      # one hot row: a run longer than a warp's share
     ld = dim + 3
     g = torch.randn(n, ld, generator=gen)
-    plan = OccurrencePlan([idx.to(DEV)], [rows])
+    plan = OccurrencePlan([idx.to(DEV)], [rows], direct=direct)
+    assert plan.direct == [direct and n <= 8192]
     gd = g.to(DEV)
     (dw,) = plan.reduce_to_dense([GradSource(gd, 1, ld, dim, rows, 0)])
     want = X.dense_embedding_grad(idx.numpy(), g[:, 1:1 + dim].numpy(), rows)
@@ -62,10 +75,11 @@ def test_segment_reduce_matches_sequential_sum(n, rows, dim):
     assert not got[untouched].any()
 
 
-def test_segment_reduce_is_deterministic_and_shares_a_plan():
+@pytest.mark.parametrize("direct", [True, False], ids=["direct", "sorted"])
+def test_segment_reduce_is_deterministic_and_shares_a_plan(direct):
     gen = torch.Generator().manual_seed(5)
     idx = [torch.randint(0, r, (4096,), generator=gen, dtype=torch.int64).to(DEV) for r in (3, 1000)]
-    plan = OccurrencePlan(idx, [3, 1000])
+    plan = OccurrencePlan(idx, [3, 1000], direct=direct)
     g16 = torch.randn(4096, 32, generator=gen).to(DEV)
     g1 = torch.randn(4096, 1, generator=gen).to(DEV)
     src = [GradSource(g16, 0, 32, 16, 3, 0), GradSource(g16, 16, 32, 16, 1000, 1),
@@ -76,6 +90,30 @@ def test_segment_reduce_is_deterministic_and_shares_a_plan():
         assert torch.equal(x, y)
     want = X.dense_embedding_grad(idx[1].cpu().numpy(), g16[:, 16:].cpu().numpy(), 1000)
     assert np.allclose(a[1].cpu().numpy(), want, rtol=1e-5, atol=1e-5)
+    want1 = X.dense_embedding_grad(idx[0].cpu().numpy(), g1.cpu().numpy(), 3)
+    assert np.allclose(a[2].cpu().numpy(), want1, rtol=1e-5, atol=1e-4)
+
+
+def test_mixed_direct_and_sorted_fields_in_one_plan():
+    """A per-sample column (direct) and a padded history (sorted, dead positions dropped) in one plan,
+    sources given in an order that interleaves the two kinds."""
+    from rank_b200 import _lib
+    gen = torch.Generator().manual_seed(12)
+    B, T, rows = 700, 9, 500
+    cat = torch.randint(0, 40, (B,), generator=gen, dtype=torch.int64)
+    hist = torch.randint(0, rows, (B, T), generator=gen, dtype=torch.int64)
+    length = torch.randint(0, T + 1, (B,), generator=gen, dtype=torch.int64)
+    live = torch.arange(T).expand(B, T) < length.unsqueeze(1)
+    plan = OccurrencePlan([cat.to(DEV), hist.view(-1).to(DEV)], [40, rows], seq_len=[None, length.to(DEV)],
+                          live_mode=[_lib.LIVE_ALL, _lib.LIVE_PREFIX])
+    assert plan.direct == [True, False]
+    g_cat = torch.randn(B, 4, generator=gen)
+    g_hist = torch.randn(B * T, 16, generator=gen) * live.view(-1, 1)
+    d_hist, d_cat = plan.reduce_to_dense([GradSource(g_hist.to(DEV), 0, 16, 16, rows, 1),
+                                          GradSource(g_cat.to(DEV), 0, 4, 4, 40, 0)])
+    assert np.allclose(d_cat.cpu().numpy(), X.dense_embedding_grad(cat.numpy(), g_cat.numpy(), 40), rtol=1e-5, atol=1e-5)
+    assert np.allclose(d_hist.cpu().numpy(), X.dense_embedding_grad(hist.view(-1).numpy(), g_hist.numpy(), rows),
+                       rtol=1e-5, atol=1e-5)
 
 
 @pytest.mark.parametrize("dims,n_dense", [([16, 2, 4, 4, 4, 4], 16), ([16] * 6, 0), ([32] * 10, 16),
