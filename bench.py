@@ -456,6 +456,7 @@ class Stepper:
         from rank_b200.staging import PackedBatch
         self.packed = PackedBatch.like(example.host_views, example.device)   # fixed addresses: graph inputs
         self.static = self.packed.device_views
+        self.packed.dev.copy_(example.dev)            # the warm-up steps below run on a real batch
         self.has_ephemeral = hasattr(model, "draw_ephemeral")
         self.graph = None
         self.grads = None
@@ -853,7 +854,10 @@ def run_ours(args, wl):
                 }
             except Exception as exc:      # one workload failing must not lose the line
                 others[k] = {"error": f"{type(exc).__name__}: {exc}"[:300]}
-                torch.cuda.synchronize()
+                try:
+                    torch.cuda.synchronize()
+                except Exception:         # a sticky device error: nothing more can run in this process
+                    break
         line["other_workloads"] = others
     if rank == 0:
         emit(line)
