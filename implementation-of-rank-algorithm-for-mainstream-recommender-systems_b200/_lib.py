@@ -19,7 +19,7 @@ RK_MAX_FIELDS = 24
 RK_MAX_TABLES = 32
 RK_MAX_LAYERS = 8
 RK_DIRECT_MAX_N = 8192
-ABI_VERSION = 1
+ABI_VERSION = 2
 
 
 class RkField(C.Structure):
@@ -50,7 +50,10 @@ class RkDinArgs(C.Structure):
 class RkBstBlock(C.Structure):
     _fields_ = [(n, C.c_void_p) for n in (
         "pos", "wq", "bq", "wk", "bk", "wv", "bv", "wo", "bo", "ln1_g", "ln1_b", "w1", "b1", "w2", "b2",
-        "ln2_g", "ln2_b")]
+        "ln2_g", "ln2_b", "rng")] + [("dropout_p", C.c_float), ("precision", C.c_int32)]
+
+
+BST_FP32, BST_BF16_TENSOR = 0, 1
 
 
 LIVE_ALL, LIVE_PREFIX, LIVE_PREFIX_OR_EMPTY = 0, 1, 2
@@ -102,7 +105,7 @@ PROTOTYPES = {
     "rk_resunits_fwd": (_I, [_P, _I, _P, _I, _P, _I, _I, _L, _P, _P, _P]),
     "rk_resunits_bwd": (_I, [_P, _P, _I, _I, _I, _L, _P, _P, _P]),
     "rk_bst_grad_floats": (_I, [_I]),
-    "rk_bst_bwd_ctas": (_I, [_L, _I]),
+    "rk_bst_bwd_ctas": (_I, [_L, _I, _I]),
     "rk_bst_block_fwd": (_I, [_P, _I, _P, _P, _L, _P, _P, _L, _I, _P, _P, _I, _I, _P, _P]),
     "rk_bst_block_bwd": (_I, [_P, _I, _P, _P, _L, _P, _P, _L, _I, _P, _P, _I, _I, _P, _P, _P, _I, _P, _P]),
     "rk_din_mlp_floats": (_I, [_I]),

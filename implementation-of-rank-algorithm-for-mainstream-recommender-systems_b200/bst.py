@@ -9,9 +9,17 @@ block is one persistent kernel (in-kernel recompute, no saved [B,heads,T,T] tens
 fixed-order reduction of the per-CTA partial gradients of the block's registered weights.  The
 DNN stays torch.
 
-Dropout inside the block (BST/bst.py:57,62,86,90) draws from the CPU/CUDA generators in the
-reference and is not reproduced by the kernel: blocks run with `dropout = 0` or in eval mode;
-training with dropout > 0 raises instead of silently changing the model.
+Dropout inside the block (BST/bst.py:57,62,86,90): in training mode with dropout > 0 the kernels
+apply inverted dropout at the reference's three sites (w_o output, inside the FFN, FFN output)
+with keep-bits from an in-kernel counter-based generator (Philox4x32-10 keyed by a per-block seed
+drawn from torch's CPU generator, an offset advanced on the device once per forward, the row and
+the site); the backward regenerates the same bits, nothing is stored.  The reference's own draws
+(torch generators) cannot be replayed, so parity with the reference is defined at dropout 0 /
+eval mode, and the dropout path is checked against the oracle run with the very same masks.
+
+`set_block_precision("bf16")` runs the block's projections, FFN and weight gradients on tcgen05
+tensor cores (bf16 operands, fp32 accumulation in TMEM; the north star's 2e-2 bar); the default
+"fp32" is the SIMT block held to 1e-5.
 """
 from __future__ import annotations
 
@@ -33,6 +41,20 @@ _PARAM_ORDER = ("position_embedding.weight", "w_q.weight", "w_q.bias", "w_k.weig
                 "ffn.3.weight", "ffn.3.bias", "norm2.weight", "norm2.bias")
 _FIELD_ORDER = ("pos", "wq", "bq", "wk", "bk", "wv", "bv", "wo", "bo", "ln1_g", "ln1_b", "w1", "b1", "w2", "b2",
                 "ln2_g", "ln2_b")
+_PRECISION = "fp32"
+
+
+def set_block_precision(precision: str) -> None:
+    """"fp32" (default): fp32 SIMT block, 1e-5 parity.  "bf16": the projections / FFN / weight
+    gradients on tcgen05 tensor cores, tested at the north star's 2e-2 bar."""
+    global _PRECISION
+    if precision not in ("fp32", "bf16"):
+        raise ValueError(f"precision must be 'fp32' or 'bf16', got {precision!r}")
+    _PRECISION = precision
+
+
+def block_precision() -> str:
+    return _PRECISION
 
 
 def load_vocabulary(vocab_file):
@@ -48,13 +70,19 @@ def leakyrelu(x, leak=0.01):
     return 0.5 * (1 + leak) * x + 0.5 * (1 - leak) * torch.abs(x)
 
 
-def _block_struct(params):
+def _block_struct(params, dropout_p, rng, precision):
     blk = _lib.RkBstBlock()
     keep = []
     for name, t in zip(_FIELD_ORDER, params):
         t = _lib.require_cuda(t, name, torch.float32)
         keep.append(t)
         setattr(blk, name, t.data_ptr())
+    blk.dropout_p = float(dropout_p)
+    blk.precision = _lib.BST_BF16_TENSOR if precision == "bf16" else _lib.BST_FP32
+    if rng is not None:
+        rng = _lib.require_cuda(rng, "dropout rng state", torch.int64)
+        keep.append(rng)
+        blk.rng = rng.data_ptr()
     return blk, keep
 
 
@@ -65,7 +93,7 @@ class _BstBlock(torch.autograd.Function):
     @staticmethod
     def forward(ctx, cfg, seq_len, idx, source, *params):
         lib = _lib.load()
-        nhead, pool = cfg
+        nhead, pool, dropout_p, rng, precision = cfg
         seq_len = _lib.require_cuda(seq_len, "seq_length", torch.int64)
         source = _lib.require_cuda(source, "sequence input", torch.float32)
         from_table = idx is not None
@@ -78,7 +106,7 @@ class _BstBlock(torch.autograd.Function):
             raise RuntimeError(f"shape '[{B}, {T}, {nhead}, -1]' is invalid for d_model {source.shape[-1]}")
         if params[0].shape[0] < T:
             raise IndexError("index out of range in self")      # position_embedding(arange(T))
-        blk, keep = _block_struct(params)
+        blk, keep = _block_struct(params, dropout_p, rng, precision)
         dev = source.device
         y = pooled = None
         if pool is None:
@@ -109,7 +137,7 @@ class _BstBlock(torch.autograd.Function):
         n_in = 4 + len(_PARAM_ORDER)
         if g is None:
             return (None,) * n_in
-        nhead, pool = ctx.cfg
+        nhead, pool = ctx.cfg[:2]
         B, T = ctx.shape
         seq_len, idx, source = ctx.saved_tensors
         dev = source.device
@@ -117,7 +145,7 @@ class _BstBlock(torch.autograd.Function):
         g_x = torch.empty(B, T, D_MODEL, dtype=torch.float32, device=dev)
         n_par = lib.rk_bst_grad_floats(T)
         g_par = torch.empty(n_par, dtype=torch.float32, device=dev)
-        n_ctas = lib.rk_bst_bwd_ctas(B, T)
+        n_ctas = lib.rk_bst_bwd_ctas(B, T, ctx.blk.precision)
         partials = torch.empty(n_ctas * n_par, dtype=torch.float32, device=dev)
         rc = lib.rk_bst_block_bwd(C.byref(ctx.blk), nhead, source.data_ptr() if ctx.from_table else None,
                                   _lib.ptr(idx), int(source.shape[0]) if ctx.from_table else 0,
@@ -169,18 +197,32 @@ class BSTTransformer(nn.Module):
         named = dict(self.named_parameters())
         return [named[n] for n in _PARAM_ORDER]
 
-    def _check_dropout(self):
-        if self.training and self.dropout.p > 0:
-            raise NotImplementedError(
-                "the fused BST block does not reproduce the reference's dropout draws: construct the "
-                "model with dropout_rate=0.0 (the parity configuration) or call .eval()")
-        if self.d_model != D_MODEL:
-            raise NotImplementedError(f"the fused BST block is built for d_model = {D_MODEL}")
+    def _dropout_state(self, device):
+        """(p, rng) of this forward: rng = a snapshot [seed, offset] of the block's device-side
+        generator state, whose offset is then advanced in-stream (capturable in a CUDA graph: every
+        replay draws new masks).  The seed comes from torch's CPU generator the first time, so
+        torch.manual_seed makes the masks reproducible."""
+        p = float(self.dropout.p)
+        if not self.training or p <= 0.0:
+            return 0.0, None
+        if p >= 1.0:
+            raise NotImplementedError("dropout = 1 zeroes the block; use the reference module for that")
+        state = getattr(self, "_rng_state", None)
+        if state is None or state.device != device:
+            seed = int(torch.randint(0, 2 ** 62, (1,)).item())
+            state = torch.tensor([seed, 0], dtype=torch.int64, device=device)
+            self._rng_state = state
+        snap = state.clone()
+        state[1:2] += 1
+        self._last_rng = snap          # what this forward's masks were drawn from (tests read it)
+        return p, snap
 
     def run(self, source, seq_len, idx=None, pool=None):
         """Fused path used by BSTModel: rows from `source[idx]` (first block) or `source[B,T,16]`."""
-        self._check_dropout()
-        return _BstBlock.apply((self.nhead, pool), seq_len, idx, source, *self._params())
+        if self.d_model != D_MODEL:
+            raise NotImplementedError(f"the fused BST block is built for d_model = {D_MODEL}")
+        p, rng = self._dropout_state(source.device)
+        return _BstBlock.apply((self.nhead, pool, p, rng, _PRECISION), seq_len, idx, source, *self._params())
 
     def forward(self, queries, keys, values, key_padding_mask=None):
         """Self-attention form of the reference signature: queries, keys and values must be the

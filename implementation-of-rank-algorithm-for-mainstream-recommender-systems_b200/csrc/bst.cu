@@ -14,27 +14,14 @@
 #include <string.h>
 #include "common.cuh"
 #include "prof.cuh"
+#include "bst.cuh"
 
 namespace rk {
 
 constexpr int kBstThreads = 128;
-constexpr int kBstRows    = 128;   // (sample, position) rows per CTA tile
-constexpr int kBstD       = 16;
 constexpr int kBstLd      = 20;    // padded row stride of the row-major shared arrays
-constexpr float kLnEps    = 1e-5f;
 
-struct BstParams {
-    const float* w[6];      // wq wk wv wo w1 w2, each [16][16] as registered (out, in)
-    const float* vec[10];   // bq bk bv bo ln1_g ln1_b b1 b2 ln2_g ln2_b
-    const float* pos;       // [max_len][16]
-    const float* table;  const int64_t* idx;  int64_t table_rows;   // x = table[idx]  (first block)
-    const float* x_in;                                              // or x = x_in[B,T,16]
-    const int64_t* seq_len;
-    int64_t B, n_tiles;
-    int32_t T, S, pool_mean;
-};
-enum { VBQ = 0, VBK, VBV, VBO, VG1, VBE1, VB1, VB2, VG2, VBE2 };
-enum { MQ = 0, MK, MV, MO, M1, M2 };
+
 
 // out[n] += sum_i in[i] * M[i*16 + n]   (M k-major -> W.in ; M as registered -> W^T.in)
 __device__ __forceinline__ void matvec16(const float* __restrict__ M, const float (&in)[16], float (&out)[16]) {
@@ -91,6 +78,31 @@ __device__ __forceinline__ void layer_norm16_bwd(const float (&dy)[16], const fl
     a *= (1.0f / 16.0f); b *= (1.0f / 16.0f);
 #pragma unroll
     for (int i = 0; i < 16; ++i) dz[i] = rstd * (dy[i] * g[i] - a - zh[i] * b);
+}
+
+// The three dropout sites of the block (BST/bst.py:86 w_o output, :62 inside the FFN, :90 FFN output):
+// 16 keep-bits each for this thread's row, regenerated identically by the backward.
+struct BstDrop {
+    uint32_t k[3];
+    float scale;
+    bool active;
+};
+__device__ __forceinline__ BstDrop bst_drop_masks(const BstParams& p, int64_t row) {
+    BstDrop d;
+    d.active = p.drop_thr != 0;
+    d.scale = p.drop_scale;
+    d.k[0] = d.k[1] = d.k[2] = 0xffffu;
+    if (d.active) {
+        const uint64_t seed = p.rng[0], offset = p.rng[1];
+#pragma unroll
+        for (int s = 0; s < 3; ++s) d.k[s] = dropout_keep16(seed, offset, (uint64_t)row, s, p.drop_thr);
+    }
+    return d;
+}
+__device__ __forceinline__ void bst_drop(const BstDrop& d, int site, float (&v)[16]) {
+    if (!d.active) return;
+#pragma unroll
+    for (int i = 0; i < 16; ++i) v[i] = ((d.k[site] >> i) & 1u) ? v[i] * d.scale : 0.f;
 }
 
 struct BstSmem {
@@ -241,9 +253,11 @@ bst_fwd_kernel(const __grid_constant__ BstParams p, float* __restrict__ y_out, f
         if (on) {
             float ctx[16], mh[H], lh[H];
             bst_attend<H>(q, sm.ks, sm.vs, s * T, L, ctx, mh, lh);
+            const BstDrop drop = bst_drop_masks(p, b * T + t);
             float z[16], zh[16], o1[16], hp[16], f[16], y[16];
             set_vec(z, sm.vec + VBO * 16);
             matvec16(sm.wt + MO * 256, ctx, z);
+            bst_drop(drop, 0, z);
 #pragma unroll
             for (int i = 0; i < 16; ++i) z[i] += qk[i];
             layer_norm16(z, sm.vec + VG1 * 16, sm.vec + VBE1 * 16, zh, o1);
@@ -251,8 +265,10 @@ bst_fwd_kernel(const __grid_constant__ BstParams p, float* __restrict__ y_out, f
             matvec16(sm.wt + M1 * 256, o1, hp);
 #pragma unroll
             for (int i = 0; i < 16; ++i) hp[i] = hp[i] > 0.f ? hp[i] : 0.01f * hp[i];
+            bst_drop(drop, 1, hp);
             set_vec(f, sm.vec + VB2 * 16);
             matvec16(sm.wt + M2 * 256, hp, f);
+            bst_drop(drop, 2, f);
 #pragma unroll
             for (int i = 0; i < 16; ++i) z[i] = o1[i] + f[i];
             layer_norm16(z, sm.vec + VG2 * 16, sm.vec + VBE2 * 16, zh, y);
@@ -334,6 +350,8 @@ bst_bwd_kernel(const __grid_constant__ BstParams p, const float* __restrict__ g_
         int L = 0;
         float zh1[16], zh2[16], act[16], rstd1 = 0.f, rstd2 = 0.f;
         unsigned hmask = 0;
+        BstDrop drop;
+        drop.active = false; drop.scale = 1.f; drop.k[0] = drop.k[1] = drop.k[2] = 0xffffu;
         float zero16[16];
 #pragma unroll
         for (int i = 0; i < 16; ++i) zero16[i] = 0.f;
@@ -367,9 +385,11 @@ bst_bwd_kernel(const __grid_constant__ BstParams p, const float* __restrict__ g_
 #pragma unroll
             for (int h = 0; h < H; ++h) { sm.mrow[r * H + h] = mh[h]; sm.lrow[r * H + h] = 1.0f / lh[h]; }   // lrow holds 1 / sum
             store_row(sm.cs + r * kBstLd, ctx);
+            drop = bst_drop_masks(p, b * T + t);
             float z[16], o1[16], hp[16], f[16], y[16];
             set_vec(z, sm.vec + VBO * 16);
             matvec16(sm.wt + MO * 256, ctx, z);
+            bst_drop(drop, 0, z);
 #pragma unroll
             for (int i = 0; i < 16; ++i) z[i] += qk[i];
             rstd1 = layer_norm16(z, sm.vec + VG1 * 16, sm.vec + VBE1 * 16, zh1, o1);
@@ -380,8 +400,10 @@ bst_bwd_kernel(const __grid_constant__ BstParams p, const float* __restrict__ g_
                 if (hp[i] > 0.f) hmask |= 1u << i;
                 act[i] = hp[i] > 0.f ? hp[i] : 0.01f * hp[i];
             }
+            bst_drop(drop, 1, act);
             set_vec(f, sm.vec + VB2 * 16);
             matvec16(sm.wt + M2 * 256, act, f);
+            bst_drop(drop, 2, f);
 #pragma unroll
             for (int i = 0; i < 16; ++i) z[i] = o1[i] + f[i];
             rstd2 = layer_norm16(z, sm.vec + VG2 * 16, sm.vec + VBE2 * 16, zh2, y);
@@ -416,9 +438,13 @@ bst_bwd_kernel(const __grid_constant__ BstParams p, const float* __restrict__ g_
 #pragma unroll
             for (int i = 0; i < 16; ++i) { dz[i] = 0.f; act[i] = 0.f; }
         }
-        // ---- C. FFN backward
+        // ---- C. FFN backward  (df = gradient of the FFN output before its dropout)
         PROF(3);
-        store_row(sm.gs + r * kBstLd, dz);
+        float df[16];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) df[i] = dz[i];
+        bst_drop(drop, 2, df);
+        store_row(sm.gs + r * kBstLd, df);
         store_row(sm.as + r * kBstLd, act);
         __syncthreads();
         bst_outer(sm.gs, sm.as, rows, macc[M2]);
@@ -428,7 +454,8 @@ bst_bwd_kernel(const __grid_constant__ BstParams p, const float* __restrict__ g_
 #pragma unroll
         for (int i = 0; i < 16; ++i) { dh[i] = 0.f; o1[i] = 0.f; }
         if (on) {
-            matvec16(sm.w + M2 * 256, dz, dh);                       // W2^T dz
+            matvec16(sm.w + M2 * 256, df, dh);                       // W2^T df
+            bst_drop(drop, 1, dh);
 #pragma unroll
             for (int i = 0; i < 16; ++i) {
                 dh[i] *= ((hmask >> i) & 1u) ? 1.0f : 0.01f;
@@ -460,12 +487,16 @@ bst_bwd_kernel(const __grid_constant__ BstParams p, const float* __restrict__ g_
 #pragma unroll
         for (int i = 0; i < 16; ++i) { dz1[i] = 0.f; dctx[i] = 0.f; }
         if (on) layer_norm16_bwd(do1, sm.vec + VG1 * 16, zh1, rstd1, dz1);
-        store_row(sm.gs + r * kBstLd, dz1);
+        float dwo[16];                                               // gradient of w_o(ctx) before its dropout
+#pragma unroll
+        for (int i = 0; i < 16; ++i) dwo[i] = dz1[i];
+        bst_drop(drop, 0, dwo);
+        store_row(sm.gs + r * kBstLd, dwo);
         __syncthreads();
-        bst_outer(sm.gs, sm.cs, rows, macc[MO]);                 // d w_o = dz1 (x) ctx
+        bst_outer(sm.gs, sm.cs, rows, macc[MO]);                 // d w_o = dwo (x) ctx
         bst_colsum(sm.gs, nullptr, rows, sm.vsum[4 * 32 + (r & 31)]);               // d b_o
         if (on) {
-            matvec16(sm.w + MO * 256, dz1, dctx);                    // W_o^T dz1
+            matvec16(sm.w + MO * 256, dwo, dctx);                    // W_o^T dwo
             float ctx[16];
             load_row(sm.cs + r * kBstLd, ctx);
 #pragma unroll
@@ -636,6 +667,11 @@ static int bst_fill(const rk_bst_block_t* blk, const float* table, const int64_t
     p->table = table; p->idx = idx; p->table_rows = table_rows; p->x_in = x_in;
     p->seq_len = seq_len;
     p->B = B; p->T = T; p->S = kBstRows / T; p->pool_mean = pool_mean;
+    RK_CHECK_ARG(blk->dropout_p >= 0.f && blk->dropout_p < 1.f, "bst: dropout_p %g outside [0,1)", (double)blk->dropout_p);
+    p->drop_thr = (uint32_t)lrintf(blk->dropout_p * 65536.f);
+    p->drop_scale = 1.0f / (1.0f - blk->dropout_p);
+    p->rng = (const unsigned long long*)blk->rng;
+    RK_CHECK_ARG(p->drop_thr == 0 || p->rng, "bst: dropout_p > 0 needs rng (device [seed, offset])");
     p->n_tiles = ceil_div(B, p->S);
     return 0;
 }
@@ -669,8 +705,9 @@ extern "C" {
 
 int rk_bst_grad_floats(int T) { return T * 16 + 6 * 256 + 160; }
 
-int rk_bst_bwd_ctas(int64_t B, int T) {
+int rk_bst_bwd_ctas(int64_t B, int T, int precision) {
     if (T < 1 || T > rk::kBstRows || B <= 0) return 1;
+    if (precision == RK_BST_BF16_TENSOR) return rk::bst_tc_bwd_ctas(B, T);
     const int64_t tiles = rk::ceil_div(B, rk::kBstRows / T);
     const int64_t cap = (int64_t)rk::sm_count() * 2;
     return (int)(tiles < cap ? tiles : cap);
@@ -687,6 +724,8 @@ int rk_bst_block_fwd(const rk_bst_block_t* blk, int nhead, const float* table, c
     RK_CHECK_ARG(y_out || pool_out, "bst_fwd: no output requested");
     if (B == 0) return 0;
     cudaStream_t s = (cudaStream_t)stream_;
+    if (blk->precision == RK_BST_BF16_TENSOR) return bst_tc_fwd(p, nhead, y_out, pool_out, pool_ld, err_flag, s);
+    RK_CHECK_ARG(blk->precision == RK_BST_FP32, "bst_fwd: unknown precision %d", blk->precision);
     switch (nhead) {
         case 1:  return bst_launch_fwd<1>(p, y_out, pool_out, pool_ld, err_flag, s);
         case 2:  return bst_launch_fwd<2>(p, y_out, pool_out, pool_ld, err_flag, s);
@@ -707,9 +746,12 @@ int rk_bst_block_bwd(const rk_bst_block_t* blk, int nhead, const float* table, c
     memset(&p, 0, sizeof(p));
     if (int rc = bst_fill(blk, table, idx, table_rows, x_in, seq_len, B, T, pool_mean, &p)) return rc;
     RK_CHECK_ARG((g_y || g_pool) && g_x && g_params && partials, "bst_bwd: NULL pointer");
-    RK_CHECK_ARG(n_ctas == rk_bst_bwd_ctas(B, T), "bst_bwd: n_ctas %d != rk_bst_bwd_ctas", n_ctas);
+    RK_CHECK_ARG(n_ctas == rk_bst_bwd_ctas(B, T, blk->precision), "bst_bwd: n_ctas %d != rk_bst_bwd_ctas", n_ctas);
     if (B == 0) return 0;
     cudaStream_t s = (cudaStream_t)stream_;
+    if (blk->precision == RK_BST_BF16_TENSOR)
+        return bst_tc_bwd(p, nhead, g_y, g_pool, g_pool_ld, g_x, g_params, partials, n_ctas, err_flag, s);
+    RK_CHECK_ARG(blk->precision == RK_BST_FP32, "bst_bwd: unknown precision %d", blk->precision);
     int rc = -1;
     switch (nhead) {
         case 1:  rc = bst_launch_bwd<1>(p, g_y, g_pool, g_pool_ld, g_x, partials, n_ctas, err_flag, s); break;

@@ -113,6 +113,42 @@ __device__ __forceinline__ void vec_zero(Vec<N>& a) {
     for (int i = 0; i < N; ++i) a.v[i] = 0.f;
 }
 
+// ---- counter-based random bits (Philox4x32-10) for in-kernel dropout masks ------------------
+// The reference draws dropout masks from torch's CPU/CUDA generators (BST/bst.py:57,62,86,90);
+// those draws cannot be replayed in a fused kernel, so masks are a pure function of
+// (seed, offset, row): the backward regenerates exactly the bits the forward used and nothing
+// is stored.  rng[0] = seed, rng[1] = offset (advanced once per forward by the caller).
+__device__ __forceinline__ uint4 philox4x32_10(uint4 c, uint2 k) {
+#pragma unroll
+    for (int r = 0; r < 10; ++r) {
+        const uint32_t hi0 = __umulhi(0xD2511F53u, c.x), lo0 = 0xD2511F53u * c.x;
+        const uint32_t hi1 = __umulhi(0xCD9E8D57u, c.z), lo1 = 0xCD9E8D57u * c.z;
+        c = make_uint4(hi1 ^ c.y ^ k.x, lo1, hi0 ^ c.w ^ k.y, lo0);
+        k.x += 0x9E3779B9u;
+        k.y += 0xBB67AE85u;
+    }
+    return c;
+}
+// 16 keep-bits (bit i set = element i kept) for dropout site `site` of `row`: two Philox calls,
+// eight 16-bit uniforms each; an element is dropped when its uniform is below thr = round(p * 65536).
+__device__ __forceinline__ uint32_t dropout_keep16(uint64_t seed, uint64_t offset, uint64_t row, int site,
+                                                   uint32_t thr) {
+    uint32_t bits = 0;
+#pragma unroll
+    for (int half = 0; half < 2; ++half) {
+        const uint4 r = philox4x32_10(make_uint4((uint32_t)row, (uint32_t)(row >> 32), (uint32_t)(2 * site + half),
+                                                 (uint32_t)offset),
+                                      make_uint2((uint32_t)seed, (uint32_t)(seed >> 32) ^ (uint32_t)(offset >> 32)));
+        const uint32_t w[4] = {r.x, r.y, r.z, r.w};
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            bits |= ((w[j] & 0xffffu) >= thr ? 1u : 0u) << (8 * half + 2 * j);
+            bits |= ((w[j] >> 16) >= thr ? 1u : 0u) << (8 * half + 2 * j + 1);
+        }
+    }
+    return bits;
+}
+
 // Clamp an index into [0, rows); flag the batch as bad if it was outside (reference: IndexError).
 __device__ __forceinline__ int64_t checked_row(int64_t i, int64_t rows, int32_t* err_flag) {
     if ((uint64_t)i >= (uint64_t)rows) {

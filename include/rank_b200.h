@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define RK_ABI_VERSION 1
+#define RK_ABI_VERSION 2
 #define RK_MAX_FIELDS 24
 #define RK_MAX_TABLES 32
 #define RK_MAX_LAYERS 8
@@ -323,18 +323,28 @@ int rk_resunits_bwd(const float* nets, const float* units, int n_units, int H, i
  * embedding) or from x_in[B,T,16] (a previous block's output).  Keys t >= seq_len[b] are masked
  * with -inf (a length-0 sample yields NaN, as in the reference).  y_out[B,T,16] and/or the
  * pooled row sum_t y[b,t,:] (divided by seq_len[b] when pool_mean) written to
- * pool_out[b*pool_ld + 0..15] are produced.  Dropout inside the block is not applied (p = 0 or
- * eval mode only). */
+ * pool_out[b*pool_ld + 0..15] are produced.
+ * Dropout (BST/bst.py:86 on w_o's output, :62 inside the FFN, :90 on the FFN output): dropout_p > 0
+ * applies inverted dropout at the three sites with keep-bits that are a pure function of
+ * (rng[0] = seed, rng[1] = offset, row b*T+t, site) — Philox4x32-10, 16-bit uniforms, an element is
+ * dropped when its uniform < round(p*65536).  The backward regenerates the same bits from the same
+ * rng values; the caller advances the offset between forwards.  The reference's own draws
+ * (torch generators) cannot be replayed, so parity is defined at dropout_p = 0. */
 typedef struct rk_bst_block {
     const float* pos;                                  /* position_embedding.weight [max_len,16] */
     const float *wq, *bq, *wk, *bk, *wv, *bv, *wo, *bo; /* w_q/w_k/w_v/w_o .weight [16,16], .bias [16] */
     const float *ln1_g, *ln1_b;                        /* norm1 */
     const float *w1, *b1, *w2, *b2;                    /* ffn.0, ffn.3 */
     const float *ln2_g, *ln2_b;                        /* norm2 */
+    const uint64_t* rng;                               /* device [seed, offset]; may be NULL when dropout_p == 0 */
+    float dropout_p;                                   /* 0 in eval mode */
+    int32_t precision;                                 /* RK_BST_FP32: fp32 SIMT block (1e-5 parity); RK_BST_BF16_TENSOR: projections / FFN / weight gradients on tcgen05 (2e-2 bar) */
 } rk_bst_block_t;
+#define RK_BST_FP32 0
+#define RK_BST_BF16_TENSOR 1
 
 int rk_bst_grad_floats(int T);            /* T*16 + 6*256 + 10*16 */
-int rk_bst_bwd_ctas(int64_t B, int T);
+int rk_bst_bwd_ctas(int64_t B, int T, int precision);
 int rk_bst_block_fwd(const rk_bst_block_t* blk, int nhead, const float* table, const int64_t* idx,
                      int64_t table_rows, const float* x_in, const int64_t* seq_len, int64_t B, int T,
                      float* y_out, float* pool_out, int pool_ld, int pool_mean, int32_t* err_flag,
@@ -342,7 +352,7 @@ int rk_bst_block_fwd(const rk_bst_block_t* blk, int nhead, const float* table, c
 /* g_y[B,T,16] and/or g_pool (row b at g_pool + b*g_pool_ld) -> g_x[B,T,16] and the gradients of the
  * block's registered tensors in g_params, laid out
  *   [pos T*16][wq 256][bq 16][wk][bk][wv][bv][wo][bo][ln1_g][ln1_b][w1][b1][w2][b2][ln2_g][ln2_b];
- * partials: scratch of rk_bst_bwd_ctas(B,T) * rk_bst_grad_floats(T) floats. */
+ * partials: scratch of rk_bst_bwd_ctas(B,T,blk->precision) * rk_bst_grad_floats(T) floats. */
 int rk_bst_block_bwd(const rk_bst_block_t* blk, int nhead, const float* table, const int64_t* idx,
                      int64_t table_rows, const float* x_in, const int64_t* seq_len, int64_t B, int T,
                      const float* g_y, const float* g_pool, int g_pool_ld, int pool_mean, float* g_x,

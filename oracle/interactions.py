@@ -156,13 +156,20 @@ def din_l2_term(l2_lambda, category_rows, target_row, attention_out):
 
 
 # --------------------------------------------------------------------------- BST
-def bst_transformer_block(x, pad_mask, p, nhead, dropout_p=0.0):
+def bst_transformer_block(x, pad_mask, p, nhead, dropout_p=0.0, keep=None):
     """BSTTransformer.forward (BST/bst.py:66-91) with queries = keys = values = x [B,T,d].
     `p` maps the block's state_dict names to tensors; pad_mask [B,T] is True on padded keys.
-    dropout_p must be 0 for a deterministic oracle."""
-    if dropout_p:
-        raise ValueError("the oracle is defined for dropout 0 only")
+    Dropout (BST/bst.py:57,62,86,90) is deterministic here: `keep` [3,B,T,d] holds the keep masks
+    of the three sites (w_o output :86, inside the FFN :62, FFN output :90) and dropout_p the rate;
+    nn.Dropout's arithmetic is x * keep / (1 - p).  keep=None requires dropout_p == 0."""
+    if dropout_p and keep is None:
+        raise ValueError("the oracle is deterministic: pass the keep masks for dropout_p > 0")
     B, T, d = x.shape
+
+    def drop(v, site):
+        if keep is None or not dropout_p:
+            return v
+        return v * keep[site].to(v.dtype) * (1.0 / (1.0 - dropout_p))
     pos = p["position_embedding.weight"][torch.arange(T, device=p["position_embedding.weight"].device)]                          # :68-69
     qk_in = x + pos                                                                # :70-71 (not values)
     q = F.linear(qk_in, p["w_q.weight"], p["w_q.bias"]).view(B, T, nhead, -1).transpose(1, 2)
@@ -172,11 +179,11 @@ def bst_transformer_block(x, pad_mask, p, nhead, dropout_p=0.0):
     scores = scores.masked_fill(pad_mask.unsqueeze(1).unsqueeze(2), float("-inf"))  # :79-80
     ctx = torch.matmul(torch.softmax(scores, dim=-1), v)                           # :82-83
     ctx = ctx.transpose(1, 2).contiguous().view(B, T, -1)                          # :84
-    o1 = F.layer_norm(qk_in + F.linear(ctx, p["w_o.weight"], p["w_o.bias"]), (d,),
+    o1 = F.layer_norm(qk_in + drop(F.linear(ctx, p["w_o.weight"], p["w_o.bias"]), 0), (d,),
                       p["norm1.weight"], p["norm1.bias"])                          # :86
-    ffn = F.linear(F.leaky_relu(F.linear(o1, p["ffn.0.weight"], p["ffn.0.bias"]), 0.01),
-                   p["ffn.3.weight"], p["ffn.3.bias"])                             # :59-64,88
-    return F.layer_norm(o1 + ffn, (d,), p["norm2.weight"], p["norm2.bias"])        # :90
+    hidden = drop(F.leaky_relu(F.linear(o1, p["ffn.0.weight"], p["ffn.0.bias"]), 0.01), 1)   # :59-62
+    ffn = F.linear(hidden, p["ffn.3.weight"], p["ffn.3.bias"])                     # :63,88
+    return F.layer_norm(o1 + drop(ffn, 2), (d,), p["norm2.weight"], p["norm2.bias"])          # :90
 
 
 def bst_sequence_feature(seq_rows, seq_length, blocks, nhead, pooling):

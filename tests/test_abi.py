@@ -35,6 +35,7 @@ def test_struct_layouts_match_header():
     assert ctypes.sizeof(_lib.RkField) == 32
     assert ctypes.sizeof(_lib.RkGradTable) == 32
     assert ctypes.sizeof(_lib.RkDirectTable) == 56       # rk_direct_table_t
+    assert ctypes.sizeof(_lib.RkBstBlock) == 18 * 8 + 8  # rk_bst_block_t
 
 
 def test_workspace_queries_need_no_gpu():

@@ -269,18 +269,69 @@ def test_bst_vs_oracle_wechat_sizes(wechat_vocab_dir, B, T, nhead, blocks, pool)
     compare(*_run_both(ours, ref, "BSTModel", synthetic.bst_batch(B, T)))
 
 
-def test_bst_rejects_training_dropout_and_bad_heads(wechat_vocab_dir):
+def test_bst_default_dropout_trains_and_bad_heads(wechat_vocab_dir):
+    """The reference's default (dropout_rate=0.1, BST/bst.py:164,417) trains: forward + backward run,
+    two forwards draw different masks, eval mode is deterministic."""
+    torch.manual_seed(5)
     m = rank_b200.BSTModel(wechat_vocab_dir, dropout_rate=0.1, max_seq_length=20).to(DEV)
-    batch = to_device(synthetic.bst_batch(32, 20), DEV)
-    with pytest.raises(NotImplementedError):
-        m(batch["dense"], batch["category"], batch["seq_feedid"], batch["seq_length"])
+    batch = to_device(synthetic.bst_batch(512, 20), DEV)
+    args = (batch["dense"], batch["category"], batch["seq_feedid"], batch["seq_length"])
+    m.train()
+    side_a, x_a = m.hot_path(*args)
+    side_b, x_b = m.hot_path(*args)
+    assert torch.equal(side_a, side_b) and not torch.equal(x_a, x_b)       # new masks every forward
+    p, _ = m(*args)
+    torch.nn.functional.binary_cross_entropy(p.squeeze(1), batch["label"]).backward()
+    for name, par in m.named_parameters():
+        assert par.grad is not None and torch.isfinite(par.grad).all(), name
     m.eval()
     with torch.no_grad():
-        p, _ = m(batch["dense"], batch["category"], batch["seq_feedid"], batch["seq_length"])
-    assert p.shape == (32, 1) and torch.isfinite(p).all()
+        p1, _ = m(*args)
+        p2, _ = m(*args)
+    assert p1.shape == (512, 1) and torch.isfinite(p1).all() and torch.equal(p1, p2)
     bad = rank_b200.BSTModel(wechat_vocab_dir, dropout_rate=0.0, nhead=3, max_seq_length=20).to(DEV)
     with pytest.raises(RuntimeError):      # the reference's view() raises for nhead 3 / 5 as well
-        bad(batch["dense"], batch["category"], batch["seq_feedid"], batch["seq_length"])
+        bad(*args)
+
+
+@pytest.mark.parametrize("p,B,T,H", [(0.1, 512, 20, 4), (0.5, 300, 50, 2), (0.25, 64, 128, 1), (0.1, 8192, 20, 4)])
+def test_bst_block_dropout_vs_oracle_with_the_same_masks(p, B, T, H):
+    """Training-mode dropout inside the block (BST/bst.py:57,62,86,90): the kernels' keep-bits are a
+    function of (seed, offset, row, site); the oracle block is run with exactly those masks
+    (oracle/philox.py) and outputs + every gradient must agree at the fp32 bar."""
+    from oracle import interactions as X
+    from oracle import philox
+    torch.manual_seed(3)
+    blk = rank_b200.BSTTransformer(16, H, T + 1, dropout=p).to(DEV).train()
+    gen = torch.Generator().manual_seed(11)
+    x = torch.randn(B, T, 16, generator=gen)
+    lens = torch.randint(1, T + 1, (B,), generator=gen)
+    pad = torch.arange(T).expand(B, T) >= lens.unsqueeze(1)
+    g = torch.randn(B, T, 16, generator=gen) / B
+    xa = x.to(DEV).requires_grad_()
+    y = blk(xa, xa, xa, key_padding_mask=pad.to(DEV))
+    seed, offset = (int(v) for v in blk._last_rng.tolist())
+    y.backward(g.to(DEV))
+    keep = torch.from_numpy(philox.bst_keep_masks(seed, offset, B * T, p).reshape(3, B, T, 16))
+    dropped = 1.0 - keep.float().mean().item()
+    assert abs(dropped - p) < 4.0 * (p * (1 - p) / keep.numel()) ** 0.5 + 1e-4, dropped
+    params = {k: v.detach().cpu().clone().requires_grad_() for k, v in blk.named_parameters()}
+    xr = x.clone().requires_grad_()
+    yr = X.bst_transformer_block(xr, pad, params, H, dropout_p=p, keep=keep)
+    yr.backward(g)
+    ref_grads = {k: v.grad for k, v in params.items()}
+    ref_grads["x"] = xr.grad
+    grads = {k: v.grad for k, v in blk.named_parameters()}
+    grads["x"] = xa.grad
+    p64 = {k: v.detach().double().requires_grad_() for k, v in params.items()}
+    x64 = x.double().requires_grad_()
+    X.bst_transformer_block(x64, pad, p64, H, dropout_p=p, keep=keep).backward(g.double())
+    grads64 = {k: v.grad for k, v in p64.items()}
+    grads64["x"] = x64.grad
+    compare([y], grads, [yr.detach()], ref_grads, FP32_TOL, grads64)
+    # the next forward advances the offset: other masks, other output
+    y2 = blk(xa, xa, xa, key_padding_mask=pad.to(DEV))
+    assert int(blk._last_rng[1]) == offset + 1 and not torch.equal(y2, y)
 
 
 @pytest.mark.parametrize("B,H,N", [(8192, 128, 2), (1000, 256, 2), (333, 24, 4), (64, 100, 0), (2048, 7, 1)])
