@@ -101,6 +101,8 @@ PROTOTYPES = {
     "rk_shard_owner": (_I, [_P, _L, _L, _L, _P, _P, _P]),
     "rk_shard_route": (_I, [_P, _P, _P, _L, _L, _L, _I, _P, _P, _P, _P]),
     "rk_plan_compact": (_I, [_P, _L, _L, _P, _P, _P, _P]),
+    "rk_plan_compact_fields": (_I, [_P, _P, _P, _P, _I, _P, _P, _P, _P]),
+    "rk_rowwise_adam_touched": (_I, [_P, _P, _P, _P, _P, _P, _L, _I, _L, _F, _F, _F, _F, _L, _P, _P]),
     "rk_resunit_pack_floats": (_I, [_I, _I]),
     "rk_resunits_fwd": (_I, [_P, _I, _P, _I, _P, _I, _I, _L, _P, _P, _P]),
     "rk_resunits_bwd": (_I, [_P, _P, _I, _I, _I, _L, _P, _P, _P]),

@@ -59,6 +59,7 @@ class _AfmPooling(torch.autograd.Function):
             ctx.fields, ctx.keep = fields, keep
             if any(ctx.needs_input_grad[5 + F:]):
                 ctx.plan = OccurrencePlan([keep[2 * f + 1] for f in range(F)], ctx.meta[4])
+                ctx.tables = list(tables)
             ctx.save_for_backward(w1, b1, w2, b2)
         return out
 
@@ -87,7 +88,7 @@ class _AfmPooling(torch.autograd.Function):
         g_tables = [None] * F
         if any(ctx.needs_input_grad[5 + F:]):
             g_tables = ctx.plan.reduce_to_dense(
-                [GradSource(g_rows, f * D, F * D, D, rows[f], f) for f in range(F)])
+                [GradSource(g_rows, f * D, F * D, D, rows[f], f, ctx.tables[f]) for f in range(F)])
         return (None, g_att[:A * D].view(A, D), g_att[A * D:A * D + A], g_att[A * D + A:A * D + 2 * A].view(1, A),
                 g_att[A * D + 2 * A:], *([None] * F), *g_tables)
 

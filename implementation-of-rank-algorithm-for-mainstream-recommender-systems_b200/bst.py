@@ -128,6 +128,7 @@ class _BstBlock(torch.autograd.Function):
             ctx.max_len = int(params[0].shape[0])
             if from_table and ctx.needs_input_grad[3]:
                 ctx.plan = OccurrencePlan([idx], [int(source.shape[0])])
+                ctx.table = source
             ctx.save_for_backward(seq_len, idx if from_table else None, source)
         return y if pool is None else pooled
 
@@ -169,7 +170,7 @@ class _BstBlock(torch.autograd.Function):
         if ctx.needs_input_grad[3]:
             if ctx.from_table:
                 (g_source,) = ctx.plan.reduce_to_dense(
-                    [GradSource(g_x, 0, D_MODEL, D_MODEL, int(source.shape[0]), 0)])
+                    [GradSource(g_x, 0, D_MODEL, D_MODEL, int(source.shape[0]), 0, ctx.table)])
             else:
                 g_source = g_x
         return (None, None, None, g_source, *grads)

@@ -13,12 +13,17 @@ namespace rk {
 template <int VEC>
 __global__ void __launch_bounds__(256)
 rowwise_adam_kernel(float* __restrict__ weight, float* __restrict__ exp_avg, float* __restrict__ exp_avg_sq,
-                    const int64_t* __restrict__ rows, const float* __restrict__ grads, int64_t n, int D, int64_t V,
+                    const int64_t* __restrict__ rows, const float* __restrict__ grads, int64_t n,
+                    const int64_t* __restrict__ n_dev, int D, int64_t V,
                     float beta1, float beta2, float eps, float step_size, int32_t* err_flag) {
     const int units = D / VEC;
     const int64_t gid = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     const int64_t i = gid / units;
     const int u = (int)(gid - i * units);
+    if (n_dev) {                                      // the live count sits on the device (no host sync upstream)
+        const int64_t live = __ldg(n_dev);
+        if (live < n) n = live;
+    }
     if (i >= n) return;
     const int64_t raw = __ldg(rows + i);
     if ((uint64_t)raw >= (uint64_t)V) {               // never write outside the table
@@ -45,8 +50,8 @@ rowwise_adam_kernel(float* __restrict__ weight, float* __restrict__ exp_avg, flo
 
 }  // namespace rk
 
-extern "C" int rk_rowwise_adam(float* weight, float* exp_avg, float* exp_avg_sq, const int64_t* rows,
-                               const float* grads, int64_t n, int D, int64_t V, float lr, float beta1, float beta2,
+static int rowwise_adam_launch(float* weight, float* exp_avg, float* exp_avg_sq, const int64_t* rows, const float* grads,
+                               int64_t n, const int64_t* n_dev, int D, int64_t V, float lr, float beta1, float beta2,
                                float eps, int64_t step, int32_t* err_flag, rk_stream_t stream_) {
     using namespace rk;
     RK_CHECK_ARG(weight && exp_avg && exp_avg_sq && (n == 0 || (rows && grads)), "rowwise_adam: NULL pointer");
@@ -61,9 +66,25 @@ extern "C" int rk_rowwise_adam(float* weight, float* exp_avg, float* exp_avg_sq,
     const int64_t threads = n * (D / vec);
     const int grid = (int)ceil_div(threads, 256);
     cudaStream_t s = (cudaStream_t)stream_;
-    if (vec == 4) rowwise_adam_kernel<4><<<grid, 256, 0, s>>>(weight, exp_avg, exp_avg_sq, rows, grads, n, D, V, beta1, beta2, eps, step_size, err_flag);
-    else if (vec == 2) rowwise_adam_kernel<2><<<grid, 256, 0, s>>>(weight, exp_avg, exp_avg_sq, rows, grads, n, D, V, beta1, beta2, eps, step_size, err_flag);
-    else rowwise_adam_kernel<1><<<grid, 256, 0, s>>>(weight, exp_avg, exp_avg_sq, rows, grads, n, D, V, beta1, beta2, eps, step_size, err_flag);
+    if (vec == 4) rowwise_adam_kernel<4><<<grid, 256, 0, s>>>(weight, exp_avg, exp_avg_sq, rows, grads, n, n_dev, D, V, beta1, beta2, eps, step_size, err_flag);
+    else if (vec == 2) rowwise_adam_kernel<2><<<grid, 256, 0, s>>>(weight, exp_avg, exp_avg_sq, rows, grads, n, n_dev, D, V, beta1, beta2, eps, step_size, err_flag);
+    else rowwise_adam_kernel<1><<<grid, 256, 0, s>>>(weight, exp_avg, exp_avg_sq, rows, grads, n, n_dev, D, V, beta1, beta2, eps, step_size, err_flag);
     RK_LAUNCH_CHECK();
     return 0;
+}
+
+extern "C" int rk_rowwise_adam(float* weight, float* exp_avg, float* exp_avg_sq, const int64_t* rows,
+                               const float* grads, int64_t n, int D, int64_t V, float lr, float beta1, float beta2,
+                               float eps, int64_t step, int32_t* err_flag, rk_stream_t stream_) {
+    return rowwise_adam_launch(weight, exp_avg, exp_avg_sq, rows, grads, n, nullptr, D, V, lr, beta1, beta2, eps, step,
+                               err_flag, stream_);
+}
+
+extern "C" int rk_rowwise_adam_touched(float* weight, float* exp_avg, float* exp_avg_sq, const int64_t* rows,
+                                       const float* grads, const int64_t* count, int64_t capacity, int D, int64_t V,
+                                       float lr, float beta1, float beta2, float eps, int64_t step, int32_t* err_flag,
+                                       rk_stream_t stream_) {
+    RK_CHECK_ARG(count, "rowwise_adam_touched: count is NULL");
+    return rowwise_adam_launch(weight, exp_avg, exp_avg_sq, rows, grads, capacity, count, D, V, lr, beta1, beta2, eps,
+                               step, err_flag, stream_);
 }

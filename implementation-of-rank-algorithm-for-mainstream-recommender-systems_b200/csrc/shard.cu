@@ -46,11 +46,27 @@ shard_route_kernel(const int64_t* __restrict__ idx, const uint32_t* __restrict__
 // One CTA, chunked scan: rank[i] = number of distinct keys before position i (keys sorted);
 // uniq[rank] = key - key_base for every head; *n_uniq = number of distinct live keys.  Keys equal
 // to dead_key (padding sentinel, sorted last) are left out.
+struct CompactField {
+    int64_t  start, n;            // slice of the sorted keys
+    uint32_t key_base, dead_key;  // of the incoming keys
+    uint32_t out_base, out_dead;  // of the rank keys written out
+};
+struct CompactFields {
+    CompactField f[RK_MAX_FIELDS];
+};
+
 __global__ void __launch_bounds__(1024)
-plan_compact_kernel(const uint32_t* __restrict__ keys, int64_t n, uint32_t key_base, uint32_t dead_key,
-                    uint32_t* __restrict__ rank_keys, int64_t* __restrict__ uniq, int64_t* __restrict__ n_uniq) {
+plan_compact_kernel(const uint32_t* __restrict__ keys_all, const __grid_constant__ CompactFields fields,
+                    uint32_t* __restrict__ rank_all, int64_t* __restrict__ uniq_all, int64_t* __restrict__ n_uniq_all) {
     __shared__ uint32_t warp_tot[32];
     __shared__ uint32_t carry_s;
+    const CompactField& fd = fields.f[blockIdx.x];
+    const uint32_t* keys = keys_all + fd.start;
+    uint32_t* rank_keys = rank_all + fd.start;
+    int64_t* uniq = uniq_all + fd.start;
+    int64_t* n_uniq = n_uniq_all + blockIdx.x;
+    const int64_t n = fd.n;
+    const uint32_t key_base = fd.key_base, dead_key = fd.dead_key;
     const int t = threadIdx.x, lane = t & 31, w = t >> 5;
     if (t == 0) carry_s = 0;
     __syncthreads();
@@ -74,7 +90,7 @@ plan_compact_kernel(const uint32_t* __restrict__ keys, int64_t n, uint32_t key_b
         const uint32_t incl = before + inc;          // heads up to and including i
         if (i < n) {
             // rank of i's segment = heads before or at i, minus one; dead keys keep a sentinel rank
-            rank_keys[i] = (k == dead_key) ? 0xffffffffu : incl - 1;
+            rank_keys[i] = (k == dead_key) ? fd.out_dead : fd.out_base + incl - 1;
             if (head) uniq[incl - 1] = (int64_t)(k - key_base);
         }
         __syncthreads();
@@ -130,8 +146,38 @@ int rk_plan_compact(const uint32_t* sorted_keys, int64_t n, int64_t rows, uint32
         return 0;
     }
     RK_CHECK_ARG(sorted_keys && rank_keys && uniq_rows, "plan_compact: NULL pointer");
-    // single-field plans only: key_base = 0, dead key = rows
-    plan_compact_kernel<<<1, 1024, 0, s>>>(sorted_keys, n, 0u, (uint32_t)rows, rank_keys, uniq_rows, n_uniq);
+    // single-field plan: key_base = 0, dead key = rows; dead positions get the sentinel rank 0xffffffff
+    CompactFields cf;
+    cf.f[0] = CompactField{0, n, 0u, (uint32_t)rows, 0u, 0xffffffffu};
+    plan_compact_kernel<<<1, 1024, 0, s>>>(sorted_keys, cf, rank_keys, uniq_rows, n_uniq);
+    RK_LAUNCH_CHECK();
+    return 0;
+}
+
+int rk_plan_compact_fields(const uint32_t* sorted_keys, const int64_t* n, const int64_t* rows, const int64_t* cap,
+                           int F, uint32_t* rank_keys, int64_t* uniq_rows, int64_t* n_uniq, rk_stream_t stream_) {
+    using namespace rk;
+    RK_CHECK_ARG(F >= 1 && F <= RK_MAX_FIELDS && n && rows && cap && n_uniq, "plan_compact_fields: bad argument");
+    cudaStream_t s = (cudaStream_t)stream_;
+    CompactFields cf;
+    int64_t start = 0, in_base = 0, out_base = 0;
+    for (int f = 0; f < F; ++f) {
+        RK_CHECK_ARG(n[f] >= 0 && rows[f] > 0 && cap[f] > 0, "plan_compact_fields: field %d: n=%lld rows=%lld cap=%lld", f,
+                     (long long)n[f], (long long)rows[f], (long long)cap[f]);
+        // the key layout of rk_plan_build / rk_embgrad_segment_reduce: field f owns rows[f] + 1 keys
+        cf.f[f] = CompactField{start, n[f], (uint32_t)in_base, (uint32_t)(in_base + rows[f]), (uint32_t)out_base,
+                               (uint32_t)(out_base + cap[f])};
+        start += n[f];
+        in_base += rows[f] + 1;
+        out_base += cap[f] + 1;
+    }
+    RK_CHECK_ARG(in_base < (1ll << 32) && out_base < (1ll << 32), "plan_compact_fields: key space overflow");
+    if (start == 0) {
+        RK_CUDA(cudaMemsetAsync(n_uniq, 0, sizeof(int64_t) * F, s));
+        return 0;
+    }
+    RK_CHECK_ARG(sorted_keys && rank_keys && uniq_rows, "plan_compact_fields: NULL pointer");
+    plan_compact_kernel<<<F, 1024, 0, s>>>(sorted_keys, cf, rank_keys, uniq_rows, n_uniq);
     RK_LAUNCH_CHECK();
     return 0;
 }

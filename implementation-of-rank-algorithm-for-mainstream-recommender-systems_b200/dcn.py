@@ -79,6 +79,7 @@ class _CrossNet(torch.autograd.Function):
             if any(ctx.needs_input_grad[5 + F:]):
                 ctx.plan = OccurrencePlan([keep[2 * f + 1] for f in range(F)],
                                           [int(t.shape[0]) for t in tables])
+                ctx.tables = list(tables)
             ctx.save_for_backward(concat_all, w, b)
         return concat_all, cross_vec
 
@@ -100,7 +101,7 @@ class _CrossNet(torch.autograd.Function):
         g_dense = g_x0[:, :n_dense] if ctx.needs_input_grad[2] else None
         g_tables = [None] * F
         if any(ctx.needs_input_grad[5 + F:]):
-            src = [GradSource(g_x0, offsets[f], d, dims[f], rows[f], f) for f in range(F)]
+            src = [GradSource(g_x0, offsets[f], d, dims[f], rows[f], f, ctx.tables[f]) for f in range(F)]
             g_tables = ctx.plan.reduce_to_dense(src)
         return (None, None, g_dense, None, None, *([None] * F), *g_tables)
 

@@ -75,6 +75,7 @@ class _ResidualStack(torch.autograd.Function):
                         [int(t.shape[0]) for t in tables], [int(t.shape[1]) for t in tables])
             if any(ctx.needs_input_grad[6 + F:]):
                 ctx.plan = OccurrencePlan([keep[2 * f + 1] for f in range(F)], ctx.meta[7])
+                ctx.tables = list(tables)
             ctx.save_for_backward(nets, units if n_units else None)
         return nets[n_units]
 
@@ -94,7 +95,7 @@ class _ResidualStack(torch.autograd.Function):
         g_tables = [None] * F
         if any(ctx.needs_input_grad[6 + F:]):
             g_tables = ctx.plan.reduce_to_dense(
-                [GradSource(g_x0, offsets[f], d, dims[f], rows[f], f) for f in range(F)])
+                [GradSource(g_x0, offsets[f], d, dims[f], rows[f], f, ctx.tables[f]) for f in range(F)])
         return (None, None, None, None, g_dense, None, *([None] * F), *g_tables)
 
 

@@ -52,6 +52,7 @@ class _FMInteraction(torch.autograd.Function):
         if any(ctx.needs_input_grad):
             # the occurrence order depends on the indices only: build it while the tower runs
             ctx.plan = OccurrencePlan([keep[2 * f + 1] for f in range(F)], ctx.rows)
+            ctx.tables = (list(args[F:2 * F]), list(second))
             ctx.save_for_backward(deep_input)
         return deep_input, fm_first, fm_second
 
@@ -71,12 +72,12 @@ class _FMInteraction(torch.autograd.Function):
             rc = lib.rk_deepfm_bwd(deep_input.data_ptr(), _lib.ptr(g_deep), _lib.ptr(g_second), F, D, B,
                                    g_rows.data_ptr(), _lib.stream_ptr())
             _lib.check(rc, "rk_deepfm_bwd")
-            sources += [GradSource(g_rows, f * D, F * D, D, ctx.rows[f], f) for f in range(F)]
+            sources += [GradSource(g_rows, f * D, F * D, D, ctx.rows[f], f, ctx.tables[1][f]) for f in range(F)]
         n_second = len(sources)
         if g_first is not None:
             g_first = _lib.require_cuda(g_first, "g_first", torch.float32)
             # every field's first-order weight receives the same per-sample scalar
-            sources += [GradSource(g_first, 0, 1, 1, ctx.rows[f], f) for f in range(F)]
+            sources += [GradSource(g_first, 0, 1, 1, ctx.rows[f], f, ctx.tables[0][f]) for f in range(F)]
         if sources:
             dense = ctx.plan.reduce_to_dense(sources)
             if n_second:

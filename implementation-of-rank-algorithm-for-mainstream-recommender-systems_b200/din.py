@@ -177,6 +177,7 @@ class _DinHotPath(torch.autograd.Function):
                                       live_mode=[_lib.LIVE_ALL] * (F + 1) + [mode])
             ctx.dims = [int(t.shape[1]) for t in cat_tabs]
             ctx.rows = rows
+            ctx.tables = [*cat_tabs, tgt_w, his_w]
             ctx.save_for_backward(concat_all, norm, att_w, masks, mlp)
         return concat_all, norm
 
@@ -198,9 +199,9 @@ class _DinHotPath(torch.autograd.Function):
                             masks.data_ptr(), _lib.ptr(g_concat), _lib.ptr(g_norm), g_row.data_ptr(),
                             g_hist.data_ptr(), _lib.err_flag(dev).data_ptr(), _lib.stream_ptr())
         _lib.check(rc, "rk_din_bwd")
-        src = [GradSource(g_row, offsets[f], width, ctx.dims[f], ctx.rows[f], f) for f in range(F)]
-        src.append(GradSource(g_row, tgt_off, width, D, ctx.rows[F], F))
-        src.append(GradSource(g_hist, 0, D, D, ctx.rows[F + 1], F + 1))
+        src = [GradSource(g_row, offsets[f], width, ctx.dims[f], ctx.rows[f], f, ctx.tables[f]) for f in range(F)]
+        src.append(GradSource(g_row, tgt_off, width, D, ctx.rows[F], F, ctx.tables[F]))
+        src.append(GradSource(g_hist, 0, D, D, ctx.rows[F + 1], F + 1, ctx.tables[F + 1]))
         dense = ctx.plan.reduce_to_dense(src)
         g_dense = [g_row[:, c] if ctx.needs_input_grad[2 + c] else None for c in range(n_dense)]
         return (None, None, *g_dense, *([None] * (F + 3)), *dense)

@@ -54,6 +54,7 @@ class _FwFMInteraction(torch.autograd.Function):
         if any(ctx.needs_input_grad):
             # the occurrence order depends on the indices only: built on the side stream
             ctx.plan = OccurrencePlan([keep[2 * f + 1] for f in range(F)], ctx.rows)
+            ctx.tables = (list(args[F:2 * F]), list(second))
             ctx.save_for_backward(emb, y, field_weight)
         return y
 
@@ -73,9 +74,9 @@ class _FwFMInteraction(torch.autograd.Function):
                              g_rows.data_ptr(), g_z.data_ptr(), partials.data_ptr(), g_pair.data_ptr(),
                              _lib.stream_ptr())
         _lib.check(rc, "rk_fwfm_bwd")
-        sources = [GradSource(g_rows, f * D, F * D, D, ctx.rows[f], f) for f in range(F)]
+        sources = [GradSource(g_rows, f * D, F * D, D, ctx.rows[f], f, ctx.tables[1][f]) for f in range(F)]
         # every field's first-order weight receives the same per-sample scalar g_z
-        sources += [GradSource(g_z, 0, 1, 1, ctx.rows[f], f) for f in range(F)]
+        sources += [GradSource(g_z, 0, 1, 1, ctx.rows[f], f, ctx.tables[0][f]) for f in range(F)]
         dense = ctx.plan.reduce_to_dense(sources)
         grads_second, grads_first = dense[:F], dense[F:]
         g_fw = g_pair[:P] if ctx.needs_input_grad[1 + 3 * F] else None

@@ -70,9 +70,50 @@ class GradSource:
     dim: int
     rows: int
     field: int           # which plan field's occurrences feed this table
+    param: object = None  # the table tensor itself (where a touched-rows gradient is attached)
 
 
 DIRECT_REDUCE = os.environ.get("RANK_B200_DIRECT", "1") != "0"
+
+# ---- opt-in sparse gradients of the replicated tables ---------------------
+# "dense"  : every table receives a dense [V, D] .grad, as the reference's nn.Embedding(sparse=False)
+#            does (DeepFM/deepfm.py:90-98) and dense optim.Adam needs (:226) — the default.
+# "touched": no dense slab is written.  Each table gets `table.touched_grad = TouchedRows(...)` — the
+#            distinct rows the batch touched and one summed gradient row each, count on the device,
+#            no host synchronisation — and `.grad` stays None.  optim.RowwiseAdam consumes it.
+_TABLE_GRADIENTS = "dense"
+
+
+def set_table_gradients(mode: str) -> None:
+    global _TABLE_GRADIENTS
+    if mode not in ("dense", "touched"):
+        raise ValueError(f"table gradients are 'dense' or 'touched', got {mode!r}")
+    _TABLE_GRADIENTS = mode
+
+
+def table_gradients() -> str:
+    return _TABLE_GRADIENTS
+
+
+@dataclass
+class TouchedRows:
+    """Sparse gradient of one table, sized without a host sync: `capacity = min(occurrences, table rows)`."""
+    rows: torch.Tensor      # [capacity] int64: the first `count` entries are the distinct touched rows, ascending
+    values: torch.Tensor    # [capacity, dim]: values[i] = summed gradient of rows[i]; zero from `count` on
+    count: torch.Tensor     # [1] int64, on the device
+    shape: tuple            # (table rows, dim)
+
+    def to_dense(self) -> torch.Tensor:
+        """The dense gradient it stands for (synchronises; tests and debugging)."""
+        n = int(self.count.item())
+        out = torch.zeros(self.shape, dtype=self.values.dtype, device=self.values.device)
+        out[self.rows[:n]] = self.values[:n]
+        return out
+
+    def to_sparse_coo(self) -> torch.Tensor:
+        """A coalesced torch sparse gradient (synchronises on the count)."""
+        n = int(self.count.item())
+        return torch.sparse_coo_tensor(self.rows[:n].unsqueeze(0), self.values[:n], self.shape, is_coalesced=True)
 
 
 class OccurrencePlan:
@@ -99,7 +140,9 @@ class OccurrencePlan:
         dev = self.indices[0].device
         self.device = dev
         modes_all = [_lib.LIVE_ALL] * self.F if live_mode is None else [int(m) for m in live_mode]
-        use_direct = DIRECT_REDUCE if direct is None else bool(direct)
+        self.touched = _TABLE_GRADIENTS == "touched" and direct is None
+        self._compact = None
+        use_direct = (DIRECT_REDUCE and not self.touched) if direct is None else bool(direct)
         self.direct = [use_direct and self.n[f] <= _lib.RK_DIRECT_MAX_N and modes_all[f] == _lib.LIVE_ALL
                        for f in range(self.F)]
         # ---- the fields that need the sorted order
@@ -166,7 +209,11 @@ class OccurrencePlan:
         self._ws = None
 
     def reduce_to_dense(self, sources: list[GradSource]) -> list[torch.Tensor]:
-        """One dense `[rows, dim]` gradient per source, summed over duplicate indices."""
+        """One dense `[rows, dim]` gradient per source, summed over duplicate indices.  In the opt-in
+        "touched" mode (set_table_gradients) nothing dense is written: every source's table receives
+        a `touched_grad` and the returned gradients are None."""
+        if self.touched:
+            return self._reduce_touched(sources)
         lib = _lib.load()
         T = len(sources)
         if not 1 <= T <= _lib.RK_MAX_TABLES:
@@ -228,6 +275,71 @@ class OccurrencePlan:
         return grads
 
 
+def _reduce_touched_impl(plan, sources):
+    lib = _lib.load()
+    T = len(sources)
+    if not 1 <= T <= _lib.RK_MAX_TABLES:
+        raise ValueError(f"{T} gradient tables (max {_lib.RK_MAX_TABLES})")
+    plan.join()
+    dev = plan.device
+    F = len(plan.sort_fields)
+    n_arr, rows_arr = _i64_array(plan.s_n), _i64_array(plan.s_rows)
+    if plan._compact is None:
+        # ranks of the distinct rows of every field + the rows themselves, one launch, no host sync
+        caps = [max(1, min(n, r)) for n, r in zip(plan.s_n, plan.s_rows)]
+        rank_keys = torch.empty(max(plan.total, 1), dtype=torch.int32, device=dev)
+        uniq = torch.empty(max(plan.total, 1), dtype=torch.int64, device=dev)
+        n_uniq = torch.empty(F, dtype=torch.int64, device=dev)
+        rc = lib.rk_plan_compact_fields(plan.sorted_keys.data_ptr(), n_arr, rows_arr, _i64_array(caps), F,
+                                        rank_keys.data_ptr(), uniq.data_ptr(), n_uniq.data_ptr(), _lib.stream_ptr())
+        _lib.check(rc, "rk_plan_compact_fields")
+        starts, acc = [], 0
+        for n in plan.s_n:
+            starts.append(acc)
+            acc += n
+        plan._compact = (caps, rank_keys, uniq, n_uniq, starts)
+    caps, rank_keys, uniq, n_uniq, starts = plan._compact
+    offs, acc = [], 0
+    for s in sources:
+        if s.param is None:
+            raise RuntimeError("touched-rows gradients need GradSource.param (the table tensor)")
+        if s.rows != plan.rows[s.field]:
+            raise ValueError("gradient table height does not match its plan field")
+        offs.append(acc)
+        acc += (caps[plan.sort_pos[s.field]] * s.dim + 3) // 4 * 4
+    slab = torch.zeros(max(acc, 1), dtype=torch.float32, device=dev)
+    tabs = (_lib.RkGradTable * T)()
+    for t, s in enumerate(sources):
+        tabs[t].g = s.base.data_ptr() + 4 * s.offset
+        tabs[t].ld = s.ld
+        tabs[t].dw = slab.data_ptr() + 4 * offs[t]
+        tabs[t].dim = s.dim
+        tabs[t].field = plan.sort_pos[s.field]
+    if plan.total:
+        ws_bytes = lib.rk_reduce_workspace_bytes(n_arr, F, tabs, T)
+        ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+        rc = lib.rk_embgrad_segment_reduce(rank_keys.data_ptr(), plan.perm.data_ptr(), n_arr, _i64_array(caps), F,
+                                           tabs, T, ws.data_ptr(), ws_bytes, _lib.stream_ptr())
+        _lib.check(rc, "rk_embgrad_segment_reduce")
+    else:
+        n_uniq.zero_()
+    for t, s in enumerate(sources):
+        k = plan.sort_pos[s.field]
+        cap = caps[k]
+        touched = TouchedRows(uniq[starts[k]:starts[k] + cap] if plan.s_n[k] else uniq[:0],
+                              slab[offs[t]:offs[t] + cap * s.dim].view(cap, s.dim) if plan.s_n[k]
+                              else slab[:0].view(0, s.dim),
+                              n_uniq[k:k + 1], (s.rows, s.dim))
+        if getattr(s.param, "touched_grad", None) is not None:
+            raise RuntimeError("a touched-rows gradient is already attached to this table: run the optimizer step "
+                               "(or clear table.touched_grad) between backward passes")
+        s.param.touched_grad = touched
+    return [None] * T
+
+
+OccurrencePlan._reduce_touched = _reduce_touched_impl
+
+
 class GatherConcat(torch.autograd.Function):
     """(dense[B,n] or None, idx_0.., table_0..) -> [dense | table_0[idx_0] | ...], differentiable
     w.r.t. dense and the tables (dense gradients through the sorted segment reduction)."""
@@ -245,6 +357,7 @@ class GatherConcat(torch.autograd.Function):
         ctx.meta = (F, n_dense, offsets, off, [int(t.shape[0]) for t in tables], [int(t.shape[1]) for t in tables])
         if any(ctx.needs_input_grad[2 + F:]):
             ctx.plan = OccurrencePlan(list(idx), ctx.meta[4])
+            ctx.tables = list(tables)
         return out
 
     @staticmethod
@@ -257,7 +370,7 @@ class GatherConcat(torch.autograd.Function):
         g_tables = [None] * F
         if any(ctx.needs_input_grad[2 + F:]):
             g_tables = ctx.plan.reduce_to_dense(
-                [GradSource(g_out, offsets[f], width, dims[f], rows[f], f) for f in range(F)])
+                [GradSource(g_out, offsets[f], width, dims[f], rows[f], f, ctx.tables[f]) for f in range(F)])
         return (None, g_dense, *([None] * F), *g_tables)
 
 

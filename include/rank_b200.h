@@ -282,6 +282,14 @@ int rk_bn_act_bwd(const float* x, const float* g_z, int64_t B, int units, const 
 int rk_rowwise_adam(float* weight, float* exp_avg, float* exp_avg_sq, const int64_t* rows,
                     const float* grads, int64_t n, int D, int64_t V, float lr, float beta1,
                     float beta2, float eps, int64_t step, int32_t* err_flag, rk_stream_t stream);
+/* The same update for a touched-rows gradient whose live count is on the device (no host sync
+ * between the backward and the optimizer): rows[capacity], grads[capacity, D], only the first
+ * *count (<= capacity) entries are applied.  This is what the replicated tables' opt-in sparse
+ * gradients feed (rk_plan_compact_fields + rk_embgrad_segment_reduce on the rank keys). */
+int rk_rowwise_adam_touched(float* weight, float* exp_avg, float* exp_avg_sq, const int64_t* rows,
+                            const float* grads, const int64_t* count, int64_t capacity, int D,
+                            int64_t V, float lr, float beta1, float beta2, float eps, int64_t step,
+                            int32_t* err_flag, rk_stream_t stream);
 
 /* ---- row-sharded table (BASELINE config 5 "scaled": BST feedid table of 1e8 rows block-
  *      partitioned by row over the ranks; the reference itself is single-process) ------------
@@ -302,6 +310,15 @@ int rk_shard_route(const int64_t* idx, const uint32_t* sorted_owner, const uint3
                    int64_t* counts, rk_stream_t stream);
 int rk_plan_compact(const uint32_t* sorted_keys, int64_t n, int64_t rows, uint32_t* rank_keys,
                     int64_t* uniq_rows, int64_t* n_uniq, rk_stream_t stream);
+/* The multi-field form, for the touched-rows gradients of replicated tables:
+ * sorted_keys is a whole rk_plan_build output over F fields (field f: n[f] keys, rows[f] table
+ * rows).  Field f's slice of rank_keys receives keys in the layout rk_embgrad_segment_reduce
+ * expects for tables of cap[f] rows (cap[f] >= the number of distinct rows; dead positions are
+ * parked on cap[f]), uniq_rows its distinct rows (slice start = sum of n[g], g < f) and n_uniq[f]
+ * their count.  One launch, one CTA per field, no host synchronisation. */
+int rk_plan_compact_fields(const uint32_t* sorted_keys, const int64_t* n, const int64_t* rows,
+                           const int64_t* cap, int F, uint32_t* rank_keys, int64_t* uniq_rows,
+                           int64_t* n_uniq, rk_stream_t stream);
 
 /* ---- DeepCrossing residual units (residual_unit + loop, DeepCrossing/deepcrossing.py:25-42,
  *      148-159), fused with the gather + concat ----------------------------------------------
