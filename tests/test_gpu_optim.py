@@ -157,7 +157,7 @@ def test_rowwise_adam_on_touched_rows_matches_sparse_adam_and_dense_adam_on_thos
             opt_d.step()
             for k in names:
                 rows = touched_rows[k]
-                assert rel_err(po[k][rows], pd[k][rows]) <= 1e-5, k
+                assert rel_err(po[k][rows], pd[k][rows]) <= 1e-4, k      # two torch formulations of one update
                 mask = torch.ones(po[k].shape[0], dtype=torch.bool, device=DEV)
                 mask[rows] = False
                 assert torch.equal(po[k][mask], before[k][mask]) and torch.equal(pd[k][mask], before[k][mask])
