@@ -477,6 +477,7 @@ class Stepper:
             with torch.cuda.graph(self.graph):
                 self._body()
             self.grads = [p.grad for p in model.parameters()]
+        self.collective_in_graph = self.graph is not None and self.reducer is not None
 
     def _body(self):
         if self.hot_only:
@@ -489,6 +490,10 @@ class Stepper:
         else:
             self.loss = self.wl.loss(self.model, self.static)
             self.loss.backward()
+            if self.reducer is not None:
+                # the gradient all-reduce is part of the step: stream-ordered behind the backward, captured in
+                # the same CUDA graph (no host work between the last kernel and the collective)
+                self.reducer.allreduce()
 
     def _eager(self, seed):
         self.model.zero_grad(set_to_none=True)
@@ -503,15 +508,11 @@ class Stepper:
     def run(self, seed):
         if self.graph is None:
             self._eager(seed)
-            grads = None
         else:
             if self.has_ephemeral and not self.hot_only:
                 torch.default_generator.manual_seed(seed)   # same draw on every rank
                 self.model.draw_ephemeral()
             self.graph.replay()
-            grads = self.grads
-        if self.reducer is not None:
-            self.reducer.allreduce(grads)
         return self.loss
 
 

@@ -95,6 +95,25 @@ def table_gradients() -> str:
     return _TABLE_GRADIENTS
 
 
+# Where the dense-gradient slabs come from: None = torch.empty; parallel.GradientAllReducer installs its
+# own so that the table gradients are born inside the buffer the all-reduce reads (no pack copy).
+_slab_provider = None
+
+
+def set_slab_provider(fn) -> None:
+    """fn(n_floats, device) -> 1-D fp32 tensor of n_floats, or None to fall back to torch.empty."""
+    global _slab_provider
+    _slab_provider = fn
+
+
+def _new_slab(n_floats, device):
+    if _slab_provider is not None:
+        t = _slab_provider(n_floats, device)
+        if t is not None:
+            return t
+    return torch.empty(n_floats, dtype=torch.float32, device=device)
+
+
 @dataclass
 class TouchedRows:
     """Sparse gradient of one table, sized without a host sync: `capacity = min(occurrences, table rows)`."""
@@ -237,10 +256,11 @@ class OccurrencePlan:
             acc += (sources[t].rows * sources[t].dim + 3) // 4 * 4          # keep every table 16-byte aligned
         if n_direct == T:
             sorted_from = acc
-        slab = torch.empty(acc, dtype=torch.float32, device=dev)
+        slab = _new_slab(acc, dev)
         if sorted_from < acc:
             slab[sorted_from:].zero_()
         grads = [slab[starts[t]:starts[t] + s.rows * s.dim].view(s.rows, s.dim) for t, s in enumerate(sources)]
+        direct_event = None
         if n_direct:
             tabs = (_lib.RkDirectTable * n_direct)()
             for k, t in enumerate(order[:n_direct]):
@@ -252,7 +272,21 @@ class OccurrencePlan:
                 tabs[k].rows = s.rows
                 tabs[k].n = self.n[s.field]
                 tabs[k].dim = s.dim
-            rc = lib.rk_embgrad_direct_reduce(tabs, n_direct, _lib.err_flag(dev).data_ptr(), _lib.stream_ptr())
+            # the two reductions write disjoint parts of the slab: when both exist, the one-launch direct
+            # reduction runs on the side stream next to the sorted one (forked and joined here)
+            side = _plan_stream(dev) if n_direct < T else None
+            if side is None:
+                rc = lib.rk_embgrad_direct_reduce(tabs, n_direct, _lib.err_flag(dev).data_ptr(), _lib.stream_ptr())
+            else:
+                main = torch.cuda.current_stream(dev)
+                side.wait_stream(main)
+                with torch.cuda.stream(side):
+                    rc = lib.rk_embgrad_direct_reduce(tabs, n_direct, _lib.err_flag(dev).data_ptr(), side.cuda_stream)
+                    direct_event = side.record_event()
+                if not torch.cuda.is_current_stream_capturing():
+                    for t in [slab, *{id(sources[t].base): sources[t].base for t in order[:n_direct]}.values(),
+                              *[self.indices[sources[t].field] for t in order[:n_direct]]]:
+                        t.record_stream(side)
             _lib.check(rc, "rk_embgrad_direct_reduce")
         if n_direct < T:
             S = T - n_direct
@@ -272,6 +306,8 @@ class OccurrencePlan:
                                                n_arr, _i64_array(self.s_rows), F, tabs, S,
                                                ws.data_ptr(), ws_bytes, _lib.stream_ptr())
             _lib.check(rc, "rk_embgrad_segment_reduce")
+        if direct_event is not None:
+            torch.cuda.current_stream(dev).wait_event(direct_event)
         return grads
 
 

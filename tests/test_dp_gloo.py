@@ -31,7 +31,8 @@ def _worker(rank, world, port, out):
     reducer = GradientAllReducer(net)
     loss = ((lin(emb(mine["idx"])).squeeze(1) - mine["y"]) ** 2).mean()
     loss.backward()
-    flat = reducer.allreduce()
+    reducer.allreduce()
+    flat = reducer.flat_gradients()
     if rank == 0:
         net.zero_grad()
         ref = ((lin(emb(full["idx"])).squeeze(1) - full["y"]) ** 2).mean()
