@@ -212,9 +212,14 @@ class BSTWorkload(Workload):
     hot_calls = ("rk_gather_concat_fwd", "rk_bst_block_fwd", "rk_plan_build", "rk_bst_block_bwd",
                  "rk_embgrad_segment_reduce")
 
+    precision = "fp32"
+
     def model(self, ns, oracle, vocab_dir):
         cls = ns.OracleBST if oracle else ns.BSTModel
-        return cls(vocab_dir, dropout_rate=0.0, nhead=4, num_transformer_blocks=1, max_seq_length=20)
+        m = cls(vocab_dir, dropout_rate=0.0, nhead=4, num_transformer_blocks=1, max_seq_length=20)
+        if not oracle:
+            m.block_precision = self.precision
+        return m
 
     def make_batch(self, B, seed):
         from rank_b200 import synthetic
@@ -226,6 +231,11 @@ class BSTWorkload(Workload):
 
     def hot(self, model, batch):
         return model.hot_path(batch["dense"], batch["category"], batch["seq_feedid"], batch["seq_length"])
+
+
+class BSTTensorCoreWorkload(BSTWorkload):
+    # Q/K/V, output projection and FFN of the block on tcgen05 (split-bf16 operands, fp32 TMEM accumulation)
+    name, precision, dtype = "bst_t20_h4_b1_tcgen05", "bf16", "bf16x3 tensor-core projections/FFN, f32 elsewhere"
 
 
 class DeepCrossingWorkload(Workload):
@@ -254,7 +264,7 @@ class DeepCrossingWorkload(Workload):
 DEFAULT_WORKLOAD = "din_tc"
 WORKLOADS = {"deepfm": DeepFMWorkload, "fwfm": FwFMWorkload, "dcn": DCNWorkload, "afm": AFMWorkload, "afm_fp32": AFMFp32Workload, "din": DINWorkload,
              "din_softmax": DINSoftmaxWorkload, "din_tc": DINTensorCoreWorkload,
-             "din_softmax_tc": DINSoftmaxTensorCoreWorkload, "bst": BSTWorkload,
+             "din_softmax_tc": DINSoftmaxTensorCoreWorkload, "bst": BSTWorkload, "bst_tc": BSTTensorCoreWorkload,
              "deepcrossing": DeepCrossingWorkload}
 
 
@@ -791,7 +801,7 @@ def measure_ours(args, wl, key, world, rank, local, dev, primary):
     return res
 
 
-OTHERS = ("din_softmax_tc", "din", "dcn", "deepfm", "fwfm", "afm", "bst", "deepcrossing")
+OTHERS = ("din_softmax_tc", "din", "dcn", "deepfm", "fwfm", "afm", "bst", "bst_tc", "deepcrossing")
 
 
 def run_ours(args, wl):

@@ -218,12 +218,14 @@ class BSTTransformer(nn.Module):
         self._last_rng = snap          # what this forward's masks were drawn from (tests read it)
         return p, snap
 
-    def run(self, source, seq_len, idx=None, pool=None):
-        """Fused path used by BSTModel: rows from `source[idx]` (first block) or `source[B,T,16]`."""
+    def run(self, source, seq_len, idx=None, pool=None, precision=None):
+        """Fused path used by BSTModel: rows from `source[idx]` (first block) or `source[B,T,16]`.
+        precision: "fp32" / "bf16" for this call, None = set_block_precision's global setting."""
         if self.d_model != D_MODEL:
             raise NotImplementedError(f"the fused BST block is built for d_model = {D_MODEL}")
         p, rng = self._dropout_state(source.device)
-        return _BstBlock.apply((self.nhead, pool, p, rng, _PRECISION), seq_len, idx, source, *self._params())
+        precision = precision or getattr(self, "block_precision", None) or _PRECISION
+        return _BstBlock.apply((self.nhead, pool, p, rng, precision), seq_len, idx, source, *self._params())
 
     def forward(self, queries, keys, values, key_padding_mask=None):
         """Self-attention form of the reference signature: queries, keys and values must be the
@@ -258,6 +260,7 @@ class BSTModel(nn.Module):
         self.batch_norm = batch_norm
         self.dropout_rate = dropout_rate
         self.pooling_method = pooling_method
+        self.block_precision = None       # "fp32" | "bf16" for this model; None = bst.set_block_precision's setting
         width = self.num_dense_features + sum(dim for _, dim in SIDE_TABLES) + 16
         layers = []
         for hidden in hidden_units:
@@ -289,7 +292,7 @@ class BSTModel(nn.Module):
             x, idx = feed.weight, seq_feedid
         for i, block in enumerate(blocks):
             last = i == len(blocks) - 1
-            x = block.run(x, seq_length, idx=idx, pool=pool if last else None)
+            x = block.run(x, seq_length, idx=idx, pool=pool if last else None, precision=self.block_precision)
             idx = None
         return side, x
 

@@ -34,6 +34,8 @@ def main():
     ap.add_argument("--rows", type=int, default=100_000_000)
     ap.add_argument("--batch", type=int, default=1024, help="per-rank batch (survey: 1024/GPU when sharded)")
     ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--eager", action="store_true", help="launch every step eagerly (default: forward + backward + "
+                    "both collectives replayed from one CUDA graph; the exchange has no host sync)")
     args = ap.parse_args()
     rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
     torch.cuda.set_device(local)
@@ -86,20 +88,58 @@ def main():
     model.embeddings["feedid"] = big
     reducer = GradientAllReducer(model)
     dense_params = [p for p in model.parameters() if not getattr(p, "_rank_local", False)]
-    opt_dense = torch.optim.Adam(dense_params, lr=1e-3)
+    opt_dense = torch.optim.Adam(dense_params, lr=1e-3, fused=True)
     from rank_b200.optim import RowwiseAdam
     opt_sparse = RowwiseAdam([big.weight], lr=1e-3)       # one kernel on the touched rows (SparseAdam's arithmetic)
     data = [synthetic.to_device(synthetic.bst_batch(B, T, seed=500 + 31 * rank + i, feed_rows=args.rows), dev)
             for i in range(4)]
     times = []
+    model.train()
+
+    def fwd_bwd(batch):
+        loss, _ = loss_of(model, batch)
+        loss.backward()
+        reducer.allreduce()
+        return loss
+
+    graph = None
+    if not args.eager:
+        # static inputs, 3 eager steps on a side stream, then capture: gather kernels, both all-to-alls, the block,
+        # the tower, the backward, the owner-side reduction and the dense all-reduce are one graph
+        static = {k: (v.clone() if torch.is_tensor(v) else {kk: vv.clone() for kk, vv in v.items()})
+                  for k, v in data[0].items()}
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            for _ in range(3):
+                opt_dense.zero_grad(set_to_none=True); opt_sparse.zero_grad(set_to_none=True)
+                fwd_bwd(static)
+        torch.cuda.current_stream().wait_stream(side)
+        torch.cuda.synchronize()
+        opt_dense.zero_grad(set_to_none=True); opt_sparse.zero_grad(set_to_none=True)
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph):
+            loss = fwd_bwd(static)
+        captured_touched = big.weight.touched_grad
+
+        def copy_in(dst, src):
+            for k, v in src.items():
+                if torch.is_tensor(v):
+                    dst[k].copy_(v, non_blocking=True)
+                else:
+                    copy_in(dst[k], v)
+
     for i in range(3 + args.steps):
         dist.barrier(); torch.cuda.synchronize()
         s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         s.record()
-        opt_dense.zero_grad(set_to_none=True); opt_sparse.zero_grad(set_to_none=True)
-        loss, _ = loss_of(model, data[i % 4])
-        loss.backward()
-        reducer.allreduce()
+        if graph is None:
+            opt_dense.zero_grad(set_to_none=True); opt_sparse.zero_grad(set_to_none=True)
+            loss = fwd_bwd(data[i % 4])
+        else:
+            copy_in(static, data[i % 4])
+            graph.replay()
+            big.weight.touched_grad = captured_touched        # refilled by the replay; the optimizer consumed the last one
         opt_dense.step(); opt_sparse.step()
         e.record(); torch.cuda.synchronize()
         if i >= 3:
@@ -112,6 +152,7 @@ def main():
             "n_gpus": world, "table_rows": args.rows, "shard_gb": big.weight.numel() * 4 / 1e9,
             "batch_per_gpu": B, "ms_per_step": float(t), "samples_per_s": world * B / (float(t) / 1e3),
             "step": "zero_grad+fwd+loss+bwd+grad allreduce+Adam(dense)+RowwiseAdam(shard)",
+            "launch": "eager" if graph is None else "cuda graph (fwd+bwd+all-to-alls+all-reduce) + eager optimizers",
             "parity_vs_replicated": {"ok_all_ranks": all(bool(g[0] > 0.5) for g in gathered),
                                      "logit_rel_err": max(float(g[1]) for g in gathered),
                                      "shard_grad_rel_err": max(float(g[2]) for g in gathered),

@@ -269,6 +269,58 @@ def test_bst_vs_oracle_wechat_sizes(wechat_vocab_dir, B, T, nhead, blocks, pool)
     compare(*_run_both(ours, ref, "BSTModel", synthetic.bst_batch(B, T)))
 
 
+@pytest.fixture
+def bst_tensor_block():
+    from rank_b200 import bst
+    bst.set_block_precision("bf16")
+    yield bst
+    bst.set_block_precision("fp32")
+
+
+@pytest.mark.parametrize("B,T,nhead,blocks,pool", [(8192, 20, 4, 1, "sum"), (2048, 20, 4, 1, "mean"), (300, 50, 8, 2, "sum"),
+                                                   (64, 128, 16, 1, "sum"), (333, 7, 1, 1, "sum"), (512, 20, 2, 2, "mean")])
+def test_bst_tensor_core_block_vs_oracle(wechat_vocab_dir, bst_tensor_block, B, T, nhead, blocks, pool):
+    """The block's projections / FFN on tcgen05 (set_block_precision("bf16")): the north star's bf16
+    tensor-core bar of 2e-2; the split-bf16 operands keep the measured error orders of magnitude inside."""
+    kw = dict(dropout_rate=0.0, nhead=nhead, num_transformer_blocks=blocks, max_seq_length=T, pooling_method=pool)
+    ours, ref = _pair("BSTModel", "OracleBST", wechat_vocab_dir, **kw)
+    o_outs, o_grads, r_outs, r_grads, _, grads64 = _run_both(ours, ref, "BSTModel", synthetic.bst_batch(B, T))
+    compare(o_outs, o_grads, r_outs, r_grads, 2e-2, grads64)
+    e_out = max(rel_err(o, r) for o, r in zip(o_outs, r_outs))
+    floor = 1e-3 * max(float(g.abs().max()) for g in r_grads.values())
+    e_grad = max(rel_err(o_grads[k], g, floor) for k, g in r_grads.items())
+    print(f"bst tensor block B={B} T={T} h={nhead}: outputs {e_out:.2e}, gradients {e_grad:.2e}")
+    assert e_out <= 1e-3                     # far inside the bar: logged so that a regression shows
+
+
+def test_bst_tensor_core_block_dropout_same_masks(bst_tensor_block):
+    """Dropout on the tensor-core block: same keep-bits as the fp32 kernels (oracle/philox.py), 2e-2 bar."""
+    from oracle import interactions as X
+    from oracle import philox
+    p, B, T, H = 0.1, 512, 20, 4
+    torch.manual_seed(3)
+    blk = rank_b200.BSTTransformer(16, H, T + 1, dropout=p).to(DEV).train()
+    gen = torch.Generator().manual_seed(11)
+    x = torch.randn(B, T, 16, generator=gen)
+    lens = torch.randint(1, T + 1, (B,), generator=gen)
+    pad = torch.arange(T).expand(B, T) >= lens.unsqueeze(1)
+    g = torch.randn(B, T, 16, generator=gen) / B
+    xa = x.to(DEV).requires_grad_()
+    y = blk(xa, xa, xa, key_padding_mask=pad.to(DEV))
+    seed, offset = (int(v) for v in blk._last_rng.tolist())
+    y.backward(g.to(DEV))
+    keep = torch.from_numpy(philox.bst_keep_masks(seed, offset, B * T, p).reshape(3, B, T, 16))
+    params = {k: v.detach().cpu().clone().requires_grad_() for k, v in blk.named_parameters()}
+    xr = x.clone().requires_grad_()
+    yr = X.bst_transformer_block(xr, pad, params, H, dropout_p=p, keep=keep)
+    yr.backward(g)
+    ref_grads = {k: v.grad for k, v in params.items()}
+    ref_grads["x"] = xr.grad
+    grads = {k: v.grad for k, v in blk.named_parameters()}
+    grads["x"] = xa.grad
+    compare([y], grads, [yr.detach()], ref_grads, 2e-2)
+
+
 def test_bst_default_dropout_trains_and_bad_heads(wechat_vocab_dir):
     """The reference's default (dropout_rate=0.1, BST/bst.py:164,417) trains: forward + backward run,
     two forwards draw different masks, eval mode is deterministic."""
