@@ -44,7 +44,8 @@ class RkDinArgs(C.Structure):
                 ("T", C.c_int32), ("att_off", C.c_int32), ("width", C.c_int32),
                 ("l2_from", C.c_int32), ("use_softmax", C.c_int32), ("precision", C.c_int32),
                 ("mlp", C.c_void_p),
-                ("B", C.c_int64)]
+                ("B", C.c_int64),
+                ("mlp_tiles", C.c_void_p)]
 
 
 class RkBstBlock(C.Structure):
@@ -111,6 +112,7 @@ PROTOTYPES = {
     "rk_bst_block_fwd": (_I, [_P, _I, _P, _P, _L, _P, _P, _L, _I, _P, _P, _I, _I, _P, _P]),
     "rk_bst_block_bwd": (_I, [_P, _I, _P, _P, _L, _P, _P, _L, _I, _P, _P, _I, _I, _P, _P, _P, _I, _P, _P]),
     "rk_din_mlp_floats": (_I, [_I]),
+    "rk_din_tile_bytes": (_I, []),
     "rk_din_fwd": (_I, [_P, _P, _P, _P, _P, _P, _P]),
     "rk_din_bwd": (_I, [_P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P]),
 }
@@ -151,7 +153,7 @@ class CallTimer:
     (bench.py's live per-call device times).  Use as a context manager; `summary()` after a
     synchronize gives {entry point: (calls, total ms)}."""
 
-    NO_KERNEL = ("rk_resunit_pack_floats", "rk_din_mlp_floats", "rk_afm_bwd_ctas", "rk_afm_tc_bwd_ctas", "rk_fwfm_bwd_ctas", "rk_dice_bn_max_batch", "rk_bst_grad_floats", "rk_bst_bwd_ctas", "rk_version", "rk_last_error", "rk_device_sm_count", "rk_launch_count", "rk_debug_spin",
+    NO_KERNEL = ("rk_resunit_pack_floats", "rk_din_mlp_floats", "rk_din_tile_bytes", "rk_afm_bwd_ctas", "rk_afm_tc_bwd_ctas", "rk_fwfm_bwd_ctas", "rk_dice_bn_max_batch", "rk_bst_grad_floats", "rk_bst_bwd_ctas", "rk_version", "rk_last_error", "rk_device_sm_count", "rk_launch_count", "rk_debug_spin",
                  "rk_plan_workspace_bytes", "rk_reduce_workspace_bytes")
 
     def __init__(self):

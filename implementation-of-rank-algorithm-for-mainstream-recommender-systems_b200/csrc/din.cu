@@ -37,6 +37,7 @@ struct DinParams {
     const int64_t* his_len;
     int32_t        T, D, att_off, width, l2_from, use_softmax;
     const float*   mlp;
+    const uint8_t* mlp_tiles;               // prologue-made operand tiles (tensor-core path), or NULL
     int64_t        B;
 };
 
@@ -567,7 +568,7 @@ struct TcFwdSmem {
     int *len;
     int64_t *ix_his, *ix_tgt, *ix_len, *ix_cat;    // the group's raw indices, landed by cp.async
     int16_t* colmap;                               // concat column -> categorical field; -1 dense/none, -2 target/attention
-    uint64_t *bar_mma;
+    uint64_t *bar_mma, *bar_w;
     uint32_t* tmem_slot;
     __device__ TcFwdSmem(uint8_t* base, int T, int F) {
         uint8_t* p = base;
@@ -586,6 +587,8 @@ struct TcFwdSmem {
         len = (int*)p;       p += sizeof(int) * kTcGroup;
         bar_mma = (uint64_t*)p;   p += 8;
         tmem_slot = (uint32_t*)p; p += 8;
+        bar_w = (uint64_t*)p;     p += 8;
+        p += 8;
         ix_his = (int64_t*)p;     p += sizeof(int64_t) * kTcGroup * T;
         ix_tgt = (int64_t*)p;     p += sizeof(int64_t) * kTcGroup;
         ix_len = (int64_t*)p;     p += sizeof(int64_t) * kTcGroup;
@@ -664,6 +667,44 @@ __device__ __forceinline__ void issue_idx(const DinParams& p, const TcFwdSmem& s
 }
 
 
+// The operand tiles of the per-call weights, laid out once per forward by din_weight_tiles_kernel in exactly
+// the swizzled split-bf16 image the kernels keep in shared memory, so that a CTA fetches them with ONE bulk
+// (TMA) copy instead of converting 24-32 KB itself (8 % of the forward, 9 % of the backward before):
+//   forward image   [W1 hi 8K][W1 lo 8K][W2 hi 4K][W2 lo 4K]                  (B operands [n][k], K-major)
+//   backward image  [W1^T hi 8K][W1^T lo 8K][W2^T hi 8K][W2^T lo 8K]
+constexpr uint32_t kTileFwdBytes = 2 * (64 * 128 + 32 * 128);
+constexpr uint32_t kTileBwdBytes = 2 * (64 * 128 + 64 * 128);
+
+__global__ void __launch_bounds__(256)
+din_weight_tiles_kernel(const float* __restrict__ mlp, uint8_t* __restrict__ tiles) {
+    const MlpLayout L(16);
+    uint8_t* f_w1 = tiles;            uint8_t* f_w1_lo = f_w1 + 64 * 128;
+    uint8_t* f_w2 = f_w1_lo + 64 * 128;  uint8_t* f_w2_lo = f_w2 + 32 * 128;
+    uint8_t* b_w1 = tiles + kTileFwdBytes;  uint8_t* b_w1_lo = b_w1 + 64 * 128;
+    uint8_t* b_w2 = b_w1_lo + 64 * 128;     uint8_t* b_w2_lo = b_w2 + 64 * 128;
+    // rows of a tile that no weight fills (backward W2^T: chunks 4..7 of a line) are never read by an MMA
+    for (int item = blockIdx.x * blockDim.x + threadIdx.x; item < 1536; item += gridDim.x * blockDim.x) {
+        float v[8];
+        if (item < 512) {                                   // forward W1[n][k]: 64 rows x 8 chunks
+            const int n = item >> 3, c = item & 7;
+            ld8(mlp + L.w1 + n * 64 + c * 8, v);
+            store_chunk_split(f_w1, f_w1_lo, n, c, v);
+        } else if (item < 768) {                            // forward W2[n][k]: 32 rows x 8 chunks
+            const int i = item - 512, n = i >> 3, c = i & 7;
+            ld8(mlp + L.w2 + n * 64 + c * 8, v);
+            store_chunk_split(f_w2, f_w2_lo, n, c, v);
+        } else if (item < 1024) {                           // backward W2^T[n][k]: 64 rows x 4 chunks
+            const int i = item - 768, n = i >> 2, c = i & 3;
+            ld8(mlp + L.w2t + n * 32 + c * 8, v);
+            store_chunk_split(b_w2, b_w2_lo, n, c, v);
+        } else {                                            // backward W1^T[c][n]: 64 rows x 8 chunks
+            const int i = item - 1024, n = i >> 3, c = i & 7;
+            ld8(mlp + L.w1t + n * 64 + c * 8, v);
+            store_chunk_split(b_w1, b_w1_lo, n, c, v);
+        }
+    }
+}
+
 __global__ void __launch_bounds__(kTcThreads)
 din_fwd_tc_kernel(const __grid_constant__ DinParams p, float* __restrict__ concat_all,
                   float* __restrict__ norm_out, float* __restrict__ att_w, uint32_t* __restrict__ masks,
@@ -686,19 +727,26 @@ din_fwd_tc_kernel(const __grid_constant__ DinParams p, float* __restrict__ conca
     // ---- one-time setup: barriers, TMEM, weights (fp32 -> split bf16, swizzled, K-major = as registered)
     if (tid == 0) {
         mbar_init(sm.bar_mma, 1);
+        mbar_init(sm.bar_w, 1);
+        if (p.mlp_tiles) {            // the four weight tiles in one bulk (TMA) copy: w1 | w1_lo | w2 | w2_lo are contiguous
+            mbar_expect_tx(sm.bar_w, kTileFwdBytes);
+            bulk_copy_g2s(sm.w1, p.mlp_tiles, kTileFwdBytes, sm.bar_w);
+        }
     }
     if (warp == 0) tmem_alloc(sm.tmem_slot, kTcTmemCols);
-    for (int item = tid; item < 64 * 8; item += kTcThreads) {         // W1[n][k]: 64 rows x 8 chunks
-        const int n = item >> 3, c = item & 7;
-        float v[8];
-        ld8(p.mlp + L.w1 + n * 64 + c * 8, v);
-        store_chunk_split(sm.w1, sm.w1_lo, n, c, v);
-    }
-    for (int item = tid; item < 32 * 8; item += kTcThreads) {         // W2[n][k]: 32 rows x 8 chunks
-        const int n = item >> 3, c = item & 7;
-        float v[8];
-        ld8(p.mlp + L.w2 + n * 64 + c * 8, v);
-        store_chunk_split(sm.w2, sm.w2_lo, n, c, v);
+    if (!p.mlp_tiles) {
+        for (int item = tid; item < 64 * 8; item += kTcThreads) {         // W1[n][k]: 64 rows x 8 chunks
+            const int n = item >> 3, c = item & 7;
+            float v[8];
+            ld8(p.mlp + L.w1 + n * 64 + c * 8, v);
+            store_chunk_split(sm.w1, sm.w1_lo, n, c, v);
+        }
+        for (int item = tid; item < 32 * 8; item += kTcThreads) {         // W2[n][k]: 32 rows x 8 chunks
+            const int n = item >> 3, c = item & 7;
+            float v[8];
+            ld8(p.mlp + L.w2 + n * 64 + c * 8, v);
+            store_chunk_split(sm.w2, sm.w2_lo, n, c, v);
+        }
     }
     for (int i = tid; i < kH1; i += kTcThreads) sm.vec[i] = __ldg(p.mlp + L.b1 + i);
     for (int i = tid; i < kH2; i += kTcThreads) {
@@ -717,6 +765,7 @@ din_fwd_tc_kernel(const __grid_constant__ DinParams p, float* __restrict__ conca
     fence_before();
     __syncthreads();
     fence_after();
+    if (p.mlp_tiles) mbar_wait(sm.bar_w, 0);
     const uint32_t tmem = *sm.tmem_slot;
     const float* b1 = sm.vec;
     const float* b2 = sm.vec + kH1;
@@ -1038,7 +1087,7 @@ struct TcBwdSmem {
     float *nrm, *gnrm;                             // [8]
     int64_t *ix_his, *ix_len;
     int* len;
-    uint64_t* bar;
+    uint64_t *bar, *bar_w;
     uint32_t* tmem_slot;
     static __host__ __device__ size_t pad16(size_t n) { return (n + 15) & ~(size_t)15; }
     __device__ TcBwdSmem(uint8_t* base, int T, int width) {
@@ -1068,10 +1117,11 @@ struct TcBwdSmem {
         wt = (float*)p;       p += sizeof(float) * kRows;
         len = (int*)p;        p += sizeof(int) * kSamples;
         bar = (uint64_t*)p;   p += 8;
+        bar_w = (uint64_t*)p; p += 8;
         tmem_slot = (uint32_t*)p;
     }
     static size_t bytes(int T, int width) {
-        return 1024 /* alignment slack */ + 2 * (128 * 128 + 2 * 64 * 128) + sizeof(float) * kRows * 16 +
+        return 16 + 1024 /* alignment slack */ + 2 * (128 * 128 + 2 * 64 * 128) + sizeof(float) * kRows * 16 +
                2 * pad16(sizeof(float) * kSamples * width) + pad16(sizeof(float) * kSamples * T) +
                pad16(sizeof(uint32_t) * kSamples * T * 3) + pad16(sizeof(int64_t) * kSamples * T) +
                sizeof(int64_t) * kSamples + sizeof(float) * (2 * kSamples + kH2 + 4 * kSamples * 16 + 8 + 2 * kRows) +
@@ -1139,25 +1189,35 @@ din_bwd_tc_kernel(const __grid_constant__ DinParams p, const float* __restrict__
     int64_t group = blockIdx.x;
     issue_group_bwd(p, sm, group, tid, concat_all, norm, att_w, masks, g_concat, g_norm);
 
-    if (tid == 0) mbar_init(sm.bar, 1);
-    if (warp == 0) tmem_alloc(sm.tmem_slot, kTcTmemCols);
-    for (int item = tid; item < 64 * 4; item += kTcThreads) {          // W2^T[n][k]: 64 rows x 32 k (4 chunks)
-        const int n = item >> 2, c = item & 3;
-        float v[8];
-        ld8(p.mlp + L.w2t + n * 32 + c * 8, v);
-        store_chunk_split(sm.w2, sm.w2_lo, n, c, v);
+    if (tid == 0) {
+        mbar_init(sm.bar, 1);
+        mbar_init(sm.bar_w, 1);
+        if (p.mlp_tiles) {            // w1 | w1_lo | w2 | w2_lo (W1^T, W2^T) in one bulk (TMA) copy
+            mbar_expect_tx(sm.bar_w, kTileBwdBytes);
+            bulk_copy_g2s(sm.w1, p.mlp_tiles + kTileFwdBytes, kTileBwdBytes, sm.bar_w);
+        }
     }
-    for (int item = tid; item < 64 * 8; item += kTcThreads) {          // W1^T[c][n]: 64 rows x 64 k
-        const int n = item >> 3, c = item & 7;
-        float v[8];
-        ld8(p.mlp + L.w1t + n * 64 + c * 8, v);
-        store_chunk_split(sm.w1, sm.w1_lo, n, c, v);
+    if (warp == 0) tmem_alloc(sm.tmem_slot, kTcTmemCols);
+    if (!p.mlp_tiles) {
+        for (int item = tid; item < 64 * 4; item += kTcThreads) {          // W2^T[n][k]: 64 rows x 32 k (4 chunks)
+            const int n = item >> 2, c = item & 3;
+            float v[8];
+            ld8(p.mlp + L.w2t + n * 32 + c * 8, v);
+            store_chunk_split(sm.w2, sm.w2_lo, n, c, v);
+        }
+        for (int item = tid; item < 64 * 8; item += kTcThreads) {          // W1^T[c][n]: 64 rows x 64 k
+            const int n = item >> 3, c = item & 7;
+            float v[8];
+            ld8(p.mlp + L.w1t + n * 64 + c * 8, v);
+            store_chunk_split(sm.w1, sm.w1_lo, n, c, v);
+        }
     }
     for (int i = tid; i < kH2; i += kTcThreads) sm.vec[i] = __ldg(p.mlp + L.w3 + i);
     fence_async_smem();
     fence_before();
     __syncthreads();
     fence_after();
+    if (p.mlp_tiles) mbar_wait(sm.bar_w, 0);
     const uint32_t tmem = *sm.tmem_slot;
     const float* w3 = sm.vec;
     const uint64_t a_desc[2]  = {umma_desc(smem_u32(sm.a)), umma_desc(smem_u32(sm.a_lo))};
@@ -1391,6 +1451,8 @@ extern "C" {
 
 int rk_din_mlp_floats(int D) { return rk::MlpLayout(D).total; }
 
+int rk_din_tile_bytes(void) { return (int)(rk::tc::kTileFwdBytes + rk::tc::kTileBwdBytes); }
+
 static int din_pack(const rk_din_args_t* a, rk::DinParams* p) {
     using namespace rk;
     RK_CHECK_ARG(a, "din: args is NULL");
@@ -1417,6 +1479,8 @@ static int din_pack(const rk_din_args_t* a, rk::DinParams* p) {
     p->T = a->T;  p->D = D;  p->att_off = a->att_off;  p->width = a->width;
     p->l2_from = a->l2_from;  p->use_softmax = a->use_softmax;
     p->mlp = a->mlp;  p->B = a->B;
+    p->mlp_tiles = (const uint8_t*)a->mlp_tiles;
+    RK_CHECK_ARG(((uintptr_t)a->mlp_tiles % 128) == 0, "din: mlp_tiles must be 128-byte aligned");
     RK_CHECK_ARG(p->width > 0 && p->att_off + D <= p->width && p->tgt_off + D <= p->width, "din: bad layout");
     return 0;
 }
@@ -1452,6 +1516,10 @@ int rk_din_fwd(const rk_din_args_t* args, float* concat_all, float* norm, float*
         // history lengths; dynamic draws keep the balance and pay the per-CTA setup once.
         const int n_groups = (int)ceil_div(p.B, tc::kTcGroup);
         const int grid_tc = n_groups < sm_count() * per_sm ? n_groups : sm_count() * per_sm;
+        if (p.mlp_tiles) {            // both directions' operand tiles, once per forward
+            tc::din_weight_tiles_kernel<<<6, 256, 0, (cudaStream_t)stream_>>>(p.mlp, (uint8_t*)args->mlp_tiles);
+            RK_LAUNCH_CHECK();
+        }
         kernel<<<grid_tc, tc::kTcThreads, smem_tc, (cudaStream_t)stream_>>>(
             p, concat_all, norm, att_w, relu_masks, err_flag);
         RK_LAUNCH_CHECK();

@@ -167,6 +167,18 @@ __device__ __forceinline__ void cp_async16(const void* dst_smem, const void* src
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
 
+// One bulk (TMA) copy global -> shared of `bytes` (a multiple of 16, both sides 16-byte aligned), completing on
+// an mbarrier: the issuing thread first announces the byte count (arrive.expect_tx), everybody then waits on
+// the barrier's phase.  Used for operand tiles that a prologue kernel has already laid out in their swizzled
+// shared-memory image: one instruction instead of a convert-and-store loop per CTA.
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_copy_g2s(void* dst_smem, const void* src, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(smem_u32(dst_smem)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+
 // instruction-descriptor bits selecting MN-major A / B
 constexpr uint32_t kUmmaAMn = 1u << 15;
 constexpr uint32_t kUmmaBMn = 1u << 16;

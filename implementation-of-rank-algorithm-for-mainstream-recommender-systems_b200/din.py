@@ -132,7 +132,12 @@ def _din_args(cat_tables, cat_idx, cat_offsets, dense_cols, target_w, target_idx
         raise ValueError("packed attention weights have the wrong size")
     a.mlp = mlp.data_ptr()
     a.B = int(hi.shape[0])
-    return a, (fields, keep, cols, col_ptrs, tw, ti, hw, hi, hl, mlp)
+    tiles = None
+    if precision == "bf16":
+        # scratch for the operand tiles the forward's prologue makes and both directions fetch by bulk (TMA) copy
+        tiles = torch.empty(_lib.load().rk_din_tile_bytes(), dtype=torch.uint8, device=hw.device)
+        a.mlp_tiles = tiles.data_ptr()
+    return a, (fields, keep, cols, col_ptrs, tw, ti, hw, hi, hl, mlp, tiles)
 
 
 class _DinHotPath(torch.autograd.Function):

@@ -125,3 +125,58 @@ class PackedBatch:
             other._copied = torch.cuda.Event()
             other._copied.record(torch.cuda.current_stream(self.dev.device))
         return self.device_views
+
+
+class Prefetcher:
+    """Double-buffered input pipeline on top of PackedBatch: the host -> device copy of batch k+1 runs on a
+    copy stream while step k computes; at the start of step k+1 one device -> device copy moves it into the
+    step's static inputs (fixed addresses, so a captured CUDA graph keeps working).
+
+        pf = Prefetcher(static)                   # static: the PackedBatch whose device views the model reads
+        slot = pf.submit(host_batches[0])
+        for k in range(steps):
+            nxt = pf.submit(host_batches[k + 1])  # starts now, overlaps step k
+            pf.consume(slot)                      # waits for ITS copy, then D2D into static.dev
+            step()
+            slot = nxt
+
+    `after` (a CUDA event) delays a submitted copy until that point of another stream's timeline."""
+
+    def __init__(self, static: PackedBatch):
+        self.static = static
+        dev = static.dev.device
+        self.stage = [torch.empty_like(static.dev), torch.empty_like(static.dev)]
+        self.stream = torch.cuda.Stream(device=dev)
+        self.ready = [None, None]      # copy finished (recorded on the copy stream)
+        self.freed = [None, None]      # stage buffer consumed (recorded on the consumer's stream)
+        self.k = 0
+
+    def submit(self, packed: PackedBatch, after=None) -> int:
+        if packed.layout != self.static.layout:
+            raise ValueError("Prefetcher.submit: layouts differ")
+        slot = self.k % 2
+        self.k += 1
+        if after is not None:
+            self.stream.wait_event(after)
+        if self.freed[slot] is not None:
+            self.stream.wait_event(self.freed[slot])
+        with torch.cuda.stream(self.stream):
+            self.stage[slot].copy_(packed.host, non_blocking=True)
+            ev = torch.cuda.Event()
+            ev.record(self.stream)
+        self.ready[slot] = ev
+        packed._copied = ev            # PackedBatch.fill waits for it before rewriting the pinned buffer
+        return slot
+
+    def wait(self, slot: int) -> None:
+        """Make the current stream wait for the copy of `slot` (without consuming it)."""
+        torch.cuda.current_stream(self.static.dev.device).wait_event(self.ready[slot])
+
+    def consume(self, slot: int):
+        main = torch.cuda.current_stream(self.static.dev.device)
+        main.wait_event(self.ready[slot])
+        self.static.dev.copy_(self.stage[slot], non_blocking=True)
+        ev = torch.cuda.Event()
+        ev.record(main)
+        self.freed[slot] = ev
+        return self.static.device_views

@@ -196,9 +196,16 @@ typedef struct rk_din_args {
                                          bf16 operands / fp32 TMEM accumulators (D = 16, 2e-2 bar) */
     const float*        mlp;
     int64_t             B;
+    void*               mlp_tiles;    /* RK_DIN_BF16_TENSOR only, may be NULL: rk_din_tile_bytes() bytes of
+                                         scratch (128-byte aligned) that rk_din_fwd fills with the split-bf16
+                                         operand tiles of `mlp` for both directions (one small prologue launch);
+                                         every CTA then fetches its weights with one bulk (TMA) copy instead of
+                                         converting them itself.  rk_din_bwd reads what the forward wrote: pass
+                                         the same buffer, untouched in between. */
 } rk_din_args_t;
 #define RK_DIN_FP32 0
 #define RK_DIN_BF16_TENSOR 1
+int rk_din_tile_bytes(void);
 
 int rk_din_mlp_floats(int D);
 int rk_din_fwd(const rk_din_args_t* args, float* concat_all, float* norm, float* att_w,

@@ -102,6 +102,10 @@ def main():
         reducer.allreduce()
         return loss
 
+    def stage(msg):
+        if os.environ.get("RANK_B200_TRACE"):
+            print(f"[rank {rank}] {msg}", file=sys.stderr, flush=True)
+
     graph = None
     if not args.eager:
         # static inputs, 3 eager steps on a side stream, then capture: gather kernels, both all-to-alls, the block,
@@ -116,11 +120,14 @@ def main():
                 fwd_bwd(static)
         torch.cuda.current_stream().wait_stream(side)
         torch.cuda.synchronize()
+        stage("warm-up done")
         opt_dense.zero_grad(set_to_none=True); opt_sparse.zero_grad(set_to_none=True)
         graph = torch.cuda.CUDAGraph()
         with torch.cuda.graph(graph):
             loss = fwd_bwd(static)
         captured_touched = big.weight.touched_grad
+        torch.cuda.synchronize()
+        stage("capture done")
 
         def copy_in(dst, src):
             for k, v in src.items():
@@ -133,6 +140,7 @@ def main():
         dist.barrier(); torch.cuda.synchronize()
         s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         s.record()
+        stage(f"step {i}")
         if graph is None:
             opt_dense.zero_grad(set_to_none=True); opt_sparse.zero_grad(set_to_none=True)
             loss = fwd_bwd(data[i % 4])
@@ -158,6 +166,10 @@ def main():
                                      "shard_grad_rel_err": max(float(g[2]) for g in gathered),
                                      "other_grad_rel_err": max(float(g[3]) for g in gathered)},
             "loss": float(loss.detach())}), flush=True)
+    # a captured graph holding NCCL work must be gone before the communicator is (the exit otherwise hangs)
+    graph = None
+    torch.cuda.synchronize()
+    dist.barrier()
     dist.destroy_process_group()
 
 

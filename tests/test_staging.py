@@ -72,3 +72,30 @@ def test_refill_waits_for_the_previous_copy():
     want = dict(_leaves(a))
     for k, v in snap.items():
         assert torch.equal(v.cpu(), want[k]), k
+
+
+@pytest.mark.gpu
+def test_prefetcher_delivers_every_batch_in_order():
+    """Double-buffered prefetch: copy k+1 is in flight on the copy stream while step k (a busy main stream)
+    runs; every step must see exactly its own batch in the static device views."""
+    from rank_b200 import _lib
+    from rank_b200.staging import Prefetcher
+    dev = torch.device("cuda", 0)
+    batches = [synthetic.side_batch(2048, 10 + i) for i in range(5)]
+    hosts = [PackedBatch.like(batches[0], dev).fill(b) for b in batches]
+    static = PackedBatch.like(batches[0], dev)
+    pf = Prefetcher(static)
+    lib = _lib.load()
+    seen = []
+    slot = pf.submit(hosts[0])
+    for k in range(5):
+        nxt = pf.submit(hosts[k + 1]) if k + 1 < 5 else None
+        views = pf.consume(slot)
+        _lib.check(lib.rk_debug_spin(2000, _lib.stream_ptr()), "rk_debug_spin")      # the "step": 2 ms of work
+        seen.append({key: v.clone() for key, v in dict(_leaves(views)).items()})
+        slot = nxt
+    torch.cuda.synchronize()
+    for k, snap in enumerate(seen):
+        want = dict(_leaves(batches[k]))
+        for key, v in snap.items():
+            assert torch.equal(v.cpu(), want[key]), (k, key)
