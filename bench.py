@@ -662,6 +662,9 @@ def measure_ours(args, wl, key, world, rank, local, dev, primary):
         evs = []
         loss = None
         pf = Prefetcher(st.packed) if from_host else None
+        # the step's result is read back into PINNED memory: a pageable destination would turn the D2H copy into a
+        # host synchronisation and expose the host's per-step work (weight draws, graph launch) on the GPU timeline
+        loss_host = torch.empty(max(n_steps, 1), dtype=torch.float32, pin_memory=True) if from_host else None
         slot = None
         for i in range(n_steps):
             flush.fill_(i & 0xff)           # evict L2 between steps; outside the timed events
@@ -679,7 +682,7 @@ def measure_ours(args, wl, key, world, rank, local, dev, primary):
                 nxt = pf.submit(pool[(i + 1) % n_pool], after=start) if i + 1 < n_steps else None
                 pf.consume(slot)                                             # D2D into the graph's static inputs
                 loss = st.run(first_seed + i)
-                loss.detach().to("cpu", non_blocking=True)      # D2H read of the step's result
+                loss_host[i:i + 1].copy_(loss.detach().reshape(1), non_blocking=True)      # D2H read of the step's result
                 if nxt is not None:
                     pf.wait(nxt)
                 e.record()

@@ -597,10 +597,11 @@ int rk_bst_block_bwd(const rk_bst_block_t* blk, int nhead, const float* table, c
     RK_CHECK_ARG(n_ctas == rk_bst_bwd_ctas(B, T, blk->precision), "bst_bwd: n_ctas %d != rk_bst_bwd_ctas", n_ctas);
     if (B == 0) return 0;
     cudaStream_t s = (cudaStream_t)stream_;
-    // RK_BST_BF16_TENSOR: the backward of the tensor-core block is this fp32 kernel (it recomputes the forward
-    // in fp32; the two agree far inside the 2e-2 bar of that path)
-    RK_CHECK_ARG(blk->precision == RK_BST_FP32 || blk->precision == RK_BST_BF16_TENSOR,
-                 "bst_bwd: unknown precision %d", blk->precision);
+    if (blk->precision == RK_BST_BF16_TENSOR) {
+        if (int rc2 = bst_tc_bwd(p, nhead, g_y, g_pool, g_pool_ld, g_x, partials, n_ctas, err_flag, s)) return rc2;
+        return launch_reduce_partials(partials, n_ctas, rk_bst_grad_floats(T), g_params, s);
+    }
+    RK_CHECK_ARG(blk->precision == RK_BST_FP32, "bst_bwd: unknown precision %d", blk->precision);
     int rc = -1;
     switch (nhead) {
         case 1:  rc = bst_launch_bwd<1>(p, g_y, g_pool, g_pool_ld, g_x, partials, n_ctas, err_flag, s); break;

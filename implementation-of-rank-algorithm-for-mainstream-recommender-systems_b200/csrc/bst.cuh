@@ -182,4 +182,7 @@ int bst_tc_bwd_ctas(int64_t B, int T);
 int bst_tc_fwd(const BstParams& p, int nhead, float* y_out, float* pool_out, int pool_ld, int32_t* err_flag,
                cudaStream_t s);
 
+int bst_tc_bwd(const BstParams& p, int nhead, const float* g_y, const float* g_pool, int g_pool_ld, float* g_x,
+               float* partials, int n_ctas, int32_t* err_flag, cudaStream_t s);
+
 }  // namespace rk
