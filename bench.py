@@ -679,9 +679,11 @@ def measure_ours(args, wl, key, world, rank, local, dev, primary):
                 start.record()
                 if slot is None:
                     slot = pf.submit(pool[i % n_pool], after=start)          # the first step waits for its own copy
-                nxt = pf.submit(pool[(i + 1) % n_pool], after=start) if i + 1 < n_steps else None
                 pf.consume(slot)                                             # D2D into the graph's static inputs
                 loss = st.run(first_seed + i)
+                # the next batch's copy is queued AFTER this step's own small upload (the per-call weights): the one
+                # host-to-device copy engine is a FIFO, a 4 MB prefetch in front of it would delay the step by ~100 us
+                nxt = pf.submit(pool[(i + 1) % n_pool], after=start) if i + 1 < n_steps else None
                 loss_host[i:i + 1].copy_(loss.detach().reshape(1), non_blocking=True)      # D2H read of the step's result
                 if nxt is not None:
                     pf.wait(nxt)
