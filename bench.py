@@ -269,13 +269,14 @@ WORKLOADS = {"deepfm": DeepFMWorkload, "fwfm": FwFMWorkload, "dcn": DCNWorkload,
 
 
 # ------------------------------------------------------------------------------- helpers
-# fused forward + backward kernels whose ncu dram__bytes (profiles/r01_traffic.json, one
+# fused forward + backward kernels whose ncu dram__bytes (profiles/r0N_traffic.json, one
 # `ncu --set full` capture per kernel) are reported as roofline.traffic
 TRAFFIC_KERNELS = {
     "din_softmax_tc": ("din_fwd_tc_kernel", "din_bwd_tc_kernel"),
     "dcn": ("crossnet_fwd_kernel", "crossnet_bwd_kernel"), "afm_fp32": ("afm_fwd_kernel", "afm_bwd_kernel"),
     "bst": ("bst_fwd_kernel", "bst_bwd_kernel"), "din_tc": ("din_fwd_tc_kernel", "din_bwd_tc_kernel"),
     "afm": ("afm_fwd_tc_kernel", "afm_bwd_tc_kernel"), "fwfm": ("fwfm_fwd_kernel", "fwfm_bwd_kernel"),
+    "bst_tc": ("bst_fwd_tc_kernel", "bst_bwd_tc_kernel"),
 }
 
 
@@ -658,9 +659,12 @@ def measure_ours(args, wl, key, world, rank, local, dev, primary):
             torch.distributed.barrier()
         torch.cuda.synchronize()
 
+    host_loop = [0.0]
+
     def timed(st, n_steps, first_seed, from_host):
         evs = []
         loss = None
+        host_t0 = time.perf_counter()
         pf = Prefetcher(st.packed) if from_host else None
         # the step's result is read back into PINNED memory: a pageable destination would turn the D2H copy into a
         # host synchronisation and expose the host's per-step work (weight draws, graph launch) on the GPU timeline
@@ -695,6 +699,7 @@ def measure_ours(args, wl, key, world, rank, local, dev, primary):
                 loss = st.run(first_seed + i)
                 e.record()
             evs.append((s, e))
+        host_loop[0] = (time.perf_counter() - host_t0) / max(n_steps, 1) * 1e3     # host time to queue one step
         torch.cuda.synchronize()
         return sum(s.elapsed_time(e) for s, e in evs), float(loss.detach().reshape(-1)[0])
 
@@ -712,6 +717,7 @@ def measure_ours(args, wl, key, world, rank, local, dev, primary):
         barrier()
         clocks.mark()
         total_ms, last_loss = timed(stepper, steps, 10_000, from_host=False)
+        host_value_ms = host_loop[0]
         barrier()
         clocks.mark()
     launches = stepper_launches_per_replay(stepper, lib) * steps if stepper.graph is not None else None
@@ -723,6 +729,7 @@ def measure_ours(args, wl, key, world, rank, local, dev, primary):
         barrier()                                # (the samplers start at different speeds on different ranks)
         clocks_e2e.mark()
         e2e_ms, _ = timed(stepper, steps, 20_000, from_host=True)
+        host_e2e_ms = host_loop[0]
         barrier()
         clocks_e2e.mark()
     clocks.absorb(clocks_e2e)
@@ -735,7 +742,9 @@ def measure_ours(args, wl, key, world, rank, local, dev, primary):
 
     # ---- the hot path alone: a CUDA graph of model.hot_path forward + backward (incl. the embedding-
     # gradient reduction) against fixed cotangents; same static inputs, same L2 flush between replays
-    hot = Stepper(model, wl, pool[0], True, None, hot_only=True)
+    # (--no-graph, the profiling mode: the hot path runs eagerly too — a capture after eager steps on the legacy
+    # stream is refused by CUDA, and ncu wants plain launches anyway)
+    hot = Stepper(model, wl, pool[0], not args.no_graph, None, hot_only=True)
     for i in range(3):
         hot.load(pool[i % n_pool])
         hot.run(i)
@@ -783,6 +792,7 @@ def measure_ours(args, wl, key, world, rank, local, dev, primary):
         "dtype": wl.dtype, "clocks": clocks.summary(),
         "gpu_launches": int(launches) if launches is not None else None,
         "h2d_bytes": pool[0].nbytes, "h2d_payload": pool[0].payload_bytes, "fill_ms": fill_ms,
+        "host_queue_ms": {"value_loop": host_value_ms, "e2e_loop": host_e2e_ms},
         "graph": stepper.graph is not None,
         "roofline": {
             "bound": wl.bound, "achieved": achieved, "peak": pk["hbm_gbs"], "unit": "GB/s",
@@ -854,7 +864,10 @@ def run_ours(args, wl):
                             "and end events of step i (the first step waits for its own copy), so all K copies lie "
                             "inside timed brackets.  Collating a dict batch into the pinned buffer "
                             "(PackedBatch.fill, host side) is outside the events",
-                    "host_fill_ms_per_batch": r["fill_ms"]},
+                    "host_fill_ms_per_batch": r["fill_ms"],
+                    # host time to QUEUE one step (weight draws, copies, graph launch): when it approaches the
+                    # device time of a step the loop is host-bound and the brackets hold idle device time
+                    "host_queue_ms_per_step": r["host_queue_ms"]},
             "gpu_launches": r["gpu_launches"],
             "roofline": r["roofline"],
             "hotpath_calls_eager_events": r["hotpath_calls_eager_events"],

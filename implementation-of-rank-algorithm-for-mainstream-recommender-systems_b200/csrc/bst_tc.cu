@@ -18,6 +18,7 @@
 #include <string.h>
 #include "bst.cuh"
 #include "umma.cuh"
+#include "prof.cuh"
 
 namespace rk {
 namespace tc {
@@ -174,7 +175,7 @@ bst_fwd_tc_kernel(const __grid_constant__ BstParams p, float* __restrict__ y_out
         for (int i = 0; i < 16; ++i) ctx[i] = 0.f;
         if (on) {
             float mh[H], lh[H];
-            bst_attend<H>(q, sm.ks, sm.vs, s * T, L, ctx, mh, lh);
+            bst_attend<H, true>(q, sm.ks, sm.vs, s * T, L, ctx, mh, lh);
         }
         const BstDrop drop = bst_drop_masks(p, b * T + t);
         store_slot_split(sm.a_hi, sm.a_lo, tid, 0, ctx);
@@ -322,12 +323,13 @@ __device__ __forceinline__ void mma_proj_acc(uint32_t d_tmem, const uint64_t (&a
 }
 
 // region (+)= (G_hi + G_lo)^T . X_hi over the 128 rows of the tile: both operands MN-major (lines = rows = K)
-__device__ __forceinline__ void mma_wgrad(uint32_t d_tmem, uint32_t g_hi, uint32_t g_lo, uint32_t x_hi, bool first_tile) {
+// (descriptors of line 0 of the three tiles, made once; 16 lines further = +2048 bytes = +128 in the address field)
+__device__ __forceinline__ void mma_wgrad(uint32_t d_tmem, uint64_t g_hi_mn, uint64_t g_lo_mn, uint64_t x_hi_mn, bool first_tile) {
 #pragma unroll
     for (int part = 0; part < 2; ++part)
 #pragma unroll
         for (int kk = 0; kk < 8; ++kk)
-            umma_bf16(d_tmem, umma_desc_mn((part ? g_lo : g_hi) + kk * 2048, 128 * 128), umma_desc_mn(x_hi + kk * 2048, 128 * 128),
+            umma_bf16(d_tmem, (part ? g_lo_mn : g_hi_mn) + 128u * kk, x_hi_mn + 128u * kk,
                       umma_idesc(64) | kUmmaAMn | kUmmaBMn, (first_tile && part == 0 && kk == 0) ? 0u : 1u);
 }
 
@@ -339,6 +341,7 @@ bst_bwd_tc_kernel(const __grid_constant__ BstParams p, const float* __restrict__
     extern __shared__ uint8_t smem_raw_bt[];
     uint8_t* base = smem_raw_bt + ((1024u - (smem_u32(smem_raw_bt) & 1023u)) & 1023u);
     BtBwdSmem sm(base, p.T, H);
+    PROF_DECL
     const int tid = threadIdx.x, warp = tid >> 5, T = p.T;
     const float scale = 1.0f / sqrtf((float)DH);
 
@@ -368,7 +371,8 @@ bst_bwd_tc_kernel(const __grid_constant__ BstParams p, const float* __restrict__
     const uint64_t wa_desc[2]  = {umma_desc(smem_u32(sm.wa_hi)), umma_desc(smem_u32(sm.wa_lo))};
     const uint64_t wb_desc[2]  = {umma_desc(smem_u32(sm.wb_hi)), umma_desc(smem_u32(sm.wb_lo))};
     const uint64_t wat_desc[2] = {umma_desc(smem_u32(sm.wat_hi)), umma_desc(smem_u32(sm.wat_lo))};
-    const uint32_t xh = smem_u32(sm.x_hi), gh = smem_u32(sm.g_hi), lo_addr = smem_u32(sm.lo);
+    const uint64_t xh = umma_desc_mn(smem_u32(sm.x_hi), 128 * 128), gh = umma_desc_mn(smem_u32(sm.g_hi), 128 * 128),
+                   lo_addr = umma_desc_mn(smem_u32(sm.lo), 128 * 128);
     uint32_t ph = 0;
     float pacc[16];
 #pragma unroll
@@ -400,6 +404,7 @@ bst_bwd_tc_kernel(const __grid_constant__ BstParams p, const float* __restrict__
         const int s = on ? tid / T : 0, t = on ? tid - s * T : 0;
         const int64_t b = b0 + s;
         const int row0 = s * T;
+        PROF(0); PROF_COUNT(12);
         // ---- A. recompute the forward
         float qk[16];
         int L = 0;
@@ -437,16 +442,18 @@ bst_bwd_tc_kernel(const __grid_constant__ BstParams p, const float* __restrict__
         }
         fence_before();
         __syncthreads();
+        PROF(1);
         float ctx[16];
 #pragma unroll
         for (int i = 0; i < 16; ++i) ctx[i] = 0.f;
         if (on) {
             float q[16], mh[H], lh[H];
             load_row(sm.qs + tid * kBstLd, q);
-            bst_attend<H>(q, sm.ks, sm.vs, row0, L, ctx, mh, lh);
+            bst_attend<H, true>(q, sm.ks, sm.vs, row0, L, ctx, mh, lh);
 #pragma unroll
             for (int h = 0; h < H; ++h) { sm.mrow[tid * H + h] = mh[h]; sm.lrow[tid * H + h] = 1.0f / lh[h]; }
         }
+        PROF(2);
         const BstDrop drop = bst_drop_masks(p, b * T + t);
         store_slot_split(sm.x_hi, sm.lo, tid, 2, ctx);                    // slot 2: ctx, kept for stage B
         round_trip([&]() { mma_proj(tmem + 48, x_desc, 2, wa_desc, MO); });
@@ -481,6 +488,7 @@ bst_bwd_tc_kernel(const __grid_constant__ BstParams p, const float* __restrict__
             for (int i = 0; i < 16; ++i) z[i] = o1[i] + f[i];
             rstd2 = layer_norm16(z, sm.vec + VG2 * 16, sm.vec + VBE2 * 16, zh2, y);
         }
+        PROF(3);
         // ---- B. upstream gradient, LayerNorm 2 backward, FFN backward
         float dz[16];
         {
@@ -523,6 +531,7 @@ bst_bwd_tc_kernel(const __grid_constant__ BstParams p, const float* __restrict__
         tmem_ld16(my_tmem + 48, do1);
 #pragma unroll
         for (int i = 0; i < 16; ++i) do1[i] = on ? do1[i] + dz[i] : 0.f;
+        PROF(4);
         // ---- C. LayerNorm 1 backward, output projection backward
         float dz1[16];
         {
@@ -559,6 +568,7 @@ bst_bwd_tc_kernel(const __grid_constant__ BstParams p, const float* __restrict__
             store_row(sm.dc + tid * kBstLd, on ? dctx : zero16);
         }
         __syncthreads();
+        PROF(5);
         // ---- D. attention backward: as a query (dq) and as a key (dk, dv)
         float dq[16], dk[16], dv[16];
 #pragma unroll
@@ -584,7 +594,7 @@ bst_bwd_tc_kernel(const __grid_constant__ BstParams p, const float* __restrict__
                         sc = fmaf(q[h * DH + j], kr[h * DH + j], sc);
                         dA = fmaf(dctx[h * DH + j], vr[h * DH + j], dA);
                     }
-                    const float a  = expf(sc * scale - mq[h]) * ilq[h];
+                    const float a  = __expf(sc * scale - mq[h]) * ilq[h];
                     const float dS = a * (dA - dlq[h]) * scale;
 #pragma unroll
                     for (int j = 0; j < DH; ++j) dq[h * DH + j] = fmaf(dS, kr[h * DH + j], dq[h * DH + j]);
@@ -604,7 +614,7 @@ bst_bwd_tc_kernel(const __grid_constant__ BstParams p, const float* __restrict__
                             sc = fmaf(qr[h * DH + j], kme[h * DH + j], sc);
                             dA = fmaf(dr[h * DH + j], vme[h * DH + j], dA);
                         }
-                        const float a  = expf(sc * scale - sm.mrow[rq * H + h]) * sm.lrow[rq * H + h];
+                        const float a  = __expf(sc * scale - sm.mrow[rq * H + h]) * sm.lrow[rq * H + h];
                         const float dS = a * (dA - sm.delta[rq * H + h]) * scale;
 #pragma unroll
                         for (int j = 0; j < DH; ++j) {
@@ -615,6 +625,7 @@ bst_bwd_tc_kernel(const __grid_constant__ BstParams p, const float* __restrict__
                 }
             }
         }
+        PROF(6);
         // ---- E. projection backward, input gradient, position-table gradient
         {
             float x[16];
@@ -665,7 +676,10 @@ bst_bwd_tc_kernel(const __grid_constant__ BstParams p, const float* __restrict__
         }
         first_tile = false;
         __syncthreads();
+        PROF(7);
     }
+    PROF(8);
+    PROF_END;
 
     // ---- per-CTA partials: the position rows from registers, everything else out of TMEM (lanes 0..63)
     float* out = partials + (int64_t)blockIdx.x * (T * 16 + 6 * 256 + 160);

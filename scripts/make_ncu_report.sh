@@ -1,6 +1,6 @@
 #!/bin/bash
 # profiles/<tag>_ncu_summary.md + raw csv + traffic json from gpurun_out/<tag>/ncu (see round_measure.sh)
-tag=${1:-r01}
+tag=${1:-r02}
 src=gpurun_out/$tag/ncu
 out=profiles/${tag}_ncu_summary.md
 S=scripts/summarize_ncu.py
@@ -10,7 +10,7 @@ cat <<HDR
 
 Commands (\`scripts/round_measure.sh\`, run through \`gpurun\`, each after the same command exited 0 without ncu):
 \`\`\`
-python bench.py --workload W --no-graph --steps 2 --warmup 3 --no-cpu-baseline
+python bench.py --workload W --no-graph --steps 2 --warmup 3 --no-cpu-baseline --no-others --no-aten
 ncu --metrics gpu__time_duration.sum --clock-control none -c 6000 --csv --log-file launches_W.csv <same>
 ncu --set full --clock-control none --import-source on -k regex:<kernels> -s N -c M -o full_W <same>
 \`\`\`
@@ -26,13 +26,17 @@ echo; echo "## Launch list — DIN step, tensor-core activation unit (eager, B =
 python $S launches $src/launches_din_tc.csv din_fwd_tc_kernel
 echo; echo "## Launch list — AFM step, tensor-core attention (eager, B = 8192, F = 10, D = 32, A = 128)"; echo
 python $S launches $src/launches_afm.csv afm_fwd_tc_kernel
-for w in dcn din_tc afm fwfm; do
+echo; echo "## Launch list — BST step, tensor-core block (eager, B = 8192, T = 20, 4 heads)"; echo
+python $S launches $src/launches_bst_tc.csv bst_fwd_tc_kernel
+for w in din_tc bst_tc dcn; do
   echo; echo "## Full capture — $w"
   python $S full $src/full_$w.ncu-rep
   ncu -i $src/full_$w.ncu-rep --page raw --csv > profiles/${tag}_full_$w.raw.csv 2>/dev/null
 done
-cp $src/launches_dcn.csv profiles/${tag}_launches_dcn.csv
-cp $src/launches_din_tc.csv profiles/${tag}_launches_din_tc.csv
-cp $src/launches_afm.csv profiles/${tag}_launches_afm.csv
+for w in dcn din_tc afm bst_tc; do cp $src/launches_$w.csv profiles/${tag}_launches_$w.csv; done
+if [ -f gpurun_out/${tag}_phase_bst_tc_bwd.txt ]; then
+  echo; echo "## Phase profile — \`tc::bst_bwd_tc_kernel\` (\`scripts/phase_profile.py run bst_tc bwd\`, clock64 of thread 0 per phase, B = 8192)"; echo
+  echo '```'; grep -v Warning gpurun_out/${tag}_phase_bst_tc_bwd.txt | tail -12; echo '```'
+fi
 } > $out.new
 echo "wrote $out.new"

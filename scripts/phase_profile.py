@@ -17,6 +17,9 @@ PHASES = {
                         "weights", "pooling", "assembly"],
     ("bst", "bwd"): ["setup", "A1 recompute q/k/v", "A2 attention+ffn fwd", "B ln2 bwd", "C ffn bwd", "D ln1+wo bwd",
                      "E attention bwd", "F1 dq/dk/dv outer", "F2 input grad", "F3 pos grad", "final"],
+    ("bst_tc", "bwd"): ["tile setup", "A1 x -> q/k/v round trip", "A2 attention fwd", "A3 Wo, W1, W2 round trips + LN",
+                        "B ln2 bwd, W2^T, W1^T + stage A", "C ln1 bwd, Wo^T + stage B", "D attention bwd",
+                        "E Wq/k/v^T + stage C, dx, pos grad", "exit"],
     ("afm", "fwd"): ["setup", "wait rows", "build A1", "mma1+prefetch", "epilogue", "softmax", "pool store", "pool sum"],
     ("afm", "bwd"): ["setup", "wait rows", "build A1", "mma1+prefetch", "epilogue1+mask", "softmax+g_s", "X line",
                         "mma2+mma3", "epilogue2", "g_rows", "final"],

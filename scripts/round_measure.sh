@@ -28,7 +28,7 @@ full() {  # workload, kernel regex, skip, count
 }
 if [ "$part" = full ] || [ "$part" = all ]; then
   full din_tc 'din_(fwd|bwd)_tc_kernel|din_weight_tiles' 6 3
-  full bst_tc 'bst_(fwd_tc|bwd)_kernel' 4 2
+  full bst_tc 'bst_(fwd|bwd)_tc_kernel' 4 2
   full dcn 'crossnet_(fwd|bwd)_kernel|direct_reduce' 9 3
 fi
 ls -la $out/bench $out/ncu
