@@ -516,13 +516,19 @@ class Stepper:
         `from_host`, device -> device otherwise."""
         self.packed.dev.copy_(packed.host if from_host else packed.dev, non_blocking=True)
 
-    def run(self, seed):
+    def run(self, seed, before_replay=None):
+        """`before_replay()` is called after the step's own uploads (the per-call weights) have been queued and
+        before the step's kernels are."""
         if self.graph is None:
+            if before_replay is not None:
+                before_replay()
             self._eager(seed)
         else:
             if self.has_ephemeral and not self.hot_only:
                 torch.default_generator.manual_seed(seed)   # same draw on every rank
                 self.model.draw_ephemeral()
+            if before_replay is not None:
+                before_replay()
             self.graph.replay()
         return self.loss
 
@@ -684,10 +690,18 @@ def measure_ours(args, wl, key, world, rank, local, dev, primary):
                 if slot is None:
                     slot = pf.submit(pool[i % n_pool], after=start)          # the first step waits for its own copy
                 pf.consume(slot)                                             # D2D into the graph's static inputs
-                loss = st.run(first_seed + i)
-                # the next batch's copy is queued AFTER this step's own small upload (the per-call weights): the one
-                # host-to-device copy engine is a FIFO, a 4 MB prefetch in front of it would delay the step by ~100 us
-                nxt = pf.submit(pool[(i + 1) % n_pool], after=start) if i + 1 < n_steps else None
+                nxt_slot = [None]
+
+                def prefetch_next(i=i):
+                    # the next batch's copy may start once this step's own small upload (the per-call weights) has
+                    # run: the host-to-device copy engine serves whichever copy is ready first, and a 4 MB prefetch
+                    # in front of that upload delays the whole step by ~100 us
+                    if i + 1 < n_steps:
+                        uploaded = torch.cuda.Event()
+                        uploaded.record()
+                        nxt_slot[0] = pf.submit(pool[(i + 1) % n_pool], after=uploaded)
+                loss = st.run(first_seed + i, before_replay=prefetch_next)
+                nxt = nxt_slot[0]
                 loss_host[i:i + 1].copy_(loss.detach().reshape(1), non_blocking=True)      # D2H read of the step's result
                 if nxt is not None:
                     pf.wait(nxt)
