@@ -21,13 +21,13 @@ void note_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
 long long launches() { return g_launches.load(std::memory_order_relaxed); }
 
 int sm_count() {
-    static int cached = 0;
-    if (cached) return cached;
+    static int cached[64] = {0};            // per device ordinal: a process may drive several GPUs
     int dev = 0, n = 0;
     if (cudaGetDevice(&dev) != cudaSuccess) return 148;
+    if (dev >= 0 && dev < 64 && cached[dev]) return cached[dev];
     if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0)
         return 148;
-    cached = n;
+    if (dev >= 0 && dev < 64) cached[dev] = n;
     return n;
 }
 

@@ -400,12 +400,9 @@ int rk_plan_build(const int64_t* const* idx, const int64_t* n, const int64_t* ro
         for (int f = 0; f < F; ++f)
             if (n[f] > 0) small.f[n_small++] = fk[f];
         const size_t smem = 2 * (size_t)kSmallN * 4 + (size_t)kSmallWarps * kSmallBins * 2;
-        static bool attr_set = false;
-        if (!attr_set) {
-            RK_CUDA(cudaFuncSetAttribute(small_field_sort_kernel,
-                                         cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            attr_set = true;
-        }
+        // per call: the attribute belongs to the current DEVICE, a process may drive several
+        RK_CUDA(cudaFuncSetAttribute(small_field_sort_kernel,
+                                     cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         small_field_sort_kernel<<<n_small, kSmallThreads, smem, s>>>(small, sorted_keys, perm, err_flag);
         RK_LAUNCH_CHECK();
         return 0;

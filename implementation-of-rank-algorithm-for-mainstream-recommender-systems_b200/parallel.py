@@ -42,7 +42,7 @@ class GradientAllReducer:
             self.views.append(self.flat[pos:pos + n].view_as(p))
             pos += n
         self._cursor = 0
-        self._layout = None           # (params copied, their compact views, floats reduced) once known
+        self._param_ids = {id(p) for p in self.params}
         self._avg = None
         if attach:
             self.attach()
@@ -60,9 +60,12 @@ class GradientAllReducer:
         from . import sparse
         sparse.set_slab_provider(None)
 
-    def _take(self, n_floats, device):
-        """A chunk of the table region for one backward's dense gradients (None: allocate normally)."""
+    def _take(self, n_floats, device, params):
+        """A chunk of the table region for one backward's dense gradients (None: allocate normally).  Only for
+        this reducer's own parameters: another model's backward in the same process must not land here."""
         if device != self.flat.device or self._cursor + n_floats > self.n_slab:
+            return None
+        if not params or any(p is None or id(p) not in self._param_ids for p in params):
             return None
         lo = self.n_staging + self._cursor
         self._cursor += (n_floats + 3) // 4 * 4

@@ -101,14 +101,15 @@ _slab_provider = None
 
 
 def set_slab_provider(fn) -> None:
-    """fn(n_floats, device) -> 1-D fp32 tensor of n_floats, or None to fall back to torch.empty."""
+    """fn(n_floats, device, params) -> 1-D fp32 tensor of n_floats, or None to fall back to torch.empty;
+    `params` are the tables whose gradients the slab will hold (a provider serves its own model only)."""
     global _slab_provider
     _slab_provider = fn
 
 
-def _new_slab(n_floats, device):
+def _new_slab(n_floats, device, params):
     if _slab_provider is not None:
-        t = _slab_provider(n_floats, device)
+        t = _slab_provider(n_floats, device, params)
         if t is not None:
             return t
     return torch.empty(n_floats, dtype=torch.float32, device=device)
@@ -256,7 +257,7 @@ class OccurrencePlan:
             acc += (sources[t].rows * sources[t].dim + 3) // 4 * 4          # keep every table 16-byte aligned
         if n_direct == T:
             sorted_from = acc
-        slab = _new_slab(acc, dev)
+        slab = _new_slab(acc, dev, [s.param for s in sources])
         if sorted_from < acc:
             slab[sorted_from:].zero_()
         grads = [slab[starts[t]:starts[t] + s.rows * s.dim].view(s.rows, s.dim) for t, s in enumerate(sources)]
