@@ -59,6 +59,9 @@ def main(tag):
                 n, d["table_rows"], d["shard_gb"], d["ms_per_step"], d["samples_per_s"], d.get("launch", "eager"),
                 "ok" if p["ok_all_ranks"] else "FAILED", p["logit_rel_err"], p["shard_grad_rel_err"], p["other_grad_rel_err"]))
         out.append("")
+    notes = os.path.join(ROOT, "profiles", f"{tag}_scaling_notes.md")
+    if os.path.exists(notes):
+        out += [open(notes).read().rstrip(), ""]
     path = os.path.join(ROOT, "profiles", f"{tag}_scaling.md")
     open(path, "w").write("\n".join(out) + "\n")
     print("\n".join(out))

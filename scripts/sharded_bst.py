@@ -38,6 +38,13 @@ def main():
                     "both collectives replayed from one CUDA graph; the exchange has no host sync)")
     args = ap.parse_args()
     rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
+    if os.environ.get("RANK_B200_TRACE"):
+        import faulthandler
+        faulthandler.dump_traceback_later(int(os.environ.get("RANK_B200_TRACE_AFTER", "60")), exit=False)
+
+    def stage(msg):
+        if os.environ.get("RANK_B200_TRACE"):
+            print(f"[rank {rank}] {msg}", file=sys.stderr, flush=True)
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     dist.init_process_group("nccl", device_id=dev)
@@ -59,9 +66,13 @@ def main():
         return F.binary_cross_entropy_with_logits(logit.squeeze(), b["label"]), logit
 
     shard.train(); full.train()
+    stage("models built")
     l_s, logit_s = loss_of(shard, mine)
+    torch.cuda.synchronize(); stage("sharded forward done")
     l_s.backward()
+    torch.cuda.synchronize(); stage("sharded backward done")
     reducer.allreduce()
+    torch.cuda.synchronize(); stage("all-reduce done")
     # the replicated model sees every rank's batch; BatchNorm uses per-rank statistics, so run the
     # ranks' batches one by one and average the losses (= what data parallelism computes)
     total = 0
@@ -70,6 +81,7 @@ def main():
         (l_r / world).backward()
         if r == rank:
             e_logit = rel(logit_s, logit_r)
+    torch.cuda.synchronize(); stage("replicated passes done")
     lo, hi = shard.embeddings["feedid"].row_range
     e_shard = rel(shard.embeddings["feedid"].weight.grad[:hi - lo], full.embeddings["feedid"].weight.grad[lo:hi])
     e_rest = max(rel(ps.grad, pf.grad) for (ns, ps), (nf, pf) in zip(shard.named_parameters(), full.named_parameters())
@@ -101,10 +113,6 @@ def main():
         loss.backward()
         reducer.allreduce()
         return loss
-
-    def stage(msg):
-        if os.environ.get("RANK_B200_TRACE"):
-            print(f"[rank {rank}] {msg}", file=sys.stderr, flush=True)
 
     graph = None
     if not args.eager:
