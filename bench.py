@@ -484,9 +484,20 @@ class Stepper:
             if self.has_ephemeral:
                 model.draw_ephemeral()
                 model.ephemeral_frozen = True
-            self.graph = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(self.graph):
-                self._body()
+            try:
+                self.graph = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(self.graph):
+                    self._body()
+            except Exception:
+                # the symmetric-memory all-reduce could not be captured on this build: NCCL's can
+                if self.reducer is None or self.reducer.symmetric is None:
+                    raise
+                self.reducer.use_nccl()
+                torch.cuda.synchronize()
+                model.zero_grad(set_to_none=True)
+                self.graph = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(self.graph):
+                    self._body()
             self.grads = [p.grad for p in model.parameters()]
         self.collective_in_graph = self.graph is not None and self.reducer is not None
 
@@ -808,6 +819,7 @@ def measure_ours(args, wl, key, world, rank, local, dev, primary):
         "h2d_bytes": pool[0].nbytes, "h2d_payload": pool[0].payload_bytes, "fill_ms": fill_ms,
         "host_queue_ms": {"value_loop": host_value_ms, "e2e_loop": host_e2e_ms},
         "graph": stepper.graph is not None,
+        "allreduce": None if reducer is None else ("nccl" if reducer.symmetric is None else "symmetric memory: " + reducer.symmetric[0]),
         "roofline": {
             "bound": wl.bound, "achieved": achieved, "peak": pk["hbm_gbs"], "unit": "GB/s",
             "frac": achieved / pk["hbm_gbs"], "peak_source": pk["source"],
@@ -866,6 +878,7 @@ def run_ours(args, wl):
             "config": {"workload": r["workload"], "batch_per_gpu": B, "global_batch": world * B, "dropout": 0.0,
                        "parallelism": f"dp{world}", "l2": "256 MiB written between steps, outside the timed events",
                        "step": "zero_grad+fwd+loss+bwd" + ("+grad allreduce" if world > 1 else ""),
+                       "allreduce": r.get("allreduce"),
                        "launch": "cuda graph replay per step" if r["graph"] else "eager",
                        "indices": "zipf(1.05), fresh batch each step from a pool of 4"},
             "clocks": r["clocks"],
