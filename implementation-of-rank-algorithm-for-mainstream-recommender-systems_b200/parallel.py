@@ -27,8 +27,14 @@ class GradientAllReducer:
     itself (ReduceOp.AVG; gloo: SUM then one scale).  Every call is stream-ordered device work — the whole
     step including the collective can be captured in a CUDA graph (bench.py does)."""
 
-    def __init__(self, model: torch.nn.Module, group=None, attach=True):
+    def __init__(self, model: torch.nn.Module, group=None, attach=True, occurrence_exchange=None):
         self.group = group
+        # opt-in (or RANK_B200_OCCURRENCE_EXCHANGE=1): see _exchange_occurrences.  Measured at 2 GPUs on DeepFM
+        # (batch 1024 per rank): 13.5 MB all-reduced -> 0.9 MB all-gathered, and the step stays at 0.339 ms either
+        # way - at this size the cost of a collective is its fixed latency and the skew between the ranks'
+        # independently launched graphs, not its bytes - so the dense all-reduce remains the default.
+        self.occurrence_exchange = (os.environ.get("RANK_B200_OCCURRENCE_EXCHANGE", "0") == "1"
+                                    if occurrence_exchange is None else bool(occurrence_exchange))
         # row-sharded tables are owned by one rank each: their gradients are not replicated
         self.params = [p for p in model.parameters()
                        if p.requires_grad and not getattr(p, "_rank_local", False)]
@@ -129,10 +135,80 @@ class GradientAllReducer:
     def attach(self):
         from . import sparse
         sparse.set_slab_provider(self._take)
+        sparse.set_occurrence_exchange(self._exchange_occurrences if self.occurrence_exchange else None)
 
     def detach(self):
         from . import sparse
         sparse.set_slab_provider(None)
+        sparse.set_occurrence_exchange(None)
+
+    # ---- small batches: exchange the occurrences, not the tables -----------------------------------
+    def _exchange_occurrences(self, plan, sources):
+        """DeepFM / FwFM at their BASELINE batch of 1024: a rank touches <= 6 144 of 213 k table rows per step, yet
+        the dense gradients are 13 MB.  When world x n occurrences fit one direct reduction (<= 8192 per index
+        column) the ranks all-gather (index, gradient row / world) — ~0.45 MB per rank — and every rank reduces
+        the occurrences of the whole global batch, rank-major, in occurrence order: the result is the averaged
+        gradient, bit-identical on all ranks, and those tables never enter the all-reduce."""
+        from . import _lib, sparse
+        if not dist.is_initialized():
+            return None
+        world = self.world_size
+        if world < 2 or not sources or plan.device != self.flat.device:
+            return None
+        n = plan.n[sources[0].field]
+        if n == 0 or world * n > _lib.RK_DIRECT_MAX_N:
+            return None
+        for s in sources:
+            if (not plan.direct[s.field] or plan.n[s.field] != n or s.param is None
+                    or id(s.param) not in self._param_ids or s.base.dtype != torch.float32):
+                return None
+        dev = plan.device
+        fields = sorted({s.field for s in sources})
+        fpos = {f: k for k, f in enumerate(fields)}
+        F = len(fields)
+        # columns of the packed gradient rows: sources that read the same columns share them (DeepFM's six
+        # first-order tables all receive the same per-sample scalar), adjacent columns of one tensor are one copy
+        cols, spans, seen, width = [], [], {}, 0
+        for s in sources:
+            key = (s.base.data_ptr(), s.offset, s.dim, s.ld)
+            if key in seen:
+                cols.append(seen[key])
+                continue
+            seen[key] = width
+            cols.append(width)
+            last = spans[-1] if spans else None
+            if last is not None and last[0] is s.base and last[3] == s.ld and last[1] + last[2] == s.offset:
+                last[2] += s.dim
+            else:
+                spans.append([s.base, s.offset, s.dim, s.ld, width])
+            width += s.dim
+        # one packed message per rank: [F, n] int64 indices | [n, width] fp32 gradient rows scaled by 1 / world
+        idx_bytes, g_bytes = F * n * 8, n * width * 4
+        send = torch.empty(idx_bytes + g_bytes, dtype=torch.uint8, device=dev)
+        send_idx = send[:idx_bytes].view(torch.int64).view(F, n)
+        send_g = send[idx_bytes:].view(torch.float32).view(n, width)
+        torch.stack([plan.indices[f].reshape(-1) for f in fields], out=send_idx)
+        for base, off, dim, ld, pos in spans:
+            rows_view = torch.as_strided(base, (n, dim), (ld, 1), base.storage_offset() + off)
+            send_g[:, pos:pos + dim].copy_(rows_view)
+        send_g.mul_(1.0 / world)
+        recv = torch.empty(world, idx_bytes + g_bytes, dtype=torch.uint8, device=dev)
+        dist.all_gather_into_tensor(recv.view(-1), send, group=self.group)
+        idx_all = recv[:, :idx_bytes].contiguous().view(torch.int64).view(world, F, n).permute(1, 0, 2).contiguous()
+        g_all = recv[:, idx_bytes:].contiguous().view(torch.float32).view(world * n, width)
+        total = sum((s.rows * s.dim + 3) // 4 * 4 for s in sources)
+        slab = torch.empty(total, dtype=torch.float32, device=dev)
+        grads, tables, acc = [], [], 0
+        for t, s in enumerate(sources):
+            g = slab[acc:acc + s.rows * s.dim].view(s.rows, s.dim)
+            acc += (s.rows * s.dim + 3) // 4 * 4
+            grads.append(g)
+            tables.append((idx_all[fpos[s.field]].data_ptr(), g_all.data_ptr() + 4 * cols[t], width, g.data_ptr(),
+                           s.rows, world * n, s.dim))
+            s.param._rk_synced = True            # already the global average: allreduce() leaves it alone
+        sparse.direct_reduce_into(tables, dev)
+        self._keep = (idx_all, g_all, recv, send)        # alive until the next step's exchange (stream-ordered use)
+        return grads
 
     def _take(self, n_floats, device, params):
         """A chunk of the table region for one backward's dense gradients (None: allocate normally).  Only for
@@ -154,7 +230,11 @@ class GradientAllReducer:
         (default: each parameter's .grad) lets a CUDA-graph step pass its static tensors.
         Afterwards every parameter's .grad is a view of the reduced buffer."""
         grads = [p.grad for p in self.params] if grads is None else list(grads)
-        in_slab = [self._in_slab(g) for g in grads]
+        synced = [bool(getattr(p, "_rk_synced", False)) for p in self.params]
+        for p in self.params:
+            if getattr(p, "_rk_synced", False):
+                p._rk_synced = False
+        in_slab = [self._in_slab(g) or sy for g, sy in zip(grads, synced)]
         staged = sum(p.numel() for p, s_ in zip(self.params, in_slab) if not s_)
         # the copied gradients sit right below the table region: [n_staging - staged, n_staging + used) is ONE range
         pos = self.n_staging - staged

@@ -115,6 +115,30 @@ def _new_slab(n_floats, device, params):
     return torch.empty(n_floats, dtype=torch.float32, device=device)
 
 
+# Data-parallel exchange of per-occurrence gradients (parallel.GradientAllReducer installs it): when every
+# rank's occurrences of a step fit one direct reduction (world x n <= RK_DIRECT_MAX_N), the ranks all-gather
+# their (index, gradient row) pairs — a few hundred KB — and each reduces the WHOLE global batch's occurrences
+# into its dense gradients, instead of reducing its own and all-reducing 13 MB of mostly-zero tables.
+_occurrence_exchange = None
+
+
+def set_occurrence_exchange(fn) -> None:
+    """fn(plan, sources) -> list of dense gradients (already global), or None to reduce locally."""
+    global _occurrence_exchange
+    _occurrence_exchange = fn
+
+
+def direct_reduce_into(tables, dev) -> None:
+    """rk_embgrad_direct_reduce over prepared (idx, g, ld, dw, rows, n, dim) tuples of device pointers."""
+    lib = _lib.load()
+    tabs = (_lib.RkDirectTable * len(tables))()
+    for k, (idx, g, ld, dw, rows, n, dim) in enumerate(tables):
+        tabs[k].idx, tabs[k].g, tabs[k].ld, tabs[k].dw = idx, g, ld, dw
+        tabs[k].rows, tabs[k].n, tabs[k].dim = rows, n, dim
+    rc = lib.rk_embgrad_direct_reduce(tabs, len(tables), _lib.err_flag(dev).data_ptr(), _lib.stream_ptr())
+    _lib.check(rc, "rk_embgrad_direct_reduce")
+
+
 @dataclass
 class TouchedRows:
     """Sparse gradient of one table, sized without a host sync: `capacity = min(occurrences, table rows)`."""
@@ -234,6 +258,10 @@ class OccurrencePlan:
         a `touched_grad` and the returned gradients are None."""
         if self.touched:
             return self._reduce_touched(sources)
+        if _occurrence_exchange is not None:
+            done = _occurrence_exchange(self, sources)
+            if done is not None:
+                return done
         lib = _lib.load()
         T = len(sources)
         if not 1 <= T <= _lib.RK_MAX_TABLES:
