@@ -38,5 +38,12 @@ if [ -f gpurun_out/${tag}_phase_bst_tc_bwd.txt ]; then
   echo; echo "## Phase profile — \`tc::bst_bwd_tc_kernel\` (\`scripts/phase_profile.py run bst_tc bwd\`, clock64 of thread 0 per phase, B = 8192)"; echo
   echo '```'; grep -v Warning gpurun_out/${tag}_phase_bst_tc_bwd.txt | tail -12; echo '```'
 fi
+echo; echo "## SASS evidence of the Blackwell paths in the shipped library (\`cuobjdump -sass librank_b200.so\`)"; echo
+echo '```'
+cuobjdump -sass implementation-*_b200/librank_b200.so 2>/dev/null | grep -oE "UTCHMMA|LDTM|UTCBAR|UBLKCP|UTMALDG|SYNCS\.[A-Z.]+|LDGSTS" | sort | uniq -c
+echo '```'
+echo "(\`UTCHMMA\` = tcgen05.mma kind::f16 — AFM, DIN and BST kernels; \`LDTM\` = tcgen05.ld; \`UTCBAR\` = tcgen05.commit; \`UBLKCP\` = cp.async.bulk"
+echo "global -> shared on an mbarrier, the TMA bulk copy of DIN's weight tiles; \`SYNCS.ARRIVE.TRANS\` = mbarrier.arrive.expect_tx;"
+echo "\`SYNCS.PHASECHK\` = mbarrier.try_wait; \`LDGSTS\` = cp.async row / index staging.)"
 } > $out.new
 echo "wrote $out.new"
