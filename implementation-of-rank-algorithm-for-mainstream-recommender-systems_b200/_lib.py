@@ -89,9 +89,10 @@ PROTOTYPES = {
     "rk_cross_layer_bwd": (_I, [_P, _P, _P, _I, _L, _P, _P, _P, _P]),
     "rk_afm_bwd_ctas": (_I, [_L, _I]),
     "rk_afm_fwd": (_I, [_P, _I, _P, _P, _P, _P, _I, _L, _P, _P, _P]),
-    "rk_afm_tc_fwd": (_I, [_P, _I, _P, _P, _P, _P, _I, _L, _P, _P, _P]),
+    "rk_afm_tile_bytes": (_I, []),
+    "rk_afm_tc_fwd": (_I, [_P, _I, _P, _P, _P, _P, _I, _L, _P, _P, _P, _P]),
     "rk_afm_tc_bwd_ctas": (_I, [_L, _I]),
-    "rk_afm_tc_bwd": (_I, [_P, _I, _P, _P, _P, _P, _I, _L, _P, _P, _P, _P, _P, _P, _P, _I, _P, _P]),
+    "rk_afm_tc_bwd": (_I, [_P, _I, _P, _P, _P, _P, _I, _L, _P, _P, _P, _P, _P, _P, _P, _I, _P, _P, _P]),
     "rk_afm_bwd": (_I, [_P, _I, _P, _P, _P, _P, _I, _L, _P, _P, _P, _P, _P, _P, _P, _I, _P, _P]),
     "rk_dice_bn_max_batch": (_I, []),
     "rk_dice_bn_fwd": (_I, [_P, _L, _I, _P, _F, _P, _P, _F, _F, _P, _P, _P, _F, _P, _P, _P, _P, _P, _P]),
@@ -153,7 +154,7 @@ class CallTimer:
     (bench.py's live per-call device times).  Use as a context manager; `summary()` after a
     synchronize gives {entry point: (calls, total ms)}."""
 
-    NO_KERNEL = ("rk_resunit_pack_floats", "rk_din_mlp_floats", "rk_din_tile_bytes", "rk_afm_bwd_ctas", "rk_afm_tc_bwd_ctas", "rk_fwfm_bwd_ctas", "rk_dice_bn_max_batch", "rk_bst_grad_floats", "rk_bst_bwd_ctas", "rk_version", "rk_last_error", "rk_device_sm_count", "rk_launch_count", "rk_debug_spin",
+    NO_KERNEL = ("rk_resunit_pack_floats", "rk_din_mlp_floats", "rk_din_tile_bytes", "rk_afm_bwd_ctas", "rk_afm_tc_bwd_ctas", "rk_afm_tile_bytes", "rk_fwfm_bwd_ctas", "rk_dice_bn_max_batch", "rk_bst_grad_floats", "rk_bst_bwd_ctas", "rk_version", "rk_last_error", "rk_device_sm_count", "rk_launch_count", "rk_debug_spin",
                  "rk_plan_workspace_bytes", "rk_reduce_workspace_bytes")
 
     def __init__(self):

@@ -46,9 +46,16 @@ class _AfmPooling(torch.autograd.Function):
         B = int(idx[0].shape[0])
         dev = w1.device
         out = torch.empty(B, D, dtype=torch.float32, device=dev)
-        fwd = lib.rk_afm_tc_fwd if precision in ("tensor", "bf16") else lib.rk_afm_fwd
-        rc = fwd(fields, F, w1.data_ptr(), b1.data_ptr(), w2.data_ptr(), b2.data_ptr(), A, B,
-                 out.data_ptr(), _lib.err_flag(dev).data_ptr(), _lib.stream_ptr())
+        tiles = None
+        if precision in ("tensor", "bf16"):
+            # scratch for the weights' operand tiles: made once by the forward's prologue, fetched by bulk (TMA)
+            # copy in every CTA of the forward and of the backward
+            tiles = torch.empty(lib.rk_afm_tile_bytes(), dtype=torch.uint8, device=dev)
+            rc = lib.rk_afm_tc_fwd(fields, F, w1.data_ptr(), b1.data_ptr(), w2.data_ptr(), b2.data_ptr(), A, B,
+                                   out.data_ptr(), tiles.data_ptr(), _lib.err_flag(dev).data_ptr(), _lib.stream_ptr())
+        else:
+            rc = lib.rk_afm_fwd(fields, F, w1.data_ptr(), b1.data_ptr(), w2.data_ptr(), b2.data_ptr(), A, B,
+                                out.data_ptr(), _lib.err_flag(dev).data_ptr(), _lib.stream_ptr())
         _lib.check(rc, "rk_afm_fwd")
         if _lib.CHECK_EVERY_CALL:
             _lib.check_index_errors(dev)
@@ -56,7 +63,7 @@ class _AfmPooling(torch.autograd.Function):
         if any(ctx.needs_input_grad):
             ctx.meta = (F, D, A, B, [int(t.shape[0]) for t in tables])
             ctx.precision = precision
-            ctx.fields, ctx.keep = fields, keep
+            ctx.fields, ctx.keep, ctx.tiles = fields, keep, tiles
             if any(ctx.needs_input_grad[5 + F:]):
                 ctx.plan = OccurrencePlan([keep[2 * f + 1] for f in range(F)], ctx.meta[4])
                 ctx.tables = list(tables)
@@ -79,11 +86,13 @@ class _AfmPooling(torch.autograd.Function):
         n_ctas = (lib.rk_afm_tc_bwd_ctas if tc else lib.rk_afm_bwd_ctas)(B, F)
         partials = torch.empty(n_ctas * g_att.numel(), dtype=torch.float32, device=dev)
         base = g_att.data_ptr()
-        bwd = lib.rk_afm_tc_bwd if tc else lib.rk_afm_bwd
-        rc = bwd(ctx.fields, F, w1.data_ptr(), b1.data_ptr(), w2.data_ptr(), b2.data_ptr(), A, B,
-                            g_out.data_ptr(), g_rows.data_ptr(), base, base + 4 * A * D,
-                            base + 4 * (A * D + A), base + 4 * (A * D + 2 * A), partials.data_ptr(), n_ctas,
-                            _lib.err_flag(dev).data_ptr(), _lib.stream_ptr())
+        common = (ctx.fields, F, w1.data_ptr(), b1.data_ptr(), w2.data_ptr(), b2.data_ptr(), A, B,
+                  g_out.data_ptr(), g_rows.data_ptr(), base, base + 4 * A * D,
+                  base + 4 * (A * D + A), base + 4 * (A * D + 2 * A), partials.data_ptr(), n_ctas)
+        if tc:
+            rc = lib.rk_afm_tc_bwd(*common, _lib.ptr(ctx.tiles), _lib.err_flag(dev).data_ptr(), _lib.stream_ptr())
+        else:
+            rc = lib.rk_afm_bwd(*common, _lib.err_flag(dev).data_ptr(), _lib.stream_ptr())
         _lib.check(rc, "rk_afm_bwd")
         g_tables = [None] * F
         if any(ctx.needs_input_grad[5 + F:]):

@@ -30,7 +30,13 @@ struct AfmTcParams {
     const float* b2;   // [1]
     int32_t      D, Kp, A, Ap, P, S, estride;
     int64_t      B, n_tiles;
+    const uint8_t* tiles;   // prologue-made operand tiles (afm_weight_tiles_kernel) or NULL: convert per CTA
 };
+
+// Image written once per forward by afm_weight_tiles_kernel and fetched by one / two bulk (TMA) copies per CTA:
+//   [B1 16 KB: W1 as the B operand, line n = [hi | lo] of W1[n][:]] [B2 16 KB: w2[a] W1[a][d] transposed, hi lines | lo
+//   lines, two K panels] [max |W1| as one float]
+constexpr uint32_t kAfmTileB1 = 128 * 128, kAfmTileB2 = 2 * 64 * 128, kAfmTileBytes = kAfmTileB1 + kAfmTileB2 + 16;
 
 struct AfmTcFwdSmem {
     uint8_t *a1, *b1t;              // [128][128 B], [Ap][128 B]  (b1t = W1 as the B operand)
@@ -38,7 +44,7 @@ struct AfmTcFwdSmem {
     int64_t *ix[2];                 // raw indices of the tiles after next
     float   *bias, *w2, *score, *attn;
     int     *pi, *pj;
-    uint64_t* bar;
+    uint64_t *bar, *bar_w;
     uint32_t* tmem_slot;
     __device__ AfmTcFwdSmem(uint8_t* base, const AfmTcParams& p) {
         uint8_t* q = base;
@@ -56,11 +62,12 @@ struct AfmTcFwdSmem {
         pi = (int*)q;      q += sizeof(int) * 128;
         pj = (int*)q;      q += sizeof(int) * 128;
         bar = (uint64_t*)q; q += 8;
+        bar_w = (uint64_t*)q; q += 8;
         tmem_slot = (uint32_t*)q;
     }
     static size_t bytes(const AfmTcParams& p) {
         return 1024 + 2 * 128 * 128 + 2 * sizeof(float) * p.S * p.fs.F * p.estride + sizeof(float) * (2 * p.Ap + 2 * kAfmTcRows) +
-               sizeof(int) * 256 + 16 + 2 * sizeof(int64_t) * 64;
+               sizeof(int) * 256 + 32 + 2 * sizeof(int64_t) * 64;
     }
 };
 
@@ -107,6 +114,77 @@ __device__ __forceinline__ void afm_issue_rows(const AfmTcParams& p, float* e, c
     }
 }
 
+// ---- the weight operand tiles (shared memory in the per-CTA path, the global image in the prologue kernel)
+// B1 line n = [hi | lo] of W1[n][:], zero beyond A / D
+template <int KP>
+__device__ __forceinline__ void afm_build_b1(uint8_t* b1t, const float* __restrict__ w1, int A, int D, int lines, int tid,
+                                             int n_threads) {
+    for (int item = tid; item < lines * (KP / 8); item += n_threads) {
+        const int n = item / (KP / 8), c = item - n * (KP / 8);
+        float hi8[8], lo8[8];
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            float4 w = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (n < A && 8 * c + 4 * h < D) w = __ldg(reinterpret_cast<const float4*>(w1 + n * D + 8 * c + 4 * h));
+            hi8[4 * h] = w.x; hi8[4 * h + 1] = w.y; hi8[4 * h + 2] = w.z; hi8[4 * h + 3] = w.w;
+        }
+#pragma unroll
+        for (int j = 0; j < 8; ++j) lo8[j] = hi8[j] - __bfloat162float(__float2bfloat16_rn(hi8[j]));
+        store_chunk(b1t, n, c, hi8);
+        store_chunk(b1t, n, KP / 8 + c, lo8);
+    }
+}
+// B2 lines n < KP: hi of w2[a] W1[a][n]; n >= KP: lo.  K = a, 64 per panel.  W1 is read row-major (coalesced
+// float4) and scattered into the transposed, pre-zeroed tile two bytes at a time.
+template <int KP>
+__device__ __forceinline__ void afm_scatter_b2(uint8_t* b2t, const float* __restrict__ w1, const float* __restrict__ w2,
+                                               int A, int D, int tid, int n_threads) {
+    for (int item = tid; item < A * (D >> 2); item += n_threads) {
+        const int a = item / (D >> 2), d0 = 4 * (item - a * (D >> 2));
+        const float4 w4 = __ldg(reinterpret_cast<const float4*>(w1 + a * D + d0));
+        const float w2a = __ldg(w2 + a);
+        const float w[4] = {w2a * w4.x, w2a * w4.y, w2a * w4.z, w2a * w4.w};
+        uint8_t* panel = b2t + (a >> 6) * (64 * 128);
+        const int c = (a & 63) >> 3, e = (a & 7) * 2;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const __nv_bfloat16 hi = __float2bfloat16_rn(w[j]);
+            const __nv_bfloat16 lo = __float2bfloat16_rn(w[j] - __bfloat162float(hi));
+            const int nh = d0 + j, nl = KP + d0 + j;
+            *reinterpret_cast<__nv_bfloat16*>(panel + nh * 128 + ((c ^ (nh & 7)) << 4) + e) = hi;
+            *reinterpret_cast<__nv_bfloat16*>(panel + nl * 128 + ((c ^ (nl & 7)) << 4) + e) = lo;
+        }
+    }
+}
+
+// Once per forward: both directions' weight tiles + max |W1| into the global image (CTA 0: B2, CTA 1: B1 and the max).
+// The attention weights are registered parameters, the same for every CTA of both kernels: 592 + 296 CTAs used to
+// convert them each for themselves (13 % / 9 % of the forward / backward).
+template <int KP>
+__global__ void __launch_bounds__(256)
+afm_weight_tiles_kernel(const float* __restrict__ w1, const float* __restrict__ w2, int A, int D, uint8_t* __restrict__ tiles) {
+    __shared__ float red[8];
+    const int tid = threadIdx.x;
+    if (blockIdx.x == 0) {
+        uint8_t* b2t = tiles + kAfmTileB1;
+        for (int i = tid; i < (int)kAfmTileB2 / 16; i += 256) reinterpret_cast<uint4*>(b2t)[i] = make_uint4(0u, 0u, 0u, 0u);
+        __syncthreads();
+        afm_scatter_b2<KP>(b2t, w1, w2, A, D, tid, 256);
+    } else {
+        afm_build_b1<KP>(tiles, w1, A, D, 128, tid, 256);
+        float m = 0.f;
+        for (int i = tid; i < A * D; i += 256) m = fmaxf(m, fabsf(__ldg(w1 + i)));
+        m = warp_max(m);
+        if ((tid & 31) == 0) red[tid >> 5] = m;
+        __syncthreads();
+        if (tid == 0) {
+            float t = 0.f;
+            for (int w = 0; w < 8; ++w) t = fmaxf(t, red[w]);
+            *reinterpret_cast<float*>(tiles + kAfmTileB1 + kAfmTileB2) = t;
+        }
+    }
+}
+
 template <int KP>
 __global__ void __launch_bounds__(kAfmTcThreads)
 afm_fwd_tc_kernel(const __grid_constant__ AfmTcParams p, float* __restrict__ out, int32_t* err_flag) {
@@ -125,22 +203,16 @@ afm_fwd_tc_kernel(const __grid_constant__ AfmTcParams p, float* __restrict__ out
         cp_async_commit();
     }
 
-    if (tid == 0) mbar_init(sm.bar, 1);
-    if (warp == 0) tmem_alloc(sm.tmem_slot, 128);
-    for (int item = tid; item < p.Ap * (KP / 8); item += kAfmTcThreads) {     // W1[n][8c..8c+7] -> B1 line n, chunks c (hi) and KP/8 + c (lo)
-        const int n = item / (KP / 8), c = item - n * (KP / 8);
-        float hi8[8], lo8[8];
-#pragma unroll
-        for (int h = 0; h < 2; ++h) {
-            float4 w = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (n < p.A && 8 * c + 4 * h < D) w = __ldg(reinterpret_cast<const float4*>(p.w1 + n * D + 8 * c + 4 * h));
-            hi8[4 * h] = w.x; hi8[4 * h + 1] = w.y; hi8[4 * h + 2] = w.z; hi8[4 * h + 3] = w.w;
+    if (tid == 0) {
+        mbar_init(sm.bar, 1);
+        mbar_init(sm.bar_w, 1);
+        if (p.tiles) {                     // W1's operand tile in one bulk (TMA) copy
+            mbar_expect_tx(sm.bar_w, (uint32_t)p.Ap * 128u);
+            bulk_copy_g2s(sm.b1t, p.tiles, (uint32_t)p.Ap * 128u, sm.bar_w);
         }
-#pragma unroll
-        for (int j = 0; j < 8; ++j) lo8[j] = hi8[j] - __bfloat162float(__float2bfloat16_rn(hi8[j]));
-        store_chunk(sm.b1t, n, c, hi8);
-        store_chunk(sm.b1t, n, KP / 8 + c, lo8);
     }
+    if (warp == 0) tmem_alloc(sm.tmem_slot, 128);
+    if (!p.tiles) afm_build_b1<KP>(sm.b1t, p.w1, p.A, D, p.Ap, tid, kAfmTcThreads);
     for (int n = tid; n < p.Ap; n += kAfmTcThreads) {
         sm.bias[n] = n < p.A ? __ldg(p.b1 + n) : 0.f;
         sm.w2[n]   = n < p.A ? __ldg(p.w2 + n) : 0.f;
@@ -154,6 +226,7 @@ afm_fwd_tc_kernel(const __grid_constant__ AfmTcParams p, float* __restrict__ out
     fence_before();
     __syncthreads();
     fence_after();
+    if (p.tiles) mbar_wait(sm.bar_w, 0);
     const uint32_t tmem = *sm.tmem_slot;
     const uint32_t my_tmem = tmem + ((uint32_t)(warp * 32) << 16);
     const uint64_t a_desc = umma_desc(smem_u32(sm.a1)), b_desc = umma_desc(smem_u32(sm.b1t));
@@ -309,7 +382,7 @@ struct AfmTcBwdSmem {
     int64_t *ix[2];
     float   *bias, *w2, *score, *attn, *ga, *gs, *dot, *red, *wmax;
     int     *pi, *pj, *pidx;
-    uint64_t* bar;
+    uint64_t *bar, *bar_w;
     uint32_t* tmem_slot;
     __device__ AfmTcBwdSmem(uint8_t* base, const AfmTcParams& p) {
         uint8_t* q = base;
@@ -338,6 +411,7 @@ struct AfmTcBwdSmem {
         pj = (int*)q;      q += sizeof(int) * 128;
         pidx = (int*)q;    q += sizeof(int) * 256;
         bar = (uint64_t*)q; q += 8;
+        bar_w = (uint64_t*)q; q += 8;
         tmem_slot = (uint32_t*)q;
     }
     static size_t bytes(const AfmTcParams& p) {
@@ -380,48 +454,28 @@ afm_bwd_tc_kernel(const __grid_constant__ AfmTcParams p, const float* __restrict
         if (tile + gridDim.x < p.n_tiles) afm_issue_idx(p, sm.ix[1], tile + gridDim.x, tid);
         cp_async_commit();
     }
-    if (tid == 0) mbar_init(sm.bar, 1);
-    if (warp == 0) tmem_alloc(sm.tmem_slot, 256);
-    for (int item = tid; item < 128 * (KP / 8); item += kAfmTcThreads) {     // W1[n][8c..8c+7] -> B1 line n, chunks c (hi) and KP/8 + c (lo)
-        const int n = item / (KP / 8), c = item - n * (KP / 8);
-        float hi8[8], lo8[8];
-#pragma unroll
-        for (int h = 0; h < 2; ++h) {
-            float4 w = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (n < A && 8 * c + 4 * h < D) w = __ldg(reinterpret_cast<const float4*>(p.w1 + n * D + 8 * c + 4 * h));
-            hi8[4 * h] = w.x; hi8[4 * h + 1] = w.y; hi8[4 * h + 2] = w.z; hi8[4 * h + 3] = w.w;
+    if (tid == 0) {
+        mbar_init(sm.bar, 1);
+        mbar_init(sm.bar_w, 1);
+        if (p.tiles) {                     // B1 and B2 in two bulk (TMA) copies on one barrier
+            mbar_expect_tx(sm.bar_w, kAfmTileB1 + kAfmTileB2);
+            bulk_copy_g2s(sm.b1t, p.tiles, kAfmTileB1, sm.bar_w);
+            bulk_copy_g2s(sm.b2t, p.tiles + kAfmTileB1, kAfmTileB2, sm.bar_w);
+            sm.wmax[0] = __ldg(reinterpret_cast<const float*>(p.tiles + kAfmTileB1 + kAfmTileB2));
         }
-#pragma unroll
-        for (int j = 0; j < 8; ++j) lo8[j] = hi8[j] - __bfloat162float(__float2bfloat16_rn(hi8[j]));
-        store_chunk(sm.b1t, n, c, hi8);
-        store_chunk(sm.b1t, n, KP / 8 + c, lo8);
     }
+    if (warp == 0) tmem_alloc(sm.tmem_slot, 256);
     for (int n = tid; n < 128; n += kAfmTcThreads) {
         sm.bias[n] = n < A ? __ldg(p.b1 + n) : 0.f;
         sm.w2[n]   = n < A ? __ldg(p.w2 + n) : 0.f;
     }
-    // B2 lines n < KP: hi of w2[a] W1[a][n]; n >= KP: lo.  K = a, 64 per panel.  W1 is read row-major
-    // (coalesced float4) and scattered into the transposed tile two bytes at a time.
-    for (int i = tid; i < 2 * 64 * 128 / 16; i += kAfmTcThreads)
-        reinterpret_cast<uint4*>(sm.b2t)[i] = make_uint4(0u, 0u, 0u, 0u);
-    __syncthreads();
-    for (int item = tid; item < A * (D >> 2); item += kAfmTcThreads) {
-        const int a = item / (D >> 2), d0 = 4 * (item - a * (D >> 2));
-        const float4 w4 = __ldg(reinterpret_cast<const float4*>(p.w1 + a * D + d0));
-        const float w2a = __ldg(p.w2 + a);
-        const float w[4] = {w2a * w4.x, w2a * w4.y, w2a * w4.z, w2a * w4.w};
-        uint8_t* panel = sm.b2t + (a >> 6) * (64 * 128);
-        const int c = (a & 63) >> 3, e = (a & 7) * 2;
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            const __nv_bfloat16 hi = __float2bfloat16_rn(w[j]);
-            const __nv_bfloat16 lo = __float2bfloat16_rn(w[j] - __bfloat162float(hi));
-            const int nh = d0 + j, nl = KP + d0 + j;
-            *reinterpret_cast<__nv_bfloat16*>(panel + nh * 128 + ((c ^ (nh & 7)) << 4) + e) = hi;
-            *reinterpret_cast<__nv_bfloat16*>(panel + nl * 128 + ((c ^ (nl & 7)) << 4) + e) = lo;
-        }
-    }
-    {   // max |W1|: scales the band around zero inside which a pre-activation is recomputed in fp32
+    if (!p.tiles) {                        // per-CTA conversion (no prologue image)
+        afm_build_b1<KP>(sm.b1t, p.w1, A, D, 128, tid, kAfmTcThreads);
+        for (int i = tid; i < 2 * 64 * 128 / 16; i += kAfmTcThreads)
+            reinterpret_cast<uint4*>(sm.b2t)[i] = make_uint4(0u, 0u, 0u, 0u);
+        __syncthreads();
+        afm_scatter_b2<KP>(sm.b2t, p.w1, p.w2, A, D, tid, kAfmTcThreads);
+        // max |W1|: scales the band around zero inside which a pre-activation is recomputed in fp32
         float m = 0.f;
         for (int i = tid; i < A * D; i += kAfmTcThreads) m = fmaxf(m, fabsf(__ldg(p.w1 + i)));
         m = warp_max(m);
@@ -452,6 +506,7 @@ afm_bwd_tc_kernel(const __grid_constant__ AfmTcParams p, const float* __restrict
     fence_before();
     __syncthreads();
     fence_after();
+    if (p.tiles) mbar_wait(sm.bar_w, 0);
     const uint32_t tmem = *sm.tmem_slot;
     const uint32_t my_tmem = tmem + ((uint32_t)(warp * 32) << 16);
     const uint64_t a1_desc = umma_desc(smem_u32(sm.a1)), b1_desc = umma_desc(smem_u32(sm.b1t));
@@ -773,7 +828,9 @@ afm_bwd_tc_kernel(const __grid_constant__ AfmTcParams p, const float* __restrict
 }  // namespace tc
 
 static int afm_tc_fill(const rk_field_t* fields, int F, const float* w1, const float* b1, const float* w2,
-                       const float* b2, int A, int64_t B, tc::AfmTcParams* p) {
+                       const float* b2, int A, int64_t B, const void* tiles, tc::AfmTcParams* p) {
+    RK_CHECK_ARG(((uintptr_t)tiles % 128) == 0, "afm: tiles must be 128-byte aligned");
+    p->tiles = (const uint8_t*)tiles;
     if (int rc = pack_fields(fields, F, &p->fs)) return rc;
     RK_CHECK_ARG(F >= 2 && F <= 16, "afm: %d fields (supported: 2..16, i.e. <= 120 pairs)", F);
     const int D = fields[0].dim;
@@ -800,10 +857,10 @@ static int afm_tc_fill(const rk_field_t* fields, int F, const float* w1, const f
 extern "C" {
 
 int rk_afm_tc_fwd(const rk_field_t* fields, int F, const float* w1, const float* b1, const float* w2,
-                  const float* b2, int A, int64_t B, float* out, int32_t* err_flag, rk_stream_t stream_) {
+                  const float* b2, int A, int64_t B, float* out, void* tiles, int32_t* err_flag, rk_stream_t stream_) {
     using namespace rk;
     tc::AfmTcParams p;
-    if (int rc = afm_tc_fill(fields, F, w1, b1, w2, b2, A, B, &p)) return rc;
+    if (int rc = afm_tc_fill(fields, F, w1, b1, w2, b2, A, B, tiles, &p)) return rc;
     RK_CHECK_ARG(out, "afm_tc_fwd: out is NULL");
     if (B == 0) return 0;
     const size_t smem = tc::AfmTcFwdSmem::bytes(p);
@@ -822,10 +879,17 @@ int rk_afm_tc_fwd(const rk_field_t* fields, int F, const float* w1, const float*
     int64_t grid = p.n_tiles;
     const int64_t cap = (int64_t)sm_count() * occ;
     if (grid > cap) grid = cap;
+    if (tiles) {                           // both directions' weight tiles, once per forward
+        if (p.Kp == 16) tc::afm_weight_tiles_kernel<16><<<2, 256, 0, (cudaStream_t)stream_>>>(w1, w2, A, p.D, (uint8_t*)tiles);
+        else            tc::afm_weight_tiles_kernel<32><<<2, 256, 0, (cudaStream_t)stream_>>>(w1, w2, A, p.D, (uint8_t*)tiles);
+        RK_LAUNCH_CHECK();
+    }
     kernel<<<(int)grid, tc::kAfmTcThreads, smem, (cudaStream_t)stream_>>>(p, out, err_flag);
     RK_LAUNCH_CHECK();
     return 0;
 }
+
+int rk_afm_tile_bytes(void) { return (int)rk::tc::kAfmTileBytes; }
 
 int rk_afm_tc_bwd_ctas(int64_t B, int F) {
     if (F < 2 || F > 16 || B <= 0) return 1;
@@ -838,11 +902,11 @@ int rk_afm_tc_bwd_ctas(int64_t B, int F) {
 
 int rk_afm_tc_bwd(const rk_field_t* fields, int F, const float* w1, const float* b1, const float* w2,
                   const float* b2, int A, int64_t B, const float* g_out, float* g_rows, float* g_w1,
-                  float* g_b1, float* g_w2, float* g_b2, float* partials, int n_ctas, int32_t* err_flag,
-                  rk_stream_t stream_) {
+                  float* g_b1, float* g_w2, float* g_b2, float* partials, int n_ctas, const void* tiles,
+                  int32_t* err_flag, rk_stream_t stream_) {
     using namespace rk;
     tc::AfmTcParams p;
-    if (int rc = afm_tc_fill(fields, F, w1, b1, w2, b2, A, B, &p)) return rc;
+    if (int rc = afm_tc_fill(fields, F, w1, b1, w2, b2, A, B, tiles, &p)) return rc;
     RK_CHECK_ARG(g_out && g_rows && g_w1 && g_b1 && g_w2 && g_b2 && partials, "afm_tc_bwd: NULL pointer");
     RK_CHECK_ARG(n_ctas == rk_afm_tc_bwd_ctas(B, F), "afm_tc_bwd: n_ctas %d != rk_afm_tc_bwd_ctas", n_ctas);
     RK_CHECK_ARG(g_b1 == g_w1 + (size_t)A * p.D && g_w2 == g_b1 + A && g_b2 == g_w2 + A,

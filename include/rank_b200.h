@@ -233,9 +233,15 @@ int rk_afm_bwd(const rk_field_t* fields, int F, const float* w1, const float* b1
                float* g_b1, float* g_w2, float* g_b2, float* partials, int n_ctas,
                int32_t* err_flag, rk_stream_t stream);
 /* The same forward with the attention MLP on the tensor cores (tcgen05.mma, split-bf16 operands
- * hi.hi + lo.hi + hi.lo, fp32 accumulation in TMEM); same arguments and outputs as rk_afm_fwd. */
+ * hi.hi + lo.hi + hi.lo, fp32 accumulation in TMEM); same arguments and outputs as rk_afm_fwd, plus
+ * `tiles`: NULL, or rk_afm_tile_bytes() bytes of scratch (128-byte aligned) that the forward fills
+ * once (one small prologue launch) with the weights' operand tiles for BOTH directions; every CTA
+ * then fetches them by bulk (TMA) copy instead of converting them itself.  rk_afm_tc_bwd reads
+ * what the forward wrote: pass the same buffer, untouched in between (or NULL). */
+int rk_afm_tile_bytes(void);
 int rk_afm_tc_fwd(const rk_field_t* fields, int F, const float* w1, const float* b1, const float* w2,
-                  const float* b2, int A, int64_t B, float* out, int32_t* err_flag, rk_stream_t stream);
+                  const float* b2, int A, int64_t B, float* out, void* tiles, int32_t* err_flag,
+                  rk_stream_t stream);
 /* The backward on the tensor cores: same arguments and outputs as rk_afm_bwd, with
  * n_ctas = rk_afm_tc_bwd_ctas(B, F).  The hidden layer only enters through its 0/1 ReLU mask
  * (exact in bf16), the other operands are split-bf16; the weight-gradient accumulator lives in
@@ -247,7 +253,7 @@ int rk_afm_tc_bwd_ctas(int64_t B, int F);
 int rk_afm_tc_bwd(const rk_field_t* fields, int F, const float* w1, const float* b1, const float* w2,
                   const float* b2, int A, int64_t B, const float* g_out, float* g_rows, float* g_w1,
                   float* g_b1, float* g_w2, float* g_b2, float* partials, int n_ctas,
-                  int32_t* err_flag, rk_stream_t stream);
+                  const void* tiles, int32_t* err_flag, rk_stream_t stream);
 
 /* ---- fused tower layers: Dice (DIN/din.py:26-36) and the BatchNorm1d that
  *      follows it in the DIN tower (DIN/din.py:272-285), training mode ------------------------
