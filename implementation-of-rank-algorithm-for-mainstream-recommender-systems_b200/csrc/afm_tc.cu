@@ -609,6 +609,7 @@ afm_bwd_tc_kernel(const __grid_constant__ AfmTcParams p, const float* __restrict
                 for (int j2 = 0; j2 < 4; ++j2) {
                     const int j = 8 * c + 2 * j2;
                     const float x0 = h[j] + sm.bias[64 * ch + j], x1 = h[j + 1] + sm.bias[64 * ch + j + 1];
+                    h[j] = x0; h[j + 1] = x1;            // kept for the rare path below
                     closest = fminf(closest, fminf(fabsf(x0), fabsf(x1)));
                     sc = fmaf(fmaxf(x0, 0.f), sm.w2[64 * ch + j], sc);
                     sc = fmaf(fmaxf(x1, 0.f), sm.w2[64 * ch + j + 1], sc);
@@ -616,12 +617,15 @@ afm_bwd_tc_kernel(const __grid_constant__ AfmTcParams p, const float* __restrict
                 }
                 *reinterpret_cast<uint4*>(panel + tid * 128 + ((c ^ (tid & 7)) << 4)) = make_uint4(w[0], w[1], w[2], w[3]);
             }
-            if (__any_sync(kFull, closest < band)) {     // rare, warp-uniform: walk the chunk column by column
-#pragma unroll 1
-                for (int j = 0; j < 64; ++j) {
-                    const float x = tmem_ld1(my_tmem + 64 * ch + j) + sm.bias[64 * ch + j];
-                    if (fabsf(x) < band) recheck(64 * ch + j);
+            if (__any_sync(kFull, closest < band)) {     // rare, warp-uniform: which columns, from the registers
+                uint32_t near0 = 0, near1 = 0;
+#pragma unroll
+                for (int j = 0; j < 32; ++j) {
+                    if (fabsf(h[j]) < band) near0 |= 1u << j;
+                    if (fabsf(h[32 + j]) < band) near1 |= 1u << j;
                 }
+                uint64_t near = ((uint64_t)near1 << 32) | near0;
+                while (near) { recheck(64 * ch + __ffsll((long long)near) - 1); near &= near - 1; }
             }
         }
         if (Ap & 32) {                                   // Ap = 32 or 96: the last 32 columns
@@ -636,6 +640,7 @@ afm_bwd_tc_kernel(const __grid_constant__ AfmTcParams p, const float* __restrict
                 for (int j2 = 0; j2 < 4; ++j2) {
                     const int j = 8 * c + 2 * j2;
                     const float x0 = h[j] + sm.bias[Ap - 32 + j], x1 = h[j + 1] + sm.bias[Ap - 32 + j + 1];
+                    h[j] = x0; h[j + 1] = x1;
                     closest = fminf(closest, fminf(fabsf(x0), fabsf(x1)));
                     sc = fmaf(fmaxf(x0, 0.f), sm.w2[Ap - 32 + j], sc);
                     sc = fmaf(fmaxf(x1, 0.f), sm.w2[Ap - 32 + j + 1], sc);
@@ -645,11 +650,11 @@ afm_bwd_tc_kernel(const __grid_constant__ AfmTcParams p, const float* __restrict
                 *reinterpret_cast<uint4*>(panel + tid * 128 + ((cc ^ (tid & 7)) << 4)) = make_uint4(w[0], w[1], w[2], w[3]);
             }
             if (__any_sync(kFull, closest < band)) {
-#pragma unroll 1
-                for (int j = 0; j < 32; ++j) {
-                    const float x = tmem_ld1(my_tmem + (Ap - 32) + j) + sm.bias[Ap - 32 + j];
-                    if (fabsf(x) < band) recheck(Ap - 32 + j);
-                }
+                uint32_t near0 = 0;
+#pragma unroll
+                for (int j = 0; j < 32; ++j)
+                    if (fabsf(h[j]) < band) near0 |= 1u << j;
+                while (near0) { recheck(Ap - 32 + __ffs(near0) - 1); near0 &= near0 - 1; }
             }
         }
         sm.score[tid] = sc;

@@ -123,6 +123,40 @@ __device__ __forceinline__ void bst_load_x(const BstParams& p, int64_t b, int t,
     }
 }
 
+// One tile ahead: this thread's gather index of `tile` (0 for rows past its end, a dense x input, or no such
+// tile) is loaded while the current tile is computed, and half-way through the tile the row it names, the
+// sample's length and the upstream-gradient rows are pulled into L2 — the row gather at the top of a tile then
+// pays one L2 latency instead of an index -> row chain to DRAM.
+__device__ __forceinline__ int64_t bst_tile_index(const BstParams& p, int64_t tile, int s, int t, int tid) {
+    if (p.x_in || tile >= p.n_tiles) return 0;
+    const int64_t b0 = tile * p.S;
+    const int ns = (int)((p.B - b0) < p.S ? (p.B - b0) : p.S);
+    return tid < ns * p.T ? __ldg(p.idx + (b0 + s) * p.T + t) : 0;
+}
+__device__ __forceinline__ void prefetch_l2(const void* ptr) { asm volatile("prefetch.global.L2 [%0];" ::"l"(ptr)); }
+__device__ __forceinline__ void bst_load_x_at(const BstParams& p, int64_t b, int t, int64_t idx, float (&x)[16], int32_t* err_flag) {
+    const float* src = p.x_in ? p.x_in + (b * p.T + t) * 16 : p.table + checked_row(idx, p.table_rows, err_flag) * 16;
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+        const float4 v = __ldg(reinterpret_cast<const float4*>(src) + c);
+        x[4 * c] = v.x; x[4 * c + 1] = v.y; x[4 * c + 2] = v.z; x[4 * c + 3] = v.w;
+    }
+}
+// rows of the next tile into L2; true when this thread owns a row there
+__device__ __forceinline__ bool bst_prefetch_next(const BstParams& p, int64_t tile_n, int s, int t, int tid, int64_t idx_next,
+                                                 int64_t* b_next) {
+    if (tile_n >= p.n_tiles) return false;
+    const int64_t b0 = tile_n * p.S;
+    const int ns = (int)((p.B - b0) < p.S ? (p.B - b0) : p.S);
+    if (tid >= ns * p.T) return false;
+    const int64_t b = b0 + s;
+    if (p.x_in) prefetch_l2(p.x_in + (b * p.T + t) * 16);
+    else prefetch_l2(p.table + ((uint64_t)idx_next < (uint64_t)p.table_rows ? idx_next : 0) * 16);
+    if (t == 0) prefetch_l2(p.seq_len + b);
+    *b_next = b;
+    return true;
+}
+
 // Scores, masked softmax and context of one query row against the L live keys of its sample.
 // exp of the attention kernels: expf on the fp32 path (1e-5 parity), the hardware ex2-based __expf on the tensor-core
 // path (2 instructions instead of ~15; ~1e-6 relative, far inside that path's 2e-2 bar)
@@ -170,8 +204,14 @@ __device__ __forceinline__ void bst_attend(const float (&q)[16], const float* __
     // L == 0: every key masked -> 0/0 = NaN, exactly as softmax over all -inf in the reference
 #pragma unroll
     for (int h = 0; h < H; ++h) {
+        if (FAST) {                      // one reciprocal per head (inf * 0 = NaN keeps the L == 0 case)
+            const float inv = 1.0f / l[h];
 #pragma unroll
-        for (int j = 0; j < DH; ++j) ctx[h * DH + j] = ctx[h * DH + j] / l[h];
+            for (int j = 0; j < DH; ++j) ctx[h * DH + j] *= inv;
+        } else {
+#pragma unroll
+            for (int j = 0; j < DH; ++j) ctx[h * DH + j] = ctx[h * DH + j] / l[h];
+        }
         m_out[h] = m[h];
         l_out[h] = l[h];
     }

@@ -127,20 +127,23 @@ bst_fwd_tc_kernel(const __grid_constant__ BstParams p, float* __restrict__ y_out
         fence_after();
     };
 
+    const int s_row = tid / T, t_row = tid - s_row * T;          // this thread's (sample, position) in every tile it is live in
+    int64_t idx_cur = bst_tile_index(p, blockIdx.x, s_row, t_row, tid);
     for (int64_t tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
         const int64_t b0 = tile * p.S;
         const int ns = (int)((p.B - b0) < p.S ? (p.B - b0) : p.S);
         const int rows = ns * T;
         const bool on = tid < rows;
-        const int s = on ? tid / T : 0, t = on ? tid - s * T : 0;
+        const int s = on ? s_row : 0, t = on ? t_row : 0;
         const int64_t b = b0 + s;
+        const int64_t idx_next = bst_tile_index(p, tile + gridDim.x, s_row, t_row, tid);   // in flight during this tile
         float x[16], qk[16];
 #pragma unroll
         for (int i = 0; i < 16; ++i) { x[i] = 0.f; qk[i] = 0.f; }
         int L = 0;
         if (on) {
             L = bst_len(p, b);
-            bst_load_x(p, b, t, x, err_flag);
+            bst_load_x_at(p, b, t, idx_cur, x, err_flag);
 #pragma unroll
             for (int i = 0; i < 16; ++i) qk[i] = x[i] + sm.pos[t * 16 + i];
         }
@@ -176,6 +179,11 @@ bst_fwd_tc_kernel(const __grid_constant__ BstParams p, float* __restrict__ y_out
         if (on) {
             float mh[H], lh[H];
             bst_attend<H, true>(q, sm.ks, sm.vs, s * T, L, ctx, mh, lh);
+        }
+        {
+            int64_t b_next;
+            bst_prefetch_next(p, tile + gridDim.x, s_row, t_row, tid, idx_next, &b_next);
+            idx_cur = idx_next;
         }
         const BstDrop drop = bst_drop_masks(p, b * T + t);
         store_slot_split(sm.a_hi, sm.a_lo, tid, 0, ctx);
@@ -270,7 +278,7 @@ struct BtBwdSmem {
     uint8_t *wat_hi, *wat_lo;                       // Wq^T|Wk^T|Wv^T|Wo^T
     float *qs, *ks, *vs, *dc;        // [128][kBstLd]
     float *mrow, *lrow, *delta;      // [128][H]
-    float *pos, *vec;
+    float *pos, *vec, *pacc;         // pacc [T][16]: this CTA's position-table gradient, element e owned by thread e % 128
     uint64_t* bar;
     uint32_t* tmem_slot;
     __device__ BtBwdSmem(uint8_t* base, int T, int H) {
@@ -290,12 +298,13 @@ struct BtBwdSmem {
         delta = (float*)p; p += sizeof(float) * kBstRows * H;
         pos = (float*)p; p += sizeof(float) * T * 16;
         vec = (float*)p; p += sizeof(float) * 160;
+        pacc = (float*)p; p += sizeof(float) * T * 16;
         bar = (uint64_t*)p;       p += 8;
         tmem_slot = (uint32_t*)p;
     }
     static size_t bytes(int T, int H) {
         return 1024 + 3 * 128 * 128 + 6 * 16 * 128 + sizeof(float) * (4 * kBstRows * kBstLd + 3 * kBstRows * H) +
-               sizeof(float) * ((size_t)T * 16 + 160) + 16;
+               sizeof(float) * ((size_t)T * 32 + 160) + 16;
     }
 };
 
@@ -350,7 +359,7 @@ bst_bwd_tc_kernel(const __grid_constant__ BstParams p, const float* __restrict__
     stage_weight_tiles(p, sm.wa_hi, sm.wa_lo, sm.wb_hi, sm.wb_lo, tid, kBtThreads);
     stage_weight_tiles_t(p, sm.wat_hi, sm.wat_lo, sm.wb_hi, sm.wb_lo, tid, kBtThreads);
     for (int i = tid; i < 160; i += kBtThreads) sm.vec[i] = __ldg(p.vec[i >> 4] + (i & 15));
-    for (int i = tid; i < T * 16; i += kBtThreads) sm.pos[i] = __ldg(p.pos + i);
+    for (int i = tid; i < T * 16; i += kBtThreads) { sm.pos[i] = __ldg(p.pos + i); sm.pacc[i] = 0.f; }
     {   // slot 3 of every X line: a one in its first element (the column of ones of the weight-gradient products)
         float one[8] = {1.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f}, zero[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
         store_chunk(sm.x_hi, tid, 6, one);
@@ -374,9 +383,6 @@ bst_bwd_tc_kernel(const __grid_constant__ BstParams p, const float* __restrict__
     const uint64_t xh = umma_desc_mn(smem_u32(sm.x_hi), 128 * 128), gh = umma_desc_mn(smem_u32(sm.g_hi), 128 * 128),
                    lo_addr = umma_desc_mn(smem_u32(sm.lo), 128 * 128);
     uint32_t ph = 0;
-    float pacc[16];
-#pragma unroll
-    for (int i = 0; i < 16; ++i) pacc[i] = 0.f;
     bool first_tile = true;
 
     auto round_trip = [&](auto issue) {
@@ -396,14 +402,17 @@ bst_bwd_tc_kernel(const __grid_constant__ BstParams p, const float* __restrict__
 #pragma unroll
     for (int i = 0; i < 16; ++i) zero16[i] = 0.f;
 
+    const int s_row = tid / T, t_row = tid - s_row * T;
+    int64_t idx_cur = bst_tile_index(p, blockIdx.x, s_row, t_row, tid);
     for (int64_t tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
         const int64_t b0 = tile * p.S;
         const int ns = (int)((p.B - b0) < p.S ? (p.B - b0) : p.S);
         const int rows = ns * T;
         const bool on = tid < rows;
-        const int s = on ? tid / T : 0, t = on ? tid - s * T : 0;
+        const int s = on ? s_row : 0, t = on ? t_row : 0;
         const int64_t b = b0 + s;
         const int row0 = s * T;
+        const int64_t idx_next = bst_tile_index(p, tile + gridDim.x, s_row, t_row, tid);
         PROF(0); PROF_COUNT(12);
         // ---- A. recompute the forward
         float qk[16];
@@ -414,7 +423,7 @@ bst_bwd_tc_kernel(const __grid_constant__ BstParams p, const float* __restrict__
             for (int i = 0; i < 16; ++i) { x[i] = 0.f; qk[i] = 0.f; }
             if (on) {
                 L = bst_len(p, b);
-                bst_load_x(p, b, t, x, err_flag);
+                bst_load_x_at(p, b, t, idx_cur, x, err_flag);
 #pragma unroll
                 for (int i = 0; i < 16; ++i) qk[i] = x[i] + sm.pos[t * 16 + i];
             }
@@ -454,6 +463,14 @@ bst_bwd_tc_kernel(const __grid_constant__ BstParams p, const float* __restrict__
             for (int h = 0; h < H; ++h) { sm.mrow[tid * H + h] = mh[h]; sm.lrow[tid * H + h] = 1.0f / lh[h]; }
         }
         PROF(2);
+        {
+            int64_t b_next;
+            if (bst_prefetch_next(p, tile + gridDim.x, s_row, t_row, tid, idx_next, &b_next)) {
+                if (g_y) prefetch_l2(g_y + (b_next * T + t_row) * 16);
+                if (g_pool && t_row == 0) prefetch_l2(g_pool + b_next * g_pool_ld);
+            }
+            idx_cur = idx_next;
+        }
         const BstDrop drop = bst_drop_masks(p, b * T + t);
         store_slot_split(sm.x_hi, sm.lo, tid, 2, ctx);                    // slot 2: ctx, kept for stage B
         round_trip([&]() { mma_proj(tmem + 48, x_desc, 2, wa_desc, MO); });
@@ -664,15 +681,12 @@ bst_bwd_tc_kernel(const __grid_constant__ BstParams p, const float* __restrict__
             store_row(sm.dc + tid * kBstLd, dqk);
         }
         __syncthreads();
-#pragma unroll
-        for (int i = 0; i < 16; ++i) {
-            const int e = tid + i * kBtThreads;
-            if (e < T * 16) {
-                const int tt = e >> 4, n = e & 15;
-                float a = pacc[i];
-                for (int ss = 0; ss < ns; ++ss) a += sm.dc[(ss * T + tt) * kBstLd + n];
-                pacc[i] = a;
-            }
+        for (int e = tid; e < T * 16; e += kBtThreads) {          // same thread, same order every tile: no barrier on pacc
+            const int tt = e >> 4, n = e & 15;
+            float a = sm.pacc[e];
+#pragma unroll 2
+            for (int ss = 0; ss < ns; ++ss) a += sm.dc[(ss * T + tt) * kBstLd + n];
+            sm.pacc[e] = a;
         }
         first_tile = false;
         __syncthreads();
@@ -683,11 +697,7 @@ bst_bwd_tc_kernel(const __grid_constant__ BstParams p, const float* __restrict__
 
     // ---- per-CTA partials: the position rows from registers, everything else out of TMEM (lanes 0..63)
     float* out = partials + (int64_t)blockIdx.x * (T * 16 + 6 * 256 + 160);
-#pragma unroll
-    for (int i = 0; i < 16; ++i) {
-        const int e = tid + i * kBtThreads;
-        if (e < T * 16) out[e] = pacc[i];
-    }
+    for (int e = tid; e < T * 16; e += kBtThreads) out[e] = sm.pacc[e];
     float* o = out + T * 16;
     fence_after();
     if (first_tile) {                              // a CTA that owned no tile: nothing was accumulated

@@ -627,6 +627,11 @@ __device__ __forceinline__ int tile_row0(const int* len, int s_begin, int s) {
     return r0;
 }
 
+// kstage rows are 64 bytes apart, so the same 16-byte chunk of 32 consecutive rows would fall on two
+// bank groups (16-way conflict for the LDGSTS writes and the LDS.128 read-back).  Chunk c of row r
+// lives at position c ^ ((r >> 1) & 3): eight consecutive rows then cover all eight bank groups.
+__device__ __forceinline__ int kstage_chunk(int row, int c) { return c ^ ((row >> 1) & 3); }
+
 // Asynchronous staging of the tile's history rows: a thread that owns a live row issues four 16-byte
 // cp.async (LDGSTS) copies of it into its own slot of kstage and commits the group; it later waits
 // for its own group only (each thread reads back just the row it copied, so no barrier is needed).
@@ -641,7 +646,7 @@ __device__ __forceinline__ void issue_rows(const DinParams& p, const TcFwdSmem& 
         const uint32_t dst = smem_u32(sm.kstage + tid * 16);
 #pragma unroll
         for (int c = 0; c < 4; ++c)
-            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst + 16 * c), "l"(src + 4 * c) : "memory");
+            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst + 16 * kstage_chunk(tid, c)), "l"(src + 4 * c) : "memory");
     }
     asm volatile("cp.async.commit_group;" ::: "memory");
 }
@@ -881,7 +886,7 @@ din_fwd_tc_kernel(const __grid_constant__ DinParams p, float* __restrict__ conca
             if (cur.on) {
 #pragma unroll
                 for (int c = 0; c < 4; ++c) {
-                    const float4 v = *reinterpret_cast<const float4*>(sm.kstage + tid * 16 + 4 * c);
+                    const float4 v = *reinterpret_cast<const float4*>(sm.kstage + tid * 16 + 4 * kstage_chunk(tid, c));
                     k[4 * c] = v.x; k[4 * c + 1] = v.y; k[4 * c + 2] = v.z; k[4 * c + 3] = v.w;
                 }
             }
@@ -1264,7 +1269,7 @@ din_bwd_tc_kernel(const __grid_constant__ DinParams p, const float* __restrict__
                 const uint32_t dst = smem_u32(sm.kstage + tid * 16);
 #pragma unroll
                 for (int c = 0; c < 4; ++c)
-                    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst + 16 * c), "l"(p.his_w + row * 16 + 4 * c) : "memory");
+                    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst + 16 * kstage_chunk(tid, c)), "l"(p.his_w + row * 16 + 4 * c) : "memory");
             }
             asm volatile("cp.async.commit_group;" ::: "memory");
         }
@@ -1284,7 +1289,7 @@ din_bwd_tc_kernel(const __grid_constant__ DinParams p, const float* __restrict__
                         const uint32_t dst = smem_u32(sm.kstage + tid * 16);
 #pragma unroll
                         for (int c = 0; c < 4; ++c)
-                            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst + 16 * c), "l"(p.his_w + row * 16 + 4 * c) : "memory");
+                            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst + 16 * kstage_chunk(tid, c)), "l"(p.his_w + row * 16 + 4 * c) : "memory");
                     }
                     asm volatile("cp.async.commit_group;" ::: "memory");
                 } else if ((int64_t)group_slot < n_groups) {
@@ -1300,7 +1305,7 @@ din_bwd_tc_kernel(const __grid_constant__ DinParams p, const float* __restrict__
                 if (on) {
 #pragma unroll
                     for (int c = 0; c < 4; ++c) {
-                        const float4 v = *reinterpret_cast<const float4*>(sm.kstage + tid * 16 + 4 * c);
+                        const float4 v = *reinterpret_cast<const float4*>(sm.kstage + tid * 16 + 4 * kstage_chunk(tid, c));
                         k[4 * c] = v.x; k[4 * c + 1] = v.y; k[4 * c + 2] = v.z; k[4 * c + 3] = v.w;
                     }
 #pragma unroll
