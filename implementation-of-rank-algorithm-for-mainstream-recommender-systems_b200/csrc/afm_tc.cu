@@ -92,12 +92,18 @@ __device__ __forceinline__ void store_line_split(uint8_t* tile, int r, const flo
 // cp.async) while the rows of tile t+1 are gathered with 16-byte cp.async from the indices that
 // landed one tile earlier, all of it issued in the shadow of tile t's first MMA.  Only the very
 // first tile of a CTA reads its indices with ordinary loads.
+// item / d for 0 <= item < 1024, 1 <= d <= 16, through a float reciprocal (exact there: (item + 0.5) / d is at
+// least 1/32 away from an integer, the product's rounding error is below 1e-4); a runtime integer division is
+// ~20 instructions, and these loops decompose two or three item numbers per tile
+__device__ __forceinline__ int small_div(int item, float inv_d) { return (int)(((float)item + 0.5f) * inv_d); }
+
 __device__ __forceinline__ void afm_issue_idx(const AfmTcParams& p, int64_t* ix, int64_t tile, int tid) {
     const int F = p.fs.F;
+    const float inv_f = 1.0f / (float)F;
     const int64_t b0 = tile * p.S;
     const int n_s = (int)((p.B - b0) < p.S ? (p.B - b0) : p.S);
     for (int item = tid; item < n_s * F; item += kAfmTcThreads) {
-        const int s = item / F, f = item - s * F;
+        const int s = small_div(item, inv_f), f = item - s * F;
         cp_async8(ix + item, p.fs.idx[f] + b0 + s);
     }
 }
@@ -106,8 +112,9 @@ __device__ __forceinline__ void afm_issue_rows(const AfmTcParams& p, float* e, c
     const int F = p.fs.F, c4 = p.D >> 2;
     const int64_t b0 = tile * p.S;
     const int n_s = (int)((p.B - b0) < p.S ? (p.B - b0) : p.S);
+    const float inv_c4 = 1.0f / (float)c4, inv_f = 1.0f / (float)F;
     for (int item = tid; item < n_s * F * c4; item += kAfmTcThreads) {
-        const int c = item % c4, sf = item / c4, f = sf % F, s = sf / F;
+        const int sf = small_div(item, inv_c4), c = item - sf * c4, s = small_div(sf, inv_f), f = sf - s * F;
         const int64_t raw = ix ? ix[sf] : __ldg(p.fs.idx[f] + b0 + s);
         const int64_t row = checked_row(raw, p.fs.rows[f], err_flag);
         cp_async16(e + (s * F + f) * p.estride + 4 * c, p.fs.weight[f] + row * p.D + 4 * c);
@@ -186,7 +193,7 @@ afm_weight_tiles_kernel(const float* __restrict__ w1, const float* __restrict__ 
 }
 
 template <int KP>
-__global__ void __launch_bounds__(kAfmTcThreads)
+__global__ void __launch_bounds__(kAfmTcThreads, 4)      // 4 CTAs / SM: at most 128 registers
 afm_fwd_tc_kernel(const __grid_constant__ AfmTcParams p, float* __restrict__ out, int32_t* err_flag) {
     extern __shared__ uint8_t afm_tc_raw[];
     uint8_t* base = afm_tc_raw + ((1024u - (smem_u32(afm_tc_raw) & 1023u)) & 1023u);
@@ -236,8 +243,9 @@ afm_fwd_tc_kernel(const __grid_constant__ AfmTcParams p, float* __restrict__ out
     uint32_t phase = 0;
     int buf = 0;
     const int c4 = D >> 2;
-    int parts = 1;                                   // power of two, <= 8, parts * S * D/4 <= threads when possible
-    while (parts < 8 && 2 * parts * p.S * c4 <= kAfmTcThreads) parts <<= 1;
+    int parts = 1, parts_sh = 0;                     // power of two, <= 8, parts * S * D/4 <= threads when possible
+    while (parts < 8 && 2 * parts * p.S * c4 <= kAfmTcThreads) { parts <<= 1; ++parts_sh; }
+    const int s_row = tid / P, pr_row = tid - s_row * P;        // this thread's (sample, pair) in every tile
     PROF(0);
 
     for (; tile < p.n_tiles; tile += gridDim.x, buf ^= 1) {
@@ -249,7 +257,7 @@ afm_fwd_tc_kernel(const __grid_constant__ AfmTcParams p, float* __restrict__ out
         PROF(1); PROF_COUNT(12);
         // ---- this thread's pair row v = e_i * e_j, split into the A operand line
         const bool on = tid < n_rows;
-        const int s = on ? tid / P : 0, pr = on ? tid - s * P : 0;
+        const int s = on ? s_row : 0, pr = on ? pr_row : 0;
         float v[KP];
 #pragma unroll
         for (int d = 0; d < KP; ++d) v[d] = 0.f;
@@ -294,13 +302,27 @@ afm_fwd_tc_kernel(const __grid_constant__ AfmTcParams p, float* __restrict__ out
             float h[64];
             tmem_ld64(my_tmem + 64 * ch, h);
 #pragma unroll
-            for (int j = 0; j < 64; ++j) sc = fmaf(fmaxf(h[j] + sm.bias[64 * ch + j], 0.f), sm.w2[64 * ch + j], sc);
+            for (int c = 0; c < 16; ++c) {               // 16-byte broadcast loads of bias and w2
+                const float4 bb = *reinterpret_cast<const float4*>(sm.bias + 64 * ch + 4 * c);
+                const float4 ww = *reinterpret_cast<const float4*>(sm.w2 + 64 * ch + 4 * c);
+                sc = fmaf(fmaxf(h[4 * c] + bb.x, 0.f), ww.x, sc);
+                sc = fmaf(fmaxf(h[4 * c + 1] + bb.y, 0.f), ww.y, sc);
+                sc = fmaf(fmaxf(h[4 * c + 2] + bb.z, 0.f), ww.z, sc);
+                sc = fmaf(fmaxf(h[4 * c + 3] + bb.w, 0.f), ww.w, sc);
+            }
         }
         if (p.Ap & 32) {
             float h[32];
             tmem_ld32(my_tmem + (p.Ap - 32), h);
 #pragma unroll
-            for (int j = 0; j < 32; ++j) sc = fmaf(fmaxf(h[j] + sm.bias[p.Ap - 32 + j], 0.f), sm.w2[p.Ap - 32 + j], sc);
+            for (int c = 0; c < 8; ++c) {
+                const float4 bb = *reinterpret_cast<const float4*>(sm.bias + p.Ap - 32 + 4 * c);
+                const float4 ww = *reinterpret_cast<const float4*>(sm.w2 + p.Ap - 32 + 4 * c);
+                sc = fmaf(fmaxf(h[4 * c] + bb.x, 0.f), ww.x, sc);
+                sc = fmaf(fmaxf(h[4 * c + 1] + bb.y, 0.f), ww.y, sc);
+                sc = fmaf(fmaxf(h[4 * c + 2] + bb.z, 0.f), ww.z, sc);
+                sc = fmaf(fmaxf(h[4 * c + 3] + bb.w, 0.f), ww.w, sc);
+            }
         }
         sm.score[tid] = sc;
         fence_before();
@@ -339,8 +361,8 @@ afm_fwd_tc_kernel(const __grid_constant__ AfmTcParams p, float* __restrict__ out
         // `parts` adjacent lanes share one 16-byte output chunk: lane `part` adds pairs part, part + parts, ...
         // and the parts are folded by a fixed shuffle tree
         for (int it0 = 0; it0 < n_s * c4 * parts; it0 += kAfmTcThreads) {
-            const int item = it0 + tid, o = item / parts, part = item - o * parts;
-            const int ss = o / c4, c = o - ss * c4;
+            const int item = it0 + tid, o = item >> parts_sh, part = item & (parts - 1);
+            const int ss = small_div(o, 1.0f / (float)c4), c = o - ss * c4;
             float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
             if (o < n_s * c4)
                 for (int q = part; q < P; q += parts) {
@@ -426,7 +448,7 @@ __device__ __forceinline__ void afm_issue_gout(const AfmTcParams& p, float* dst,
     const int64_t b0 = tile * p.S;
     const int n_s = (int)((p.B - b0) < p.S ? (p.B - b0) : p.S);
     for (int item = tid; item < n_s * c4; item += kAfmTcThreads) {
-        const int s = item / c4, c = item - s * c4;
+        const int s = small_div(item, 1.0f / (float)c4), c = item - s * c4;
         asm volatile("cp.async.cg.shared.global [%0], [%1], 16;"
                      ::"r"(smem_u32(dst + s * 32 + 4 * c)), "l"(g_out + (b0 + s) * p.D + 4 * c) : "memory");
     }
@@ -516,6 +538,7 @@ afm_bwd_tc_kernel(const __grid_constant__ AfmTcParams p, const float* __restrict
     int buf = 0;
     bool first_tile = true;
     float gb2_acc = 0.f;
+    const int s_row = tid / P, pr_row = tid - s_row * P;        // this thread's (sample, pair) in every tile
     PROF(0);
 
     for (; tile < p.n_tiles; tile += gridDim.x, buf ^= 1) {
@@ -526,7 +549,7 @@ afm_bwd_tc_kernel(const __grid_constant__ AfmTcParams p, const float* __restrict
         __syncthreads();
         PROF(1); PROF_COUNT(12);
         const bool on = tid < n_rows;
-        const int s = on ? tid / P : 0, pr = on ? tid - s * P : 0;
+        const int s = on ? s_row : 0, pr = on ? pr_row : 0;
         const float* esm = sm.e[buf];
         float v[KP];
         float ga = 0.f;
@@ -605,14 +628,19 @@ afm_bwd_tc_kernel(const __grid_constant__ AfmTcParams p, const float* __restrict
 #pragma unroll
             for (int c = 0; c < 8; ++c) {
                 uint32_t w[4];
+                float bb[8], ww[8];                      // 16-byte broadcast loads: bias and w2 of these 8 columns
+                *reinterpret_cast<float4*>(bb)     = *reinterpret_cast<const float4*>(sm.bias + 64 * ch + 8 * c);
+                *reinterpret_cast<float4*>(bb + 4) = *reinterpret_cast<const float4*>(sm.bias + 64 * ch + 8 * c + 4);
+                *reinterpret_cast<float4*>(ww)     = *reinterpret_cast<const float4*>(sm.w2 + 64 * ch + 8 * c);
+                *reinterpret_cast<float4*>(ww + 4) = *reinterpret_cast<const float4*>(sm.w2 + 64 * ch + 8 * c + 4);
 #pragma unroll
                 for (int j2 = 0; j2 < 4; ++j2) {
                     const int j = 8 * c + 2 * j2;
-                    const float x0 = h[j] + sm.bias[64 * ch + j], x1 = h[j + 1] + sm.bias[64 * ch + j + 1];
+                    const float x0 = h[j] + bb[2 * j2], x1 = h[j + 1] + bb[2 * j2 + 1];
                     h[j] = x0; h[j + 1] = x1;            // kept for the rare path below
                     closest = fminf(closest, fminf(fabsf(x0), fabsf(x1)));
-                    sc = fmaf(fmaxf(x0, 0.f), sm.w2[64 * ch + j], sc);
-                    sc = fmaf(fmaxf(x1, 0.f), sm.w2[64 * ch + j + 1], sc);
+                    sc = fmaf(fmaxf(x0, 0.f), ww[2 * j2], sc);
+                    sc = fmaf(fmaxf(x1, 0.f), ww[2 * j2 + 1], sc);
                     w[j2] = (x0 > 0.f ? 0x3F80u : 0u) | (x1 > 0.f ? 0x3F800000u : 0u);
                 }
                 *reinterpret_cast<uint4*>(panel + tid * 128 + ((c ^ (tid & 7)) << 4)) = make_uint4(w[0], w[1], w[2], w[3]);
@@ -636,14 +664,19 @@ afm_bwd_tc_kernel(const __grid_constant__ AfmTcParams p, const float* __restrict
 #pragma unroll
             for (int c = 0; c < 4; ++c) {
                 uint32_t w[4];
+                float bb[8], ww[8];
+                *reinterpret_cast<float4*>(bb)     = *reinterpret_cast<const float4*>(sm.bias + Ap - 32 + 8 * c);
+                *reinterpret_cast<float4*>(bb + 4) = *reinterpret_cast<const float4*>(sm.bias + Ap - 32 + 8 * c + 4);
+                *reinterpret_cast<float4*>(ww)     = *reinterpret_cast<const float4*>(sm.w2 + Ap - 32 + 8 * c);
+                *reinterpret_cast<float4*>(ww + 4) = *reinterpret_cast<const float4*>(sm.w2 + Ap - 32 + 8 * c + 4);
 #pragma unroll
                 for (int j2 = 0; j2 < 4; ++j2) {
                     const int j = 8 * c + 2 * j2;
-                    const float x0 = h[j] + sm.bias[Ap - 32 + j], x1 = h[j + 1] + sm.bias[Ap - 32 + j + 1];
+                    const float x0 = h[j] + bb[2 * j2], x1 = h[j + 1] + bb[2 * j2 + 1];
                     h[j] = x0; h[j + 1] = x1;
                     closest = fminf(closest, fminf(fabsf(x0), fabsf(x1)));
-                    sc = fmaf(fmaxf(x0, 0.f), sm.w2[Ap - 32 + j], sc);
-                    sc = fmaf(fmaxf(x1, 0.f), sm.w2[Ap - 32 + j + 1], sc);
+                    sc = fmaf(fmaxf(x0, 0.f), ww[2 * j2], sc);
+                    sc = fmaf(fmaxf(x1, 0.f), ww[2 * j2 + 1], sc);
                     w[j2] = (x0 > 0.f ? 0x3F80u : 0u) | (x1 > 0.f ? 0x3F800000u : 0u);
                 }
                 const int cc = (((Ap - 32) & 63) >> 3) + c;
@@ -762,7 +795,8 @@ afm_bwd_tc_kernel(const __grid_constant__ AfmTcParams p, const float* __restrict
         // g_e[s][f][d] = sum_{g != f} g_v[pair(f,g)][d] * e[s][g][d]
         // one thread per (sample, field, 16-byte chunk); partners in ascending field order (ptab)
         for (int item = tid; item < n_s * F * c4; item += kAfmTcThreads) {
-            const int c = item % c4, sf = item / c4, f = sf % F, ss = sf / F;
+            const int sf = small_div(item, 1.0f / (float)c4), c = item - sf * c4;
+            const int ss = small_div(sf, 1.0f / (float)F), f = sf - ss * F;
             float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll 3
             for (int k = 0; k < F - 1; ++k) {
@@ -809,11 +843,17 @@ afm_bwd_tc_kernel(const __grid_constant__ AfmTcParams p, const float* __restrict
         if (tid < A) {
             const float w2a = sm.w2[tid];
             float gw2 = sm.bias[tid] * u0;
+            float w1row[KP];
+#pragma unroll
+            for (int c = 0; c < KP / 4; ++c) {           // D is a multiple of 4: 16-byte loads, all in flight together
+                const float4 w = 4 * c < D ? __ldg(reinterpret_cast<const float4*>(p.w1 + tid * D) + c) : make_float4(0.f, 0.f, 0.f, 0.f);
+                w1row[4 * c] = w.x; w1row[4 * c + 1] = w.y; w1row[4 * c + 2] = w.z; w1row[4 * c + 3] = w.w;
+            }
 #pragma unroll
             for (int d = 0; d < KP; ++d)
                 if (d < D) {
                     outp[tid * D + d] = w2a * u[d];
-                    gw2 = fmaf(__ldg(p.w1 + tid * D + d), u[d], gw2);
+                    gw2 = fmaf(w1row[d], u[d], gw2);
                 }
             outp[A * D + tid]     = w2a * u0;
             outp[A * D + A + tid] = gw2;
