@@ -584,7 +584,7 @@ struct TcFwdSmem {
         att = (float*)p;     p += sizeof(float) * kTcGroup * 16;
         score = (float*)p;   p += sizeof(float) * kRows;
         wt = (float*)p;      p += sizeof(float) * kRows;
-        len = (int*)p;       p += sizeof(int) * kTcGroup;
+        len = (int*)p;       p += sizeof(int) * 3 * kTcGroup;      // [0,8) lengths, [8,17) their prefix sums
         bar_mma = (uint64_t*)p;   p += 8;
         tmem_slot = (uint32_t*)p; p += 8;
         bar_w = (uint64_t*)p;     p += 8;
@@ -597,7 +597,7 @@ struct TcFwdSmem {
     }
     static size_t bytes(int width, int T, int F) {
         return 1024 /* alignment slack */ + 2 * (128 * 128 + 64 * 128 + 32 * 128) + sizeof(float) * kRows * 16 +
-               sizeof(float) * (kH1 + 2 * kH2 + 4 + 2 * kTcGroup * 16 + 2 * kRows) + sizeof(int) * kTcGroup + 32 +
+               sizeof(float) * (kH1 + 2 * kH2 + 4 + 2 * kTcGroup * 16 + 2 * kRows) + sizeof(int) * 3 * kTcGroup + 32 +
                sizeof(int64_t) * kTcGroup * (size_t)(T + 2 + F) + sizeof(int16_t) * (size_t)width;
     }
 };
@@ -608,23 +608,39 @@ struct TcTile {
     int s_end, n_rows, my_s, my_t;
     bool on;
 };
-__device__ __forceinline__ TcTile plan_tile_tc(const int* len, int n_samples, int s_begin, int tid) {
-    TcTile t;
-    int rows = 0, s = s_begin;
-    t.my_s = s_begin; t.my_t = 0; t.on = false;
-    while (s < n_samples && rows + len[s] <= kRows) {
-        if (tid >= rows && tid < rows + len[s]) { t.my_s = s; t.my_t = tid - rows; t.on = true; }
-        rows += len[s];
-        ++s;
+// len[0..8) are the group's clipped lengths, len[8 + i] = len[0] + ... + len[i-1] (i = 0..8): the rows of samples
+// [s_begin, i) are a difference of two prefix sums, so planning a tile is straight-line code on registers instead
+// of a loop of dependent shared-memory loads.
+__device__ __forceinline__ void store_len_prefix(int* len, const int64_t* ix_len, int n_samples, int T, int tid) {
+    if (tid < kTcGroup) len[tid] = tid < n_samples ? clip_len(ix_len[tid], T) : 0;
+    else if (tid < 2 * kTcGroup + 1) {
+        int a = 0;
+        for (int j = 0; j < tid - kTcGroup; ++j) a += j < n_samples ? clip_len(ix_len[j], T) : 0;
+        len[tid] = a;
     }
-    t.s_end = s;
-    t.n_rows = rows;
+}
+__device__ __forceinline__ TcTile plan_tile_tc(const int* len, int n_samples, int s_begin, int tid) {
+    const int4 p0 = *reinterpret_cast<const int4*>(len + kTcGroup), p1 = *reinterpret_cast<const int4*>(len + kTcGroup + 4);
+    const int pre[kTcGroup + 1] = {p0.x, p0.y, p0.z, p0.w, p1.x, p1.y, p1.z, p1.w, len[2 * kTcGroup]};
+    const int base = len[kTcGroup + s_begin];
+    TcTile t;
+    t.s_end = s_begin; t.n_rows = 0;
+    int my_s = s_begin, start = 0;
+#pragma unroll
+    for (int i = 0; i < kTcGroup; ++i) {
+        const int end_i = pre[i + 1] - base;         // rows of samples [s_begin, i]
+        // whole samples while they fit: the prefix sums are monotone, so this holds on one run starting at s_begin
+        const bool fits = i >= s_begin && i < n_samples && end_i <= kRows;
+        if (fits) { t.s_end = i + 1; t.n_rows = end_i; }
+        if (fits && tid >= end_i) { my_s = i + 1; start = end_i; }
+    }
+    t.on = tid < t.n_rows;
+    t.my_s = t.on ? my_s : s_begin;
+    t.my_t = t.on ? tid - start : 0;
     return t;
 }
 __device__ __forceinline__ int tile_row0(const int* len, int s_begin, int s) {
-    int r0 = 0;
-    for (int i = s_begin; i < s; ++i) r0 += len[i];
-    return r0;
+    return len[kTcGroup + s] - len[kTcGroup + s_begin];
 }
 
 // kstage rows are 64 bytes apart, so the same 16-byte chunk of 32 consecutive rows would fall on two
@@ -795,7 +811,7 @@ din_fwd_tc_kernel(const __grid_constant__ DinParams p, float* __restrict__ conca
         const int n_samples = (int)((p.B - b0) < kTcGroup ? (p.B - b0) : kTcGroup);
         wait_rows();                             // this group's indices (issue_idx) have landed ...
         __syncthreads();                         // ... for every thread
-        if (tid < kTcGroup) sm.len[tid] = tid < n_samples ? clip_len(sm.ix_len[tid], T) : 0;
+        store_len_prefix(sm.len, sm.ix_len, n_samples, T, tid);
         if (tid < n_samples * 4) {               // target rows: 4 x 16 bytes per sample, same commit group as the tile rows
             const int s = tid >> 2, c = tid & 3;
             const int64_t row = checked_row(sm.ix_tgt[s], p.tgt_rows, err_flag);
@@ -949,10 +965,15 @@ din_fwd_tc_kernel(const __grid_constant__ DinParams p, float* __restrict__ conca
                     tmem_ld32(my_tmem + 32 * half, v);
                     uint32_t bits = 0;
 #pragma unroll
-                    for (int j = 0; j < 32; ++j) {
-                        v[j] = fmaxf(v[j] + b1[32 * half + j], 0.f);
-                        bits |= (v[j] > 0.f ? 1u : 0u) << j;
+                    for (int c = 0; c < 8; ++c) {            // 16-byte broadcast loads of the bias
+                        const float4 bb = *reinterpret_cast<const float4*>(b1 + 32 * half + 4 * c);
+                        v[4 * c]     = fmaxf(v[4 * c] + bb.x, 0.f);
+                        v[4 * c + 1] = fmaxf(v[4 * c + 1] + bb.y, 0.f);
+                        v[4 * c + 2] = fmaxf(v[4 * c + 2] + bb.z, 0.f);
+                        v[4 * c + 3] = fmaxf(v[4 * c + 3] + bb.w, 0.f);
                     }
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) bits |= (v[j] > 0.f ? 1u : 0u) << j;
                     if (half == 0) m1a = bits; else m1b = bits;
 #pragma unroll
                     for (int c = 0; c < 4; ++c) {
@@ -986,10 +1007,14 @@ din_fwd_tc_kernel(const __grid_constant__ DinParams p, float* __restrict__ conca
                     float sc = b3;
                     uint32_t m2 = 0;
 #pragma unroll
-                    for (int j = 0; j < 32; ++j) {
-                        const float h = fmaxf(v[j] + b2[j], 0.f);
-                        m2 |= (h > 0.f ? 1u : 0u) << j;
-                        sc = fmaf(h, w3[j], sc);
+                    for (int c = 0; c < 8; ++c) {
+                        const float4 bb = *reinterpret_cast<const float4*>(b2 + 4 * c);
+                        const float4 ww = *reinterpret_cast<const float4*>(w3 + 4 * c);
+                        const float h0 = fmaxf(v[4 * c] + bb.x, 0.f), h1 = fmaxf(v[4 * c + 1] + bb.y, 0.f);
+                        const float h2 = fmaxf(v[4 * c + 2] + bb.z, 0.f), h3 = fmaxf(v[4 * c + 3] + bb.w, 0.f);
+                        m2 |= ((h0 > 0.f ? 1u : 0u) | (h1 > 0.f ? 2u : 0u) | (h2 > 0.f ? 4u : 0u) | (h3 > 0.f ? 8u : 0u)) << (4 * c);
+                        sc = fmaf(h0, ww.x, sc); sc = fmaf(h1, ww.y, sc);
+                        sc = fmaf(h2, ww.z, sc); sc = fmaf(h3, ww.w, sc);
                     }
                     sm.score[tid] = sc;
                     if (cur.on && masks) {
@@ -1120,7 +1145,7 @@ struct TcBwdSmem {
         dot = (float*)p;      p += sizeof(float) * 8;
         score = (float*)p;    p += sizeof(float) * kRows;
         wt = (float*)p;       p += sizeof(float) * kRows;
-        len = (int*)p;        p += sizeof(int) * kSamples;
+        len = (int*)p;        p += sizeof(int) * 3 * kSamples;     // [0,8) lengths, [8,17) their prefix sums
         bar = (uint64_t*)p;   p += 8;
         bar_w = (uint64_t*)p; p += 8;
         tmem_slot = (uint32_t*)p;
@@ -1130,7 +1155,7 @@ struct TcBwdSmem {
                2 * pad16(sizeof(float) * kSamples * width) + pad16(sizeof(float) * kSamples * T) +
                pad16(sizeof(uint32_t) * kSamples * T * 3) + pad16(sizeof(int64_t) * kSamples * T) +
                sizeof(int64_t) * kSamples + sizeof(float) * (2 * kSamples + kH2 + 4 * kSamples * 16 + 8 + 2 * kRows) +
-               sizeof(int) * kSamples + 16;
+               sizeof(int) * 3 * kSamples + 16;
     }
 };
 
@@ -1240,7 +1265,7 @@ din_bwd_tc_kernel(const __grid_constant__ DinParams p, const float* __restrict__
         const int n_samples = (int)((p.B - b0) < kSamples ? (p.B - b0) : kSamples);
         wait_rows();                                 // the group's inputs (issue_group_bwd) have landed ...
         __syncthreads();                             // ... for every thread
-        if (tid < kSamples) sm.len[tid] = tid < n_samples ? clip_len(sm.ix_len[tid], T) : 0;
+        store_len_prefix(sm.len, sm.ix_len, n_samples, T, tid);
         for (int i = tid; i < n_samples * D; i += kTcThreads) {
             const int s = i / D, e = i - s * D;
             sm.q[i] = sm.ca[s * W + p.tgt_off + e];
