@@ -113,6 +113,10 @@ class _BstBlock(torch.autograd.Function):
             y = torch.empty(B, T, D_MODEL, dtype=torch.float32, device=dev)
         else:
             pooled = torch.empty(B, D_MODEL, dtype=torch.float32, device=dev)
+        plan = None
+        if from_table and ctx.needs_input_grad[3]:
+            # forked before the forward kernel is queued, so the sort of the sequence ids overlaps it
+            plan = OccurrencePlan([idx], [int(source.shape[0])])
         rc = lib.rk_bst_block_fwd(C.byref(blk), nhead, source.data_ptr() if from_table else None,
                                   _lib.ptr(idx), int(source.shape[0]) if from_table else 0,
                                   None if from_table else source.data_ptr(), seq_len.data_ptr(), B, T,
@@ -126,8 +130,8 @@ class _BstBlock(torch.autograd.Function):
             ctx.cfg, ctx.shape, ctx.from_table = cfg, (B, T), from_table
             ctx.blk, ctx.keep = blk, keep
             ctx.max_len = int(params[0].shape[0])
-            if from_table and ctx.needs_input_grad[3]:
-                ctx.plan = OccurrencePlan([idx], [int(source.shape[0])])
+            if plan is not None:
+                ctx.plan = plan
                 ctx.table = source
             ctx.save_for_backward(seq_len, idx if from_table else None, source)
         return y if pool is None else pooled

@@ -1581,6 +1581,12 @@ int rk_din_bwd(const rk_din_args_t* args, const float* concat_all, const float* 
         RK_CHECK_ARG(smem_tc <= 227 * 1024, "din_bwd: %zu bytes of shared memory (width %d)", smem_tc, p.width);
         RK_CUDA(cudaFuncSetAttribute(tc::din_bwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                      (int)smem_tc));
+        // Two CTAs need ~190 KB; with the carve-out the driver would pick for that (196 KB) nothing else fits on
+        // the SM while they are resident, and the sort of the history ids (plan_sort.cu, 21 KB per CTA, on its own
+        // stream) would have to wait for this kernel to drain.  The full 228 KB leaves it room to run alongside;
+        // this kernel's global traffic is cp.async / streaming and does not miss the L1 it gives up.
+        RK_CUDA(cudaFuncSetAttribute(tc::din_bwd_tc_kernel, cudaFuncAttributePreferredSharedMemoryCarveout,
+                                     (int)cudaSharedmemCarveoutMaxShared));
         // persistent CTAs, two per SM by shared memory; the grid never exceeds the group count
         static const int per_sm = [] {
             const char* e = getenv("RANK_B200_DIN_TC_BWD_CTAS_PER_SM");

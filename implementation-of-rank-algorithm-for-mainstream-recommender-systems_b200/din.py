@@ -165,6 +165,15 @@ class _DinHotPath(torch.autograd.Function):
         norm = torch.empty(B, dtype=torch.float32, device=dev)
         att_w = torch.empty(B, T, dtype=torch.float32, device=dev)
         masks = torch.empty(B, T, 3, dtype=torch.int32, device=dev) if need_grad else None
+        plan = rows = None
+        if need_grad:
+            # forked BEFORE the forward kernel is queued: the plan's side stream waits for what is on the main
+            # stream at this point (the indices), so the sort of the history ids overlaps the forward kernel
+            idx_cols = [keep[1][2 * f + 1] for f in range(F)] + [keep[5], keep[7]]
+            rows = [int(t.shape[0]) for t in cat_tabs] + [int(tgt_w.shape[0]), int(his_w.shape[0])]
+            mode = _lib.LIVE_PREFIX_OR_EMPTY if use_softmax else _lib.LIVE_PREFIX
+            plan = OccurrencePlan(idx_cols, rows, seq_len=[None] * (F + 1) + [keep[8]],
+                                  live_mode=[_lib.LIVE_ALL] * (F + 1) + [mode])
         rc = lib.rk_din_fwd(C.byref(a), concat_all.data_ptr(), norm.data_ptr(), att_w.data_ptr(),
                             _lib.ptr(masks), _lib.err_flag(dev).data_ptr(), _lib.stream_ptr())
         _lib.check(rc, "rk_din_fwd")
@@ -175,11 +184,7 @@ class _DinHotPath(torch.autograd.Function):
             ctx.cfg = cfg
             ctx.args, ctx.keep = a, keep
             ctx.shape = (B, T, D, width, tgt_off)
-            idx_cols = [keep[1][2 * f + 1] for f in range(F)] + [keep[5], keep[7]]
-            rows = [int(t.shape[0]) for t in cat_tabs] + [int(tgt_w.shape[0]), int(his_w.shape[0])]
-            mode = _lib.LIVE_PREFIX_OR_EMPTY if use_softmax else _lib.LIVE_PREFIX
-            ctx.plan = OccurrencePlan(idx_cols, rows, seq_len=[None] * (F + 1) + [keep[8]],
-                                      live_mode=[_lib.LIVE_ALL] * (F + 1) + [mode])
+            ctx.plan = plan
             ctx.dims = [int(t.shape[1]) for t in cat_tabs]
             ctx.rows = rows
             ctx.tables = [*cat_tabs, tgt_w, his_w]

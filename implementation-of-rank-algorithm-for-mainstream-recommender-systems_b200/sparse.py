@@ -47,6 +47,7 @@ def _i64_array(values):
 
 
 _plan_streams: dict = {}
+PLAN_STREAM_PRIORITY = int(os.environ.get("RANK_B200_PLAN_PRIORITY", "-1"))
 PLAN_ON_SIDE_STREAM = os.environ.get("RANK_B200_PLAN_STREAM", "1") != "0"
 
 
@@ -57,7 +58,24 @@ def _plan_stream(device):
     key = device.index if device.index is not None else torch.cuda.current_device()
     stream = _plan_streams.get(key)
     if stream is None:
-        stream = _plan_streams[key] = torch.cuda.Stream(device=device)
+        # high priority: the sort is short and something (the segment reduce) always ends up waiting for it, while
+        # the kernels it shares the GPU with (forward / backward of the hot path, the tower) are long
+        stream = _plan_streams[key] = torch.cuda.Stream(device=device, priority=PLAN_STREAM_PRIORITY)
+    return stream
+
+
+_direct_streams = {}
+
+
+def _direct_stream(device):
+    """Side stream of the one-launch direct reduction when a sorted reduction runs next to it (its own stream:
+    it depends on the backward kernel only, not on the plan)."""
+    if not PLAN_ON_SIDE_STREAM:
+        return None
+    key = device.index if device.index is not None else torch.cuda.current_device()
+    stream = _direct_streams.get(key)
+    if stream is None:
+        stream = _direct_streams[key] = torch.cuda.Stream(device=device)
     return stream
 
 
@@ -172,7 +190,8 @@ class OccurrencePlan:
 
     def __init__(self, indices: list[torch.Tensor], rows: list[int], seq_len=None, live_mode=None, direct=None):
         """`seq_len[f]` (int64 [B]) and `live_mode[f]` (_lib.LIVE_*) mark field f as a padded
-        sequence field whose dead positions are left out of the reduction."""
+        sequence field whose dead positions are left out of the reduction.  Create the plan BEFORE queueing
+        the forward kernel: its side stream waits for everything on the current stream at this point."""
         lib = _lib.load()
         self.F = len(indices)
         if not 1 <= self.F <= _lib.RK_MAX_FIELDS:
@@ -266,7 +285,6 @@ class OccurrencePlan:
         T = len(sources)
         if not 1 <= T <= _lib.RK_MAX_TABLES:
             raise ValueError(f"{T} gradient tables (max {_lib.RK_MAX_TABLES})")
-        self.join()
         dev = self.device
         for s in sources:
             if s.rows != self.rows[s.field]:
@@ -303,7 +321,7 @@ class OccurrencePlan:
                 tabs[k].dim = s.dim
             # the two reductions write disjoint parts of the slab: when both exist, the one-launch direct
             # reduction runs on the side stream next to the sorted one (forked and joined here)
-            side = _plan_stream(dev) if n_direct < T else None
+            side = _direct_stream(dev) if n_direct < T else None
             if side is None:
                 rc = lib.rk_embgrad_direct_reduce(tabs, n_direct, _lib.err_flag(dev).data_ptr(), _lib.stream_ptr())
             else:
@@ -317,6 +335,7 @@ class OccurrencePlan:
                               *[self.indices[sources[t].field] for t in order[:n_direct]]]:
                         t.record_stream(side)
             _lib.check(rc, "rk_embgrad_direct_reduce")
+        self.join()                 # only the sorted reduction needs the plan; the direct one is already queued
         if n_direct < T:
             S = T - n_direct
             tabs = (_lib.RkGradTable * S)()
