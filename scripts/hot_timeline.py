@@ -62,16 +62,10 @@ def main(workload="din_tc", full=False):
     end = max(e.time_range.end for e in run)
     print("%s %s: %d kernels, first start -> last end = %.1f us" % (workload, "step" if full else "hot path", len(run), end - t0))
     print("%9s %9s %8s  %-6s %s" % ("start us", "end us", "dur us", "stream", "kernel"))
-    last_end = {}
     for e in run:
         s, d = e.time_range.start - t0, e.time_range.elapsed_us()
-        stream = getattr(e, "device_index", 0)
-        try:
-            stream = e.device_resource_id
-        except AttributeError:
-            pass
+        stream = getattr(e, "device_resource_id", getattr(e, "device_index", 0))
         print("%9.1f %9.1f %8.1f  %-6s %s" % (s, s + d, d, stream, e.name[:90]))
-        last_end[stream] = s + d
 
 
 if __name__ == "__main__":
